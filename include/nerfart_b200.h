@@ -1,0 +1,170 @@
+/*
+ * nerfart_b200.h -- C ABI of libnerfart_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the volumetric-render hot path of cassiePython/NeRF-Art.  The reference has
+ * no FFI / plugin registry (it is 100 % Python): the "interface" this library replaces
+ * is the set of Python call sites listed beside each entry point (file:line in the reference tree).
+ * The reference-side binding a maintainer adds is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns every buffer,
+ *     including the workspace; nothing is allocated or freed inside the library
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation
+ *   - returns 0 on success, a negative NA_ERR_* code otherwise (no C++ exceptions cross the boundary)
+ *   - no global mutable state; calls on different streams / devices may run concurrently
+ *   - fp32 tensors, row-major, innermost dimension contiguous
+ */
+#ifndef NERFART_B200_H
+#define NERFART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NA_OK                 0
+#define NA_ERR_BAD_ARG       -1
+#define NA_ERR_WORKSPACE     -2   /* workspace too small */
+#define NA_ERR_CUDA          -3   /* a CUDA runtime call failed; see na_last_cuda_error() */
+#define NA_ERR_UNSUPPORTED   -4   /* shape / option outside what the kernels implement */
+
+#define NA_FRAMEWORK_VOLSDF   0
+#define NA_FRAMEWORK_NEUS     1
+
+/* MLP arithmetic mode (DESIGN.md "precision modes"):
+ *   FP32   : CUDA-core fp32 FFMA everywhere (bit-for-bit reproducible, tightest parity)
+ *   TC     : tcgen05 tensor cores; SDF net in 3-way bf16 split (fp32-equivalent products, fp32
+ *            accumulate in TMEM), radiance net in 2-way bf16 split                                  */
+#define NA_PRECISION_FP32     0
+#define NA_PRECISION_TC       1
+
+/* Network geometry.  Mirrors what models/frameworks/volsdf.py:943-975 / neus.py:693-731 build:
+ * SDF net  D=8, W=256, skip at layer 4, embed_multires=6 (39-d), W_geo_feat=256 (models/base.py:131-241)
+ * radiance D=4, W=256, embed_multires=-1, embed_multires_view=-1 (VolSDF) or 4 (NeuS)  (base.py:312-369).
+ * Other geometries return NA_ERR_UNSUPPORTED. */
+typedef struct NaNetDesc {
+    int32_t framework;          /* NA_FRAMEWORK_* */
+    int32_t multires_view;      /* -1 (identity, 3-d) or 4 (27-d) */
+    float   bounding_radius;    /* VolSDF sphere background radius (volsdf.py:341-357); unused for NeuS */
+    float   reserved;
+} NaNetDesc;
+
+/* Raw (un-folded) parameters in the reference checkpoint layout:
+ * for each layer: bias [out], weight_g [out,1], weight_v [out,in].  14 layers: 9 SDF then 5 radiance. */
+#define NA_NUM_SDF_LAYERS 9
+#define NA_NUM_RAD_LAYERS 5
+typedef struct NaRawParams {
+    const float* bias[NA_NUM_SDF_LAYERS + NA_NUM_RAD_LAYERS];
+    const float* weight_g[NA_NUM_SDF_LAYERS + NA_NUM_RAD_LAYERS];
+    const float* weight_v[NA_NUM_SDF_LAYERS + NA_NUM_RAD_LAYERS];
+} NaRawParams;
+
+typedef struct NaVolsdfCfg {              /* kwargs of volsdf.volume_render, volsdf.py:389-424 */
+    int32_t n_samples;                    /* N_samples (128)            */
+    int32_t n_importance;                 /* N_importance (64)          */
+    int32_t max_upsample_steps;           /* max_upsample_steps (YAML max_upsample_iter, 6) */
+    int32_t max_bisection_steps;          /* max_bisection_steps (10)   */
+    float   near, far;                    /* 0.0, 6.0                   */
+    float   epsilon;                      /* 0.1                        */
+    int32_t white_bkgd;                   /* 0/1                        */
+    int32_t perturb;                      /* 0: det linspace u; 1: u_final supplied by the caller */
+    int32_t precision;                    /* NA_PRECISION_*             */
+    int32_t detailed;                     /* 1: fill the per-sample NaVolsdfDetail arrays */
+    int32_t reserved;
+} NaVolsdfCfg;
+
+typedef struct NaVolsdfOut {              /* return values of volume_render, volsdf.py:566-594 */
+    float* rgb;                           /* [n_rays,3]  */
+    float* depth;                         /* [n_rays]    depth_volume */
+    float* acc;                           /* [n_rays]    mask_volume  */
+    float* normals;                       /* [n_rays,3]  normals_volume (may be NULL) */
+    float* beta_map;                      /* [n_rays]    */
+    float* iter_usage;                    /* [n_rays]    float like the reference: 0..max, -1 = not converged */
+    /* detailed_output (all may be NULL unless cfg.detailed); P = n_samples + n_importance */
+    float* d_vals;                        /* [n_rays,P]   */
+    float* sdf;                           /* [n_rays,P]   implicit_surface */
+    float* nablas;                        /* [n_rays,P,3] implicit_nablas  */
+    float* radiance;                      /* [n_rays,P,3] */
+    float* sigma;                         /* [n_rays,P]   */
+    float* tau;                           /* [n_rays,P-1] visibility_weights */
+} NaVolsdfOut;
+
+typedef struct NaNeusCfg {                /* kwargs of neus.volume_render, neus.py:142-185 ('official_solution') */
+    int32_t n_samples;                    /* 64 */
+    int32_t n_importance;                 /* 64 */
+    int32_t n_upsample_iters;             /* 4  */
+    float   bounding_radius;              /* obj_bounding_radius (1.0) */
+    int32_t white_bkgd;
+    int32_t perturb;                      /* 1: u supplied by caller [n_upsample_iters][n_rays][n_importance/iters] */
+    int32_t precision;
+    int32_t detailed;
+} NaNeusCfg;
+
+typedef struct NaNeusOut {                /* neus.py:385-407 */
+    float* rgb; float* depth; float* acc; float* normals;
+    float* d_all;                         /* [n_rays,P]   */
+    float* sdf;                           /* [n_rays,P]   */
+    float* nablas;                        /* [n_rays,P,3] */
+    float* radiance;                      /* [n_rays,P-1,3] */
+    float* alpha;                         /* [n_rays,P-1] */
+    float* weights;                       /* [n_rays,P-1] visibility_weights */
+} NaNeusOut;
+
+/* ---- capability / errors ------------------------------------------------------------------- */
+int         na_version(void);
+const char* na_error_string(int code);
+int         na_last_cuda_error(void);                 /* cudaError_t of the last NA_ERR_CUDA on this thread */
+int64_t     na_kernel_launch_count(void);             /* kernels launched by this library since load (bench "gpu_launches") */
+
+/* ---- weights: replaces nn.utils.weight_norm's per-forward W = g*v/||v|| (models/base.py:226-227,365-366) */
+size_t na_packed_weights_bytes(const NaNetDesc* desc);
+int    na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, void* packed, void* stream);
+
+/* ---- per-sample networks (stage-wise parity + ImplicitSurface / RadianceNet / mesh / ray-casting callers) */
+/* ImplicitSurface.forward (models/base.py:243-263): x [m,3] -> sdf [m], feat [m,256] (feat may be NULL).
+ * apply_bg!=0: VolSDF.forward_surface, min(sdf, R-||x||) (volsdf.py:341-347). */
+int na_sdf_eval(const NaNetDesc* desc, const void* packed, const float* x, int64_t m, int apply_bg,
+                int precision, float* sdf, float* feat, void* workspace, size_t ws_bytes, void* stream);
+/* VolSDF.forward / NeuS.forward (volsdf.py:359-370, neus.py:120-123): x,view [m,3] -> radiance [m,3], sdf [m], nablas [m,3]
+ * (ImplicitSurface.forward_with_nablas base.py:265-282 + RadianceNet.forward base.py:372-391). */
+int na_full_eval(const NaNetDesc* desc, const void* packed, const float* x, const float* view, int64_t m,
+                 int precision, float* radiance, float* sdf, float* nablas, float* feat,
+                 void* workspace, size_t ws_bytes, void* stream);
+size_t na_eval_workspace_bytes(int64_t m);
+
+/* ---- ray generation: rend_util.get_rays (utils/rend_util.py:112-165) with N_rays=-1 ------------ */
+int na_get_rays(const float* c2w /*[4,4]*/, const float* intrinsics /*[4,4]*/, int H, int W,
+                float* rays_o /*[H*W,3]*/, float* rays_d /*[H*W,3]*/, void* stream);
+
+/* ---- sampler stages (parity of rend_util.sample_pdf 256-293, sample_cdf 295-328, volsdf.error_bound 56-94) */
+int na_error_bound(const float* d_vals, const float* sdf, int64_t rows, int n, const float* alpha_beta_rows /*[rows,2] or NULL*/,
+                   float alpha, float beta, float* bounds /*[rows,n-1]*/, void* stream);
+int na_sample_pdf(const float* bins, const float* weights, int64_t rows, int n, const float* u /*[n_out] shared or [rows,n_out]*/,
+                  int u_per_row, int n_out, float* samples, int64_t* inds /*may be NULL*/, void* stream);
+int na_sample_cdf(const float* bins, const float* cdf, int64_t rows, int n, const float* u, int u_per_row, int n_out,
+                  float* samples, int64_t* inds, void* stream);
+
+/* ---- VolSDF renderer: volsdf.volume_render (volsdf.py:389-615) -------------------------------- */
+size_t na_volsdf_workspace_bytes(const NaVolsdfCfg* cfg, int64_t n_rays);
+/* rays_d un-normalised (normalised inside, volsdf.py:442).  alpha_beta: device [2] = VolSDF.forward_ab().
+ * t_coarse [n_samples], t_init [4*n_samples], u_up [4*n_samples+2], u_imp [n_importance]: the torch.linspace(0,1,.)
+ * tables the reference builds at volsdf.py:472,483 and rend_util.py:269,304 (passed in so both sides use identical
+ * values); u_final [n_rays,n_importance] only when cfg.perturb. */
+int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, const NaVolsdfCfg* cfg,
+                         const float* rays_o, const float* rays_d, int64_t n_rays, const float* alpha_beta,
+                         const float* t_coarse, const float* t_init, const float* u_up, const float* u_imp,
+                         const float* u_final, const NaVolsdfOut* out, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- NeuS renderer: neus.volume_render (neus.py:142-424) -------------------------------------- */
+size_t na_neus_workspace_bytes(const NaNeusCfg* cfg, int64_t n_rays);
+int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, const NaNeusCfg* cfg,
+                       const float* rays_o, const float* rays_d, int64_t n_rays, const float* s_dev /*[1] = NeuS.forward_s()*/,
+                       const float* t_coarse, const float* u_imp, const float* u_rand,
+                       const NaNeusOut* out, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,141 @@
+"""ctypes binding of libnerfart_b200.so (the C ABI in include/nerfart_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every tensor crosses the boundary as a raw
+device pointer.  There is NO fallback: if the shared library is missing or a call fails, a RuntimeError
+is raised.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnerfart_b200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'mlp_tc.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '--compiler-options', '-fPIC', '-shared']
+
+NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS = 0, 1
+NA_PRECISION_FP32, NA_PRECISION_TC = 0, 1
+PRECISIONS = {'fp32': NA_PRECISION_FP32, 'tc': NA_PRECISION_TC}
+
+
+class NaNetDesc(C.Structure):
+    _fields_ = [('framework', C.c_int32), ('multires_view', C.c_int32), ('bounding_radius', C.c_float), ('reserved', C.c_float)]
+
+
+class NaRawParams(C.Structure):
+    _fields_ = [('bias', C.c_void_p * 14), ('weight_g', C.c_void_p * 14), ('weight_v', C.c_void_p * 14)]
+
+
+class NaVolsdfCfg(C.Structure):
+    _fields_ = [('n_samples', C.c_int32), ('n_importance', C.c_int32), ('max_upsample_steps', C.c_int32),
+                ('max_bisection_steps', C.c_int32), ('near', C.c_float), ('far', C.c_float), ('epsilon', C.c_float),
+                ('white_bkgd', C.c_int32), ('perturb', C.c_int32), ('precision', C.c_int32), ('detailed', C.c_int32),
+                ('reserved', C.c_int32)]
+
+
+class NaVolsdfOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ('rgb', 'depth', 'acc', 'normals', 'beta_map', 'iter_usage',
+                                          'd_vals', 'sdf', 'nablas', 'radiance', 'sigma', 'tau')]
+
+
+class NaNeusCfg(C.Structure):
+    _fields_ = [('n_samples', C.c_int32), ('n_importance', C.c_int32), ('n_upsample_iters', C.c_int32),
+                ('bounding_radius', C.c_float), ('white_bkgd', C.c_int32), ('perturb', C.c_int32),
+                ('precision', C.c_int32), ('detailed', C.c_int32)]
+
+
+class NaNeusOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ('rgb', 'depth', 'acc', 'normals', 'd_all', 'sdf', 'nablas', 'radiance',
+                                          'alpha', 'weights')]
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libnerfart_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + \
+        [os.path.join(_HERE, '..', 'include', 'nerfart_b200.h')]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + srcs
+    if verbose:
+        print(' '.join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (never builds implicitly on a GPU box: the .so ships in-tree)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"`. '
+                               'nerfart_b200 has no CPU / PyTorch fallback.')
+        L = C.CDLL(LIB_PATH)
+        L.na_version.restype = C.c_int
+        L.na_error_string.restype = C.c_char_p
+        L.na_error_string.argtypes = [C.c_int]
+        L.na_last_cuda_error.restype = C.c_int
+        L.na_kernel_launch_count.restype = C.c_int64
+        L.na_packed_weights_bytes.restype = C.c_size_t
+        L.na_packed_weights_bytes.argtypes = [C.POINTER(NaNetDesc)]
+        L.na_pack_weights.argtypes = [C.POINTER(NaNetDesc), C.POINTER(NaRawParams), C.c_void_p, C.c_void_p]
+        L.na_eval_workspace_bytes.restype = C.c_size_t
+        L.na_eval_workspace_bytes.argtypes = [C.c_int64]
+        L.na_sdf_eval.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_full_eval.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_get_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.na_error_bound.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p]
+        for fn in (L.na_sample_pdf, L.na_sample_cdf):
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                           C.c_void_p, C.c_void_p]
+        L.na_volsdf_workspace_bytes.restype = C.c_size_t
+        L.na_volsdf_workspace_bytes.argtypes = [C.POINTER(NaVolsdfCfg), C.c_int64]
+        L.na_volsdf_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaVolsdfCfg), C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(NaVolsdfOut), C.c_void_p, C.c_size_t, C.c_void_p]
+        if hasattr(L, 'na_neus_render_fwd'):
+            L.na_neus_workspace_bytes.restype = C.c_size_t
+            L.na_neus_workspace_bytes.argtypes = [C.POINTER(NaNeusCfg), C.c_int64]
+            L.na_neus_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaNeusCfg), C.c_void_p, C.c_void_p,
+                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.POINTER(NaNeusOut), C.c_void_p, C.c_size_t, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        L = lib()
+        msg = L.na_error_string(code).decode()
+        if code == -3:
+            msg += f' [cudaError {L.na_last_cuda_error()}]'
+        raise RuntimeError(f'nerfart_b200: {what} failed: {msg}')
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (or NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('nerfart_b200 kernels need CUDA tensors (there is no CPU path)')
+    assert t.is_contiguous(), 'tensor must be contiguous'
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch_count():
+    return int(lib().na_kernel_launch_count())

@@ -1,0 +1,94 @@
+// Shared definitions for libnerfart_b200 (sm_100a).  See DESIGN.md for the data layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/nerfart_b200.h"
+
+namespace na {
+
+// ---------------------------------------------------------------------------------------------
+// launch accounting / error plumbing
+// ---------------------------------------------------------------------------------------------
+extern thread_local int g_last_cuda_error;
+void count_launch(int n = 1);
+inline int check_cuda(cudaError_t e) {
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return NA_ERR_CUDA; }
+    return NA_OK;
+}
+#define NA_CHECK_LAUNCH()                                                     \
+    do { na::count_launch();                                                  \
+         cudaError_t _e = cudaGetLastError();                                 \
+         if (_e != cudaSuccess) { na::g_last_cuda_error = (int)_e; return NA_ERR_CUDA; } } while (0)
+#define NA_TRY(x) do { int _r = (x); if (_r != NA_OK) return _r; } while (0)
+
+int num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// network geometry (fixed; NaNetDesc documents where it comes from)
+// ---------------------------------------------------------------------------------------------
+constexpr int W = 256;              // hidden width
+constexpr int EMB = 39;             // 3 + 3*2*6
+constexpr int EMB_PAD = 40;
+constexpr int SKIP_H = 217;         // 256 - 39: width of layer 3 (models/base.py:186-187)
+constexpr int N_SDF_HID = 8;
+
+__host__ __device__ inline int small_dim(int multires_view) {       // x(3) + view + nabla(3)
+    return 3 + (multires_view < 0 ? 3 : 3 + 6 * multires_view) + 3;
+}
+__host__ __device__ inline int small_pad(int multires_view) { return (small_dim(multires_view) + 7) / 8 * 8; }
+
+// Packed fp32 weights ("SIMT pack"): offsets in floats from the start of the packed buffer.
+struct PackF32 {
+    size_t sdf_wt[N_SDF_HID];       // forward  B[r=in][c=out]  [Kp][256]   (layer 4 pre-scaled by 1/sqrt2)
+    size_t sdf_w[N_SDF_HID];        // backward B[r=out][c=in]  [256][256]  (zero padded)
+    size_t sdf_b[N_SDF_HID];        // [256]
+    size_t w8_sdf;                  // [256]  row 0 of layer 8
+    size_t b8_sdf;                  // [4]
+    size_t w8t_feat;                // [256][256]  rows 1..256 of layer 8, transposed
+    size_t b8_feat;                 // [256]
+    size_t rad_wt[4];               // layer 0: [256+small_pad][256] (feat rows first, then x|view|nabla), 1..3: [256][256]
+    size_t rad_b[4];                // [256]
+    size_t rad_w4;                  // [3][256]
+    size_t rad_b4;                  // [4]
+    size_t total;                   // floats
+};
+__host__ inline PackF32 pack_layout_f32(int multires_view) {
+    PackF32 L; size_t o = 0;
+    for (int i = 0; i < N_SDF_HID; ++i) { L.sdf_wt[i] = o; o += (size_t)(i == 0 ? EMB_PAD : W) * W; }
+    for (int i = 0; i < N_SDF_HID; ++i) { L.sdf_w[i] = o; o += (size_t)W * W; }
+    for (int i = 0; i < N_SDF_HID; ++i) { L.sdf_b[i] = o; o += W; }
+    L.w8_sdf = o; o += W;  L.b8_sdf = o; o += 4;
+    L.w8t_feat = o; o += (size_t)W * W;  L.b8_feat = o; o += W;
+    L.rad_wt[0] = o; o += (size_t)(W + small_pad(multires_view)) * W;
+    for (int i = 1; i < 4; ++i) { L.rad_wt[i] = o; o += (size_t)W * W; }
+    for (int i = 0; i < 4; ++i) { L.rad_b[i] = o; o += W; }
+    L.rad_w4 = o; o += 3 * W;  L.rad_b4 = o; o += 4;
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// where the points of one MLP launch come from, and where results go
+// ---------------------------------------------------------------------------------------------
+struct EvalJob {
+    // explicit points (na_sdf_eval / na_full_eval): x != nullptr, m points
+    const float* x;  const float* view;  long long m;
+    // ray points: point(row, j) = o[ray] + d[ray] * t[ray*t_stride + t_off + j], ray = row_ids ? row_ids[row] : row
+    const float* rays_o;  const float* rays_d;      // [n_rays,3], d normalised
+    const int*   row_ids;                            // nullable
+    const int*   n_rows_dev;                         // nullable: row count lives on the device
+    int          n_rows;                             // host row count (upper bound when n_rows_dev != nullptr)
+    int          P;                                  // points per row
+    const float* t;  long long t_stride;  int t_off;
+    int          midpoints;                          // 1: t_j := 0.5*(t[j]+t[j+1])   (NeuS pts_mid, neus.py:312)
+    // outputs.  index = explicit ? w : ray*o_stride + o_off + j
+    long long o_stride;  int o_off;
+    float* sdf;  float* feat;  float* rad;  float* nab;
+    // behaviour
+    int   apply_bg;  float bound_r;                  // VolSDF sphere background
+    int   want_full;                                 // 0: SDF only; 1: + nablas (+ radiance if rad != nullptr)
+    int   multires_view;
+};
+
+}  // namespace na

@@ -1,0 +1,186 @@
+"""Host-side engine: owns the packed weights + workspace of one model and issues the C-ABI calls.
+
+Everything here is pointer plumbing around `libnerfart_b200.so`; tensors are allocated with torch so that the
+caching allocator and the current stream are shared with the caller (train.py / render.py of the reference).
+"""
+import ctypes as C
+import torch
+
+from . import _lib
+from ._lib import (NaNetDesc, NaRawParams, NaVolsdfCfg, NaVolsdfOut, NaNeusCfg, NaNeusOut, check, ptr, stream_ptr,
+                   NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS, PRECISIONS)
+
+_LINSPACE_CACHE = {}
+
+
+def cpu_linspace(n, device):
+    """torch.linspace(0, 1, n) evaluated on the CPU (the reference's oracle side) and shipped to `device` once.
+    The reference builds these tables at volsdf.py:472,483 / rend_util.py:269,304 / neus.py:235."""
+    key = (int(n), str(device))
+    t = _LINSPACE_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, int(n), dtype=torch.float32).to(device)
+        _LINSPACE_CACHE[key] = t
+    return t
+
+
+class NetEngine:
+    def __init__(self, implicit_surface, radiance_net, framework, multires_view, bounding_radius):
+        self.surface, self.radiance = implicit_surface, radiance_net
+        self.framework = framework
+        self.desc = NaNetDesc(NA_FRAMEWORK_VOLSDF if framework == 'volsdf' else NA_FRAMEWORK_NEUS,
+                              int(multires_view), float(bounding_radius), 0.0)
+        self.packed = None
+        self._ws = None
+        self._dummy = None
+        self.precision = 'fp32'
+
+    # ------------------------------------------------------------------------------------------
+    def _device(self):
+        return self.surface.surface_fc_layers[0].weight_v.device
+
+    def _raw_params(self):
+        dev = self._device()
+        if dev.type != 'cuda':
+            raise RuntimeError('nerfart_b200: the model must live on a CUDA device (no CPU path exists)')
+        raw = NaRawParams()
+        keep = []
+        layers = list(self.surface.surface_fc_layers)
+        if self.radiance is not None:
+            layers += list(self.radiance.layers)
+        else:                                           # stand-alone ImplicitSurface: zero radiance net of the right shapes
+            if self._dummy is None:
+                sd = 9 if self.desc.multires_view < 0 else 33
+                shapes = [(256, 256 + sd), (256, 256), (256, 256), (256, 256), (3, 256)]
+                self._dummy = [(torch.zeros(o, device=dev), torch.ones(o, 1, device=dev), torch.ones(o, i, device=dev))
+                               for o, i in shapes]
+            layers += self._dummy
+        assert len(layers) == 14
+        for i, l in enumerate(layers):
+            b, g, v = (l.bias, l.weight_g, l.weight_v) if not isinstance(l, tuple) else l
+            for t in (b, g, v):
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError('parameters must be contiguous fp32')
+            raw.bias[i], raw.weight_g[i], raw.weight_v[i] = b.data_ptr(), g.data_ptr(), v.data_ptr()
+            keep += [b, g, v]
+        return raw, keep
+
+    def pack(self):
+        """Fold weight-norm etc. into the GEMM-ready planes.  Cheap (2 launches); called at the start of every render /
+        eval so that optimiser steps and load_state_dict are always reflected."""
+        L = _lib.lib()
+        dev = self._device()
+        nbytes = L.na_packed_weights_bytes(C.byref(self.desc))
+        if self.packed is None or self.packed.device != dev or self.packed.numel() * 4 < nbytes:
+            self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+        raw, keep = self._raw_params()
+        with torch.cuda.device(dev):
+            check(L.na_pack_weights(C.byref(self.desc), C.byref(raw), ptr(self.packed), stream_ptr(dev)), 'na_pack_weights')
+        return self.packed
+
+    def workspace(self, nbytes):
+        dev = self._device()
+        if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        return self._ws
+
+    # ------------------------------------------------------------------------------------------
+    def sdf_eval(self, x, apply_bg, want_feat=False):
+        L = _lib.lib()
+        shape = x.shape[:-1]
+        xf = x.detach().reshape(-1, 3).float().contiguous()
+        m = xf.shape[0]
+        dev = xf.device
+        sdf = torch.empty(m, device=dev, dtype=torch.float32)
+        feat = torch.empty(m, 256, device=dev, dtype=torch.float32) if want_feat else None
+        self.pack()
+        ws = self.workspace(L.na_eval_workspace_bytes(m))
+        with torch.cuda.device(dev):
+            check(L.na_sdf_eval(C.byref(self.desc), ptr(self.packed), ptr(xf), m, int(bool(apply_bg)), PRECISIONS[self.precision],
+                                ptr(sdf), ptr(feat), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_sdf_eval')
+        return sdf.reshape(shape), (feat.reshape(*shape, 256) if want_feat else None)
+
+    def full_eval(self, x, view_dirs, want_radiance=True, apply_bg=None):
+        L = _lib.lib()
+        shape = x.shape[:-1]
+        xf = x.detach().reshape(-1, 3).float().contiguous()
+        m = xf.shape[0]
+        dev = xf.device
+        vf = view_dirs.detach().reshape(-1, 3).float().contiguous() if view_dirs is not None else None
+        rad = torch.empty(m, 3, device=dev, dtype=torch.float32) if want_radiance else None
+        sdf = torch.empty(m, device=dev, dtype=torch.float32)
+        nab = torch.empty(m, 3, device=dev, dtype=torch.float32)
+        feat = torch.empty(m, 256, device=dev, dtype=torch.float32)
+        self.pack()
+        ws = self.workspace(L.na_eval_workspace_bytes(m))
+        desc = self.desc
+        if apply_bg is not None and bool(apply_bg) != (desc.framework == NA_FRAMEWORK_VOLSDF):
+            desc = NaNetDesc(NA_FRAMEWORK_VOLSDF if apply_bg else NA_FRAMEWORK_NEUS, desc.multires_view, desc.bounding_radius, 0.0)
+        with torch.cuda.device(dev):
+            check(L.na_full_eval(C.byref(desc), ptr(self.packed), ptr(xf), ptr(vf), m, PRECISIONS[self.precision],
+                                 ptr(rad), ptr(sdf), ptr(nab), ptr(feat), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_full_eval')
+        return (rad.reshape(*shape, 3) if want_radiance else None), sdf.reshape(shape), nab.reshape(*shape, 3), feat.reshape(*shape, 256)
+
+    # ------------------------------------------------------------------------------------------
+    def volsdf_render(self, rays_o, rays_d, alpha_beta, *, near, far, N_samples, N_importance, max_upsample_steps,
+                      max_bisection_steps, epsilon, white_bkgd, perturb, calc_normal, detailed_output, u_final=None):
+        """rays [N,3] (un-normalised directions) -> dict of flat outputs.  volsdf.volume_render, volsdf.py:389-615."""
+        L = _lib.lib()
+        dev = rays_o.device
+        n = rays_o.shape[0]
+        P = N_samples + N_importance
+        cfg = NaVolsdfCfg(int(N_samples), int(N_importance), int(max_upsample_steps), int(max_bisection_steps), float(near),
+                          float(far), float(epsilon), int(bool(white_bkgd)), int(bool(perturb)), PRECISIONS[self.precision],
+                          int(bool(detailed_output)), 0)
+        f32 = dict(device=dev, dtype=torch.float32)
+        o = dict(rgb=torch.empty(n, 3, **f32), depth=torch.empty(n, **f32), acc=torch.empty(n, **f32),
+                 normals=torch.empty(n, 3, **f32) if calc_normal else None,
+                 beta_map=torch.empty(n, **f32), iter_usage=torch.empty(n, **f32))
+        if detailed_output:
+            o.update(d_vals=torch.empty(n, P, **f32), sdf=torch.empty(n, P, **f32), nablas=torch.empty(n, P, 3, **f32),
+                     radiance=torch.empty(n, P, 3, **f32), sigma=torch.empty(n, P, **f32), tau=torch.empty(n, P - 1, **f32))
+        out = NaVolsdfOut(*[ptr(o.get(k)) for k in ('rgb', 'depth', 'acc', 'normals', 'beta_map', 'iter_usage',
+                                                     'd_vals', 'sdf', 'nablas', 'radiance', 'sigma', 'tau')])
+        if perturb and u_final is None:
+            u_final = torch.rand(n, N_importance, **f32)           # rend_util.py:307 draws these with torch.rand
+        self.pack()
+        ws = self.workspace(L.na_volsdf_workspace_bytes(C.byref(cfg), n))
+        tc, ti = cpu_linspace(N_samples, dev), cpu_linspace(4 * N_samples, dev)
+        uu, ui = cpu_linspace(4 * N_samples + 2, dev), cpu_linspace(N_importance, dev)
+        with torch.cuda.device(dev):
+            check(L.na_volsdf_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
+                                         ptr(alpha_beta), ptr(tc), ptr(ti), ptr(uu), ptr(ui),
+                                         ptr(u_final.contiguous()) if u_final is not None else None,
+                                         C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_volsdf_render_fwd')
+        return o
+
+    def neus_render(self, rays_o, rays_d, s_dev, *, obj_bounding_radius, N_samples, N_importance, N_upsample_iters,
+                    white_bkgd, perturb, detailed_output, u_rand=None):
+        """neus.volume_render ('official_solution', N_outside=0), neus.py:142-424."""
+        L = _lib.lib()
+        dev = rays_o.device
+        n = rays_o.shape[0]
+        P = N_samples + N_importance
+        cfg = NaNeusCfg(int(N_samples), int(N_importance), int(N_upsample_iters), float(obj_bounding_radius),
+                        int(bool(white_bkgd)), int(bool(perturb)), PRECISIONS[self.precision], int(bool(detailed_output)))
+        f32 = dict(device=dev, dtype=torch.float32)
+        o = dict(rgb=torch.empty(n, 3, **f32), depth=torch.empty(n, **f32), acc=torch.empty(n, **f32),
+                 normals=torch.empty(n, 3, **f32))
+        if detailed_output:
+            o.update(d_all=torch.empty(n, P, **f32), sdf=torch.empty(n, P, **f32), nablas=torch.empty(n, P, 3, **f32),
+                     radiance=torch.empty(n, P - 1, 3, **f32), alpha=torch.empty(n, P - 1, **f32),
+                     weights=torch.empty(n, P - 1, **f32))
+        out = NaNeusOut(*[ptr(o.get(k)) for k in ('rgb', 'depth', 'acc', 'normals', 'd_all', 'sdf', 'nablas', 'radiance',
+                                                   'alpha', 'weights')])
+        n_new = N_importance // N_upsample_iters
+        if perturb and u_rand is None:
+            u_rand = torch.rand(N_upsample_iters, n, n_new, **f32)
+        self.pack()
+        ws = self.workspace(L.na_neus_workspace_bytes(C.byref(cfg), n))
+        tc, ui = cpu_linspace(N_samples, dev), cpu_linspace(n_new, dev)
+        with torch.cuda.device(dev):
+            check(L.na_neus_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
+                                       ptr(s_dev), ptr(tc), ptr(ui), ptr(u_rand.contiguous()) if u_rand is not None else None,
+                                       C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_neus_render_fwd')
+        return o
