@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- MLP samples/sec on the synthetic VolSDF 480x270x128 render (BASELINE.json configs[1]).
+
+One "step" = one full-frame render of 129 600 rays through the hot path (hierarchical error-bound sampler with 512
+SDF-only network evaluations per ray, 192 full evaluations (sdf + d sdf/dx + radiance) per ray, sdf->sigma, front-to-back
+compositing).  metric value = n_rays * 192 / t  (SURVEY.md 8d "full-MLP samples/s").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|tc]
+Multi-GPU: launched by torchrun, one rank per GPU; the rays of ONE frame are block-partitioned over the ranks (strong
+scaling) and the rendered RGB tiles are all-gathered over NCCL at the end of every step (north star).
+`--impl reference` times the CPU oracle port (oracle/nerfart_oracle.py; the reference is Python and cannot travel to
+the GPU box) on the host cores, on a bounded ray sample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+H, W = 480, 270
+N_SAMPLES, N_IMPORTANCE = 128, 64
+P = N_SAMPLES + N_IMPORTANCE
+# matmul MACs x 2.  SDF-only evaluations skip the unused 256-wide feature head (918 016 instead of 1 049 088).
+F_SDF = 2 * (39 * 256 + 256 * 256 * 2 + 256 * 217 + 256 * 256 * 4 + 256)
+F_FULL = 2 * (524544 + 459008 + 265216)
+RENDER_KW = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=False, white_bkgd=False,
+                 max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, epsilon=0.1, max_bisection_steps=10,
+                 require_nablas=True, calc_normal=True, detailed_output=False)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_inputs():
+    import fixtures as fx
+    c2w, K = fx.closed_form_camera(H, W)
+    return c2w, K
+
+
+def cpu_baseline(n_rays_sample, repeats=1):
+    """The oracle port on the host cores, on a strided ray sample of the same frame.  Returns (samples/s, seconds)."""
+    import nerfart_oracle as orc
+    from helpers import make_volsdf, oracle_net
+    torch.set_num_threads(os.cpu_count())
+    net = oracle_net(make_volsdf(0.1, 0.0), 'volsdf')
+    c2w, K = make_inputs()
+    ro, rd = orc.get_rays(c2w.numpy(), K.numpy(), H, W)
+    sel = np.linspace(0, H * W - 1, n_rays_sample).astype(np.int64)
+    best = None
+    for _ in range(repeats):
+        t0 = time.time()
+        orc.volsdf_render(net, ro[sel], rd[sel], N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, rayschunk=2048)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    return n_rays_sample * P / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_sample = 256
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_baseline(n_sample)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.sum(times))
+    value = n_sample * P * args.steps / t
+    line = {'impl': 'reference', 'metric': 'MLP samples/sec (VolSDF 480x270x128)', 'value': value, 'unit': 'samples/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, extra={'sample': f'{n_sample} of {H*W} rays (strided), same 128+64 samples/ray'}),
+            'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': f'{n_sample} strided rays of the 480x270 frame per step, numpy+BLAS fp32 oracle port of the reference'},
+            'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, extra=None):
+    c = {'workload': f'VolSDF fangzhou_nature-shaped synthetic render {H}x{W} ({H*W} rays), N_samples={N_SAMPLES}, N_importance={N_IMPORTANCE}, '
+                     'd_init=512, seed-0 sphere init beta=0.1, radiance gains x3, closed-form camera',
+         'evals_per_ray': {'sdf_only': 4 * N_SAMPLES, 'full': P},
+         'parallelism': f'ray-partition x{args.gpus}' + (' + NCCL all-gather of RGB tiles' if args.gpus > 1 else ''),
+         'precision_mode': args.precision,
+         'l2': 'per-step working set (3.7 GB per-ray depth/sdf arrays + 0.9 GB per-sample outputs) >> 126 MB L2; no explicit flush'}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('NA_PRECISION', 'auto'))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (nerfart_b200 has no CPU path); use --impl reference for the CPU arm')
+    import nerfart_b200
+    from helpers import make_volsdf
+    from nerfart_b200.models.frameworks.volsdf import volume_render
+    from nerfart_b200.utils import rend_util
+    import torch.distributed as dist
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if args.precision == 'auto':
+        args.precision = nerfart_b200.default_precision() if hasattr(nerfart_b200, 'default_precision') else 'fp32'
+    model = make_volsdf(0.1, 0.0, device=dev)
+    model.engine().precision = args.precision
+    c2w_h, K_h = make_inputs()
+    c2w_pin, K_pin = c2w_h[None].pin_memory(), K_h[None].pin_memory()
+    n_rays = H * W
+    per = (n_rays + world - 1) // world
+    lo, hi = min(rank * per, n_rays), min((rank + 1) * per, n_rays)
+    rgb_host = torch.empty(n_rays, 3, dtype=torch.float32).pin_memory()
+    gathered = torch.empty(world * per, 3, device=dev)
+
+    def step(e2e):
+        with torch.no_grad():
+            if e2e:
+                c2w, K = c2w_pin.to(dev, non_blocking=True), K_pin.to(dev, non_blocking=True)
+                ro, rd, _ = rend_util.get_rays(c2w, K, H, W)
+                step.rays = (ro, rd)
+            ro, rd = step.rays
+            rgb, depth, ex = volume_render(ro[:, lo:hi], rd[:, lo:hi], model, **RENDER_KW)
+            if world > 1:
+                tile = torch.zeros(per, 3, device=dev); tile[:hi - lo] = rgb[0]
+                dist.all_gather_into_tensor(gathered, tile)
+                img = gathered[:n_rays]
+            else:
+                img = rgb[0]
+            if e2e:
+                rgb_host.copy_(img, non_blocking=True)
+        return img
+
+    def timed(e2e, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            a.record(); step(e2e); b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) * 1e-3
+
+    step(True)                                     # builds rays once, sizes the workspace
+    for _ in range(args.warmup):
+        step(False)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = nerfart_b200.launch_count()
+    t_dev = timed(False, args.steps)
+    launches = nerfart_b200.launch_count() - l0
+    t_e2e = timed(True, args.steps) if os.environ.get('NA_BENCH_LIGHT') != '1' else float('nan')
+    clk = clocks.stop() if rank == 0 else None
+    img = step(False)
+    torch.cuda.synchronize()
+
+    # ---- roofline of the dominant kernel (the fused MLP kernel, SDF-only mode: 512 of the 704 evaluations per ray) --------
+    roof = None
+    light = os.environ.get('NA_BENCH_LIGHT') == '1'          # profiling runs: skip the isolated-kernel and e2e sections
+    if rank == 0 and not light:
+        pk, pk_kind = peaks()
+        m = 8 * 1024 * 1024                                            # 8 Mi points per launch (6.3 % of one frame's sampler work)
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        x = (torch.rand(m, 3, device=dev, generator=g) * 4 - 2)
+        eng = model.engine()
+        for _ in range(2):
+            eng.sdf_eval(x, apply_bg=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            eng.sdf_eval(x, apply_bg=True)
+        e1.record(); torch.cuda.synchronize()
+        t_k = e0.elapsed_time(e1) * 1e-3 / reps
+        v = torch.nn.functional.normalize(torch.randn(m // 4, 3, device=dev, generator=g), dim=-1)
+        eng.full_eval(x[:m // 4], v)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            eng.full_eval(x[:m // 4], v)
+        e1.record(); torch.cuda.synchronize()
+        t_f = e0.elapsed_time(e1) * 1e-3 / reps
+        ach = m * F_SDF / t_k / 1e12
+        peak = pk['bf16_tflops']
+        roof = {'bound': 'tensor', 'kernel': 'mlp kernel, SDF-only mode', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': ach / peak, 'traffic': None, 'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
+                'flop_per_sample': F_SDF, 'samples_per_launch': m, 'launch_ms': t_k * 1e3,
+                'full_mode': {'achieved': (m // 4) * F_FULL / t_f / 1e12, 'flop_per_sample': F_FULL, 'launch_ms': t_f * 1e3,
+                              'frac': (m // 4) * F_FULL / t_f / 1e12 / peak},
+                'frame_flop': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL),
+                'frame_frac_of_peak': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL) / (t_dev / args.steps) / 1e12 / peak / world}
+        del x, v
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import nerfart_oracle as orc
+        from helpers import oracle_net
+        n_cpu = 512
+        v, dt = cpu_baseline(n_cpu)
+        cpu = {'value': v, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': f'{n_cpu} strided rays of the same frame ({dt:.1f} s), numpy+BLAS fp32 oracle port of the reference'}
+        # parity spot check of the rendered frame on the same sample (reported, not timed)
+        sel = np.linspace(0, n_rays - 1, n_cpu).astype(np.int64)
+        ro, rd = orc.get_rays(c2w_h.numpy(), K_h.numpy(), H, W)
+        ref = orc.volsdf_render(oracle_net(model, 'volsdf'), ro[sel], rd[sel], N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
+        cpu['rgb_linf_vs_oracle'] = float(np.abs(img[torch.as_tensor(sel, device=dev)].cpu().numpy() - ref['rgb']).max())
+    if rank == 0:
+        samples = n_rays * P * args.steps
+        line = {'metric': 'MLP samples/sec (VolSDF 480x270x128)', 'value': samples / t_dev, 'unit': 'samples/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16x3-split (fp32-equivalent) / f32 accumulate',
+                'data': 'synthetic', 'config': workload_config(args),
+                'all_evals_per_s': n_rays * (4 * N_SAMPLES + P) * args.steps / t_dev,
+                'e2e': {'value': samples / t_e2e, 'unit': 'samples/s', 'ms_per_step': 1e3 * t_e2e / args.steps,
+                        'h2d_bytes_per_step': 2 * 16 * 4, 'd2h_bytes_per_step': n_rays * 3 * 4},
+                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

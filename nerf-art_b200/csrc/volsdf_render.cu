@@ -21,6 +21,12 @@ __global__ void normalize_dirs_kernel(const float* __restrict__ d_in, float* __r
     d_out[i * 3] = __fdiv_rn(x, nrm); d_out[i * 3 + 1] = __fdiv_rn(y, nrm); d_out[i * 3 + 2] = __fdiv_rn(z, nrm);
 }
 
+int launch_normalize_dirs(const float* d_in, float* d_out, long long n, cudaStream_t stream) {
+    normalize_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_in, d_out, n);
+    NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
 __global__ void init_depths_kernel(float* __restrict__ T, long long cap, int n0, const float* __restrict__ t_init,
                                    float near, float far, long long n_rays) {
     // d_init = nears*(1-t) + fars*t  (volsdf.py:483-484), each op rounded like the tensor expression
@@ -312,8 +318,7 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
     const PackF32 L = pack_layout_f32(desc->multires_view);
     const float* pk = (const float*)packed;
 
-    normalize_dirs_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, stream>>>(rays_d, dirs, n_rays);
-    NA_CHECK_LAUNCH();
+    NA_TRY(launch_normalize_dirs(rays_d, dirs, n_rays, stream));
 
     int cap_pad = (int)cap, up_pad = 1; while (up_pad < n_up) up_pad <<= 1;
     int ppad = 1; while (ppad < P) ppad <<= 1;

@@ -17,9 +17,46 @@ float32 inputs in float64 (`at::acc_type<float, /*is_cuda=*/false>` = double) an
 prefix back to float32.
 """
 from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
+import os
 import numpy as np
 
 F32 = np.float32
+
+# Row-parallel evaluation of the per-sample networks: numpy's elementwise kernels are single threaded, the reference's
+# torch CPU kernels are not.  Splitting the rows over a thread pool (numpy releases the GIL inside ufuncs and BLAS) lets the
+# oracle use every host core when it is timed as the CPU baseline; results do not depend on the split (row-wise functions).
+_POOL = None
+_CHUNK = 8192
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1))
+    return _POOL
+
+
+def _rowwise(fn, *arrays):
+    m = arrays[0].shape[0]
+    if m <= _CHUNK:
+        return fn(*arrays)
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:                                   # pragma: no cover
+        threadpool_limits = None
+    cuts = list(range(0, m, _CHUNK))
+
+    def run(c0):
+        return fn(*[a[c0:c0 + _CHUNK] for a in arrays])
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=1, user_api='blas'):
+            parts = list(_pool().map(run, cuts))
+    else:
+        parts = list(_pool().map(run, cuts))
+    if isinstance(parts[0], tuple):
+        return tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(len(parts[0])))
+    return np.concatenate(parts, axis=0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -144,6 +181,10 @@ class Net:
 
 
 def sdf_net(net, x, with_nablas=False):
+    return _rowwise(lambda xx: _sdf_net(net, xx, with_nablas), x)
+
+
+def _sdf_net(net, x, with_nablas=False):
     """ImplicitSurface.forward (models/base.py:243-263) and forward_with_nablas (265-282).
     The gradient is the closed-form reverse sweep autograd performs.
     x [M,3] -> sdf [M], feat [M,256] (, nabla [M,3])."""
@@ -185,6 +226,10 @@ def sdf_net(net, x, with_nablas=False):
 
 
 def radiance_net(net, x, view_dirs, nablas, feat):
+    return _rowwise(lambda a, b, c, d: _radiance_net(net, a, b, c, d), x, view_dirs, nablas, feat)
+
+
+def _radiance_net(net, x, view_dirs, nablas, feat):
     """RadianceNet.forward, models/base.py:372-391: cat[x, embed_view(v), nablas, feat] -> 4x(Linear,ReLU)
     -> Linear,Sigmoid."""
     h = np.concatenate([embed(x, -1), embed(view_dirs, net.multires_view), nablas, feat], axis=-1).astype(F32)

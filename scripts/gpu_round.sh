@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU-box session: sanity, sanitizer, parity tests, bench, ncu.  Everything lands in gpurun_out/.
+# usage: scripts/gpu_round.sh [tag] [steps...]   (steps default: all)
+set -u
+TAG=${1:-r1}; shift || true
+STEPS=${*:-"info sanitize tests smoke bench launches ncu"}
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+for s in $STEPS; do
+  echo "=== $s ($(date +%T))"
+  case $s in
+    info) nvidia-smi > $OUT/nvidia_smi.txt 2>&1; nproc > $OUT/nproc.txt; python -c "import torch;print(torch.cuda.get_device_name(0))" ;;
+    sanitize) timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > $OUT/sanitize.log 2>&1; echo "sanitize exit $?"; tail -5 $OUT/sanitize.log ;;
+    tests) timeout 1500 python -m pytest tests -m gpu -x -q -s > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -25 $OUT/pytest_gpu.log ;;
+    smoke) timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 ;;
+    bench) timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; tail -c 600 $OUT/bench_ref.json ;;
+    launches) NA_BENCH_LIGHT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1; echo "ncu launches exit $?"; tail -3 $OUT/launches.csv ;;
+    ncu) NA_BENCH_LIGHT=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_ -s 4 -c 2 -f -o $OUT/prof_mlp python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "ncu full exit $?"; ls -la $OUT/ ;;
+    *) echo "unknown step $s" ;;
+  esac
+done
+echo "=== done ($(date +%T))"

@@ -1,0 +1,178 @@
+"""-m gpu: the CUDA path (through the C ABI / the Python mirror of the reference API) against the oracle and the
+reference-generated golden vectors.  Tolerances are stated per test; integer outputs (searchsorted indices) are bit-exact."""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, make_volsdf, make_neus, oracle_net, linf, orc, fx
+from test_oracle_golden import compare_volsdf, VOLSDF_CASES
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+S = golden('stages')
+
+
+def T(a):
+    return torch.tensor(np.ascontiguousarray(a), device=DEV)
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from nerfart_b200 import _lib
+    return _lib.lib()
+
+
+def test_library_is_native(lib):
+    assert lib.na_version() >= 100
+    import nerfart_b200
+    assert nerfart_b200.launch_count() >= 0
+
+
+@pytest.mark.parametrize('tag', ['v', 'n'])
+def test_networks_vs_reference_golden(tag):
+    """fp32 CUDA-core MLP vs the reference's own outputs.  Tolerance: 3e-5 abs on sdf/feature/radiance (fp32 summation
+    order), 3e-4 on nablas (products of 8 layer Jacobians)."""
+    m = make_volsdf(0.01, 0.5, device=DEV) if tag == 'v' else make_neus(0.05, 0.5, device=DEV)
+    x, v = T(S[f'net_{tag}_x']), T(S[f'net_{tag}_v'])
+    with torch.no_grad():
+        sdf, feat = m.implicit_surface.forward(x, return_h=True)
+        sdf2, nab, feat2 = m.implicit_surface.forward_with_nablas(x)
+        rad, sdf3, nab3 = m.forward(x, v)
+    assert linf(sdf.cpu(), S[f'net_{tag}_sdf']) < 3e-5
+    assert linf(feat.cpu(), S[f'net_{tag}_feat']) < 6e-5
+    assert linf(nab.cpu(), S[f'net_{tag}_nabla']) < 3e-4
+    assert torch.equal(sdf, sdf2) and torch.equal(feat, feat2) and torch.equal(nab, nab3)
+    if tag == 'v':
+        assert linf(rad.cpu(), S['net_v_fwd_rad']) < 6e-5
+        assert linf(sdf3.cpu(), S['net_v_fwd_sdf']) < 3e-5
+        assert linf(m.forward_surface(x)[0].cpu(), S['net_v_surface']) < 3e-5
+    else:
+        assert linf(rad.cpu(), S['net_n_rad']) < 6e-5
+        assert linf(sdf3.cpu(), S['net_n_sdf']) < 3e-5
+
+
+def test_network_ragged_and_empty_batches():
+    m = make_volsdf(0.01, 0.5, device=DEV)
+    x = T(S['net_v_x'])
+    with torch.no_grad():
+        full = m.implicit_surface.forward(x)
+        for n in (0, 1, 127, 128, 129, 300):
+            part = m.implicit_surface.forward(x[:n])
+            assert part.shape == (n,)
+            assert torch.equal(part, full[:n])                    # per-sample results do not depend on the tile they land in
+
+
+def test_error_bound_stage(lib):
+    from nerfart_b200._lib import ptr, check
+    d, sdf = T(S['eb_d']), T(S['eb_sdf'])
+    rows, n = d.shape
+    for i, (a, b) in enumerate([(10.0, 0.1), (100.0, 0.01), (500.0, 0.002)]):
+        out = torch.empty(rows, n - 1, device=DEV)
+        check(lib.na_error_bound(ptr(d), ptr(sdf), rows, n, None, a, b, ptr(out), None), 'na_error_bound')
+        ref = S[f'ebound_{i}']; got = out.cpu().numpy()
+        assert np.array_equal(np.isinf(ref), np.isinf(got))
+        fin = np.isfinite(ref)
+        np.testing.assert_allclose(got[fin], ref[fin], rtol=3e-4, atol=5e-7)
+    br = S['eb_beta_row']
+    ab = T(np.concatenate([1.0 / br, br], axis=1).astype(np.float32))
+    out = torch.empty(rows, n - 1, device=DEV)
+    check(lib.na_error_bound(ptr(d), ptr(sdf), rows, n, ptr(ab), 0.0, 0.0, ptr(out), None), 'na_error_bound')
+    ref = S['ebound_row']; got = out.cpu().numpy(); fin = np.isfinite(ref)
+    assert np.array_equal(np.isinf(ref), np.isinf(got))
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=3e-4, atol=5e-7)
+
+
+def test_sample_stages_indices_bit_exact(lib):
+    """sample_cdf / sample_pdf with injected identical inputs: searchsorted indices must be bit-exact, samples within 2e-6
+    (sample_cdf: no arithmetic before the search) / 2e-5 (sample_pdf: the cdf is built from fp32 divisions and a prefix sum)."""
+    from nerfart_b200._lib import ptr, check
+    d = T(S['eb_d']); rows, n = d.shape
+    cdf = T(S['scdf_cdf']); u_det = torch.linspace(0, 1, 16).to(DEV); u = T(S['samp_u'])
+    for (uu, per_row, ref_s) in ((u_det, 0, S['scdf_det']), (u, 1, S['scdf_rand'])):
+        out = torch.empty(rows, 16, device=DEV); inds = torch.empty(rows, 16, device=DEV, dtype=torch.int64)
+        check(lib.na_sample_cdf(ptr(d), ptr(cdf), rows, n, ptr(uu), per_row, 16, ptr(out), C.c_void_p(inds.data_ptr()), None), 'na_sample_cdf')
+        o_s, o_i = orc.sample_cdf(S['eb_d'], S['scdf_cdf'], 16, det=per_row == 0, u=S['samp_u'], return_inds=True)
+        assert np.array_equal(inds.cpu().numpy(), o_i)
+        assert linf(out.cpu(), ref_s) < 2e-6
+    w = T(S['spdf_w']); u50 = torch.linspace(0, 1, 50).to(DEV)
+    out = torch.empty(rows, 50, device=DEV); inds = torch.empty(rows, 50, device=DEV, dtype=torch.int64)
+    check(lib.na_sample_pdf(ptr(d), ptr(w), rows, n, ptr(u50), 0, 50, ptr(out), C.c_void_p(inds.data_ptr()), None), 'na_sample_pdf')
+    o_s, o_i = orc.sample_pdf(S['eb_d'], S['spdf_w'], 50, det=True, return_inds=True)
+    assert np.array_equal(inds.cpu().numpy()[:, :-1], o_i[:, :-1])      # u == 1.0 column: see oracle/sample_pdf note
+    assert linf(out.cpu().numpy()[:, :-1], S['spdf_det'][:, :-1]) < 2e-5
+
+
+def test_get_rays():
+    from nerfart_b200.utils import rend_util
+    for cam in ('closed', 'tilted'):
+        ro, rd, idx = rend_util.get_rays(T(S[f'rays_{cam}_c2w'])[None], T(S[f'rays_{cam}_K'])[None], 6, 5)
+        assert ro.shape == (1, 30, 3) and idx.shape == (1, 30)
+        assert linf(ro[0].cpu(), S[f'rays_{cam}_o']) == 0
+        assert linf(rd[0].cpu(), S[f'rays_{cam}_d']) < 1e-6
+
+
+def _render_volsdf(name, bump, **over):
+    from nerfart_b200.models.frameworks.volsdf import volume_render
+    G = golden(name)
+    beta_init, _, H, W, Ns, Ni = G['meta']
+    m = make_volsdf(float(beta_init), bump, device=DEV)
+    M = G['rays_o'].shape[0]
+    uf = T(np.broadcast_to(G['u0'], (M, int(Ni))).copy()) if 'u0' in G else None
+    kw = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=uf is not None, white_bkgd=False,
+              max_upsample_steps=6, N_samples=int(Ns), N_importance=int(Ni), epsilon=0.1, max_bisection_steps=10,
+              require_nablas=True, calc_normal=True, detailed_output='d_vals' in G, rayschunk=2048, u_final=uf)
+    kw.update(over)
+    with torch.no_grad():
+        rgb, depth, ex = volume_render(T(G['rays_o'])[None], T(G['rays_d'])[None], m, **kw)
+    return G, {k: v[0].cpu().numpy() for k, v in ex.items()}
+
+
+@pytest.mark.parametrize('name,bump', VOLSDF_CASES)
+def test_volsdf_render_vs_reference_golden(name, bump):
+    """End to end through the reference-shaped API.  Tolerances: see compare_volsdf (rgb median 3e-6 / q98 3e-3 on
+    path-consistent rays; every ray of the beta=0.1 BASELINE fixtures must be path-consistent)."""
+    G, out = _render_volsdf(name, bump)
+    same = compare_volsdf(out, G, name)
+    if G['meta'][0] >= 0.1:
+        assert same.all()
+        assert linf(out['rgb'], G['rgb']) < 1e-4
+    if 'd_vals' in G:
+        assert (np.diff(out['d_vals'], axis=-1) >= 0).all()                       # sortedness
+        for k in ('implicit_surface', 'radiance', 'implicit_nablas', 'sigma', 'visibility_weights', 'alpha', 'p_i'):
+            assert out[k].shape == G[k].shape, k
+
+
+def test_volsdf_render_is_deterministic_and_ray_independent():
+    """Size-independent properties: idempotence (bit-identical re-render) and ray independence (rendering a subset gives
+    the bits of the subset), which is what makes the multi-GPU ray partition exact."""
+    from nerfart_b200.models.frameworks.volsdf import volume_render
+    G = golden('volsdf_det_b0.01')
+    m = make_volsdf(0.01, 0.5, device=DEV)
+    ro, rd = T(G['rays_o']), T(G['rays_d'])
+    kw = dict(batched=False, near=0.0, far=6.0, perturb=False, max_upsample_steps=6, N_samples=32, N_importance=16,
+              require_nablas=True, calc_normal=True, detailed_output=False)
+    with torch.no_grad():
+        a = volume_render(ro, rd, m, **kw)[2]
+        b = volume_render(ro, rd, m, **kw)[2]
+        c = volume_render(ro[37:301], rd[37:301], m, **kw)[2]
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a[k][37:301], c[k]), k
+
+
+def test_volsdf_white_background_and_unbatched_layout():
+    from nerfart_b200.models.frameworks.volsdf import volume_render
+    G = golden('volsdf_det_b0.1')
+    m = make_volsdf(0.1, 0.5, device=DEV)
+    ro, rd = T(G['rays_o']), T(G['rays_d'])
+    kw = dict(near=0.0, far=6.0, perturb=False, max_upsample_steps=6, N_samples=32, N_importance=16, require_nablas=True,
+              calc_normal=True, detailed_output=False)
+    with torch.no_grad():
+        rgb0, _, ex0 = volume_render(ro, rd, m, batched=False, white_bkgd=False, **kw)
+        rgb1, _, ex1 = volume_render(ro, rd, m, batched=False, white_bkgd=True, **kw)
+        rgb2, d2, ex2 = volume_render(ro[None], rd[None], m, batched=True, white_bkgd=False, **kw)
+    assert rgb0.shape == (400, 3) and rgb2.shape == (1, 400, 3) and d2.shape == (1, 400)
+    assert torch.equal(rgb0, rgb2[0])
+    assert torch.allclose(rgb1, rgb0 + (1.0 - ex0['mask_volume'][..., None]), atol=1e-6)
+    assert set(ex0.keys()) == {'rgb', 'depth_volume', 'mask_volume', 'normals_volume'}
