@@ -24,6 +24,28 @@ int num_sms() {
 
 int launch_mlp_simt(const EvalJob& job, const float* packed, const PackF32& L, float* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t mlp_simt_scratch_bytes(int grid);
+struct TcPackLayout { size_t wtc_off, unscale_off, meta_off, total; unsigned stage0[21]; int n_kb[21], n_nh[21]; unsigned n_stages; };
+TcPackLayout tc_pack_layout(size_t f32_bytes);
+int tc_pack(const float* pk_f32, const PackF32& L, unsigned char* base, const TcPackLayout& T, cudaStream_t stream);
+int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
+                  size_t scratch_bytes, cudaStream_t stream);
+size_t mlp_tc_scratch_bytes(int grid);
+
+size_t packed_f32_bytes(int multires_view) {
+    const PackF32 L = pack_layout_f32(multires_view);
+    return ((L.total + 63) / 64 * 64 + 14 * 260 + 64) * sizeof(float);
+}
+// one entry point for both arithmetic modes
+int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    const PackF32 L = pack_layout_f32(job.multires_view);
+    if (precision == NA_PRECISION_FP32) return launch_mlp_simt(job, (const float*)packed, L, scratch, scratch_bytes, stream);
+    if (precision == NA_PRECISION_TC) return launch_mlp_tc(job, (const unsigned char*)packed, packed_f32_bytes(job.multires_view), L, scratch, scratch_bytes, stream);
+    return NA_ERR_UNSUPPORTED;
+}
+size_t mlp_scratch_bytes() {
+    const size_t a = mlp_simt_scratch_bytes(num_sms()), b = mlp_tc_scratch_bytes(num_sms());
+    return a > b ? a : b;
+}
 
 // -----------------------------------------------------------------------------------------------
 // weight packing: fold nn.utils.weight_norm (W = g * v / ||v||_row, models/base.py:226-227,365-366), the 1/sqrt(2) of
@@ -102,8 +124,7 @@ static size_t pack_dims_off(const PackF32& L) { return pack_scale_off(L) + 14 * 
 
 extern "C" size_t na_packed_weights_bytes(const NaNetDesc* desc) {
     if (!desc) return 0;
-    const PackF32 L = pack_layout_f32(desc->multires_view);
-    return (pack_dims_off(L) + 64) * sizeof(float);
+    return tc_pack_layout(packed_f32_bytes(desc->multires_view)).total;
 }
 
 extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, void* packed_, void* stream_) {
@@ -150,38 +171,37 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
     add(L.rad_b4, 1, 4, 13, 2, 0, 3, 0, 1.f);
     pack_fill_kernel<<<dim3(64, tab.n), 256, 0, stream>>>(*raw, tab, scale, packed);
     NA_CHECK_LAUNCH();
-    return NA_OK;
+    // tensor-core operand image (hi/lo fp16, UMMA K-major SWIZZLE_128B stages) derived from the fp32 planes
+    return tc_pack(packed, L, (unsigned char*)packed_, tc_pack_layout(packed_f32_bytes(desc->multires_view)), stream);
 }
 
 // -----------------------------------------------------------------------------------------------
 extern "C" size_t na_eval_workspace_bytes(int64_t m) {
     (void)m;
-    return mlp_simt_scratch_bytes(num_sms());
+    return mlp_scratch_bytes();
 }
 
 extern "C" int na_sdf_eval(const NaNetDesc* desc, const void* packed, const float* x, int64_t m, int apply_bg,
                            int precision, float* sdf, float* feat, void* workspace, size_t ws_bytes, void* stream) {
-    if (!desc || !packed || !x || !sdf || !workspace || m < 0) return NA_ERR_BAD_ARG;
-    if (precision != NA_PRECISION_FP32) return NA_ERR_UNSUPPORTED;
     if (m == 0) return NA_OK;
+    if (!desc || !packed || !x || !sdf || !workspace || m < 0) return NA_ERR_BAD_ARG;
     EvalJob job = {};
     job.x = x; job.m = m; job.sdf = sdf; job.feat = feat;
     job.apply_bg = apply_bg; job.bound_r = desc->bounding_radius; job.want_full = 0; job.multires_view = desc->multires_view;
-    return launch_mlp_simt(job, (const float*)packed, pack_layout_f32(desc->multires_view), (float*)workspace, ws_bytes, (cudaStream_t)stream);
+    return launch_mlp(job, packed, precision, (float*)workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int na_full_eval(const NaNetDesc* desc, const void* packed, const float* x, const float* view, int64_t m,
                             int precision, float* radiance, float* sdf, float* nablas, float* feat,
                             void* workspace, size_t ws_bytes, void* stream) {
+    if (m == 0) return NA_OK;
     if (!desc || !packed || !x || !workspace || m < 0) return NA_ERR_BAD_ARG;
     if (radiance && !view) return NA_ERR_BAD_ARG;
-    if (precision != NA_PRECISION_FP32) return NA_ERR_UNSUPPORTED;
-    if (m == 0) return NA_OK;
     EvalJob job = {};
     job.x = x; job.view = view; job.m = m; job.sdf = sdf; job.feat = feat; job.rad = radiance; job.nab = nablas;
     job.apply_bg = desc->framework == NA_FRAMEWORK_VOLSDF; job.bound_r = desc->bounding_radius;
     job.want_full = 1; job.multires_view = desc->multires_view;
-    return launch_mlp_simt(job, (const float*)packed, pack_layout_f32(desc->multires_view), (float*)workspace, ws_bytes, (cudaStream_t)stream);
+    return launch_mlp(job, packed, precision, (float*)workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 // -----------------------------------------------------------------------------------------------

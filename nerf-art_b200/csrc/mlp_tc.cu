@@ -1,0 +1,624 @@
+// Fused per-sample network kernel, tcgen05 tensor-core path (NA_PRECISION_TC).  sm_100a only.
+//
+// One persistent CTA per SM; each tile is 128 samples = the 128 TMEM lanes of one UMMA accumulator.
+// Every layer GEMM  D[128 x 256] = A[128 x K] * B[256 x K]^T  runs on the 5th-gen tensor cores
+// (tcgen05.mma.cta_group::1.kind::f16, M=128, N=128 per instruction, fp32 accumulate in TMEM).
+//
+// Precision: both operands are carried as TWO fp16 terms  v = hi + lo  (22 significant bits, power-of-two
+// pre-scaling keeps lo out of the fp16 subnormal range), and three products  hi*hi + hi*lo + lo*hi  are
+// accumulated -- the dropped lo*lo term is 2^-22 relative, i.e. fp32-level.  Activation functions, the
+// softplus derivative needed by the reverse sweep, the narrow heads (sdf, rgb) and the small radiance
+// inputs (x, view, nabla) stay in fp32 on the CUDA cores.
+//
+// Warp roles (10 warps):  warp 0 lane 0 streams pre-swizzled 16 KB weight stages with cp.async.bulk into a
+// 4-deep mbarrier ring; warp 1 lane 0 issues the MMAs and owns TMEM; warps 2..9 are the epilogue: warp w reads TMEM
+// lanes 32*(w%4).., i.e. thread = one sample row, two warps per row splitting the 256 columns; they apply bias /
+// softplus / relu, split the result into hi/lo fp16 and write it back, in the UMMA K-major SWIZZLE_128B layout,
+// as the A operand of the next layer.  Activations never leave the SM.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace na {
+
+constexpr int TC_TM = 128;
+constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_NS = 4;                         // weight stages
+constexpr int STAGE_BYTES = 16384;               // 128 rows x 64 fp16
+constexpr int A_SPLIT_BYTES = 4 * STAGE_BYTES;   // 128 rows x 256 fp16
+constexpr float ACT_SCALE = 16.f;                // activations are stored x16 (keeps the lo term normal in fp16)
+constexpr int TC_MAX_GEMM = 24;
+
+struct TcGemm { unsigned w_stage0; unsigned char n_kb, n_nh, pad0, pad1; };
+struct TcProgram { int n_gemm; TcGemm g[TC_MAX_GEMM]; };
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, unsigned ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns: thread i of the warp receives lane (base+i), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// K-major, SWIZZLE_128B UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B between 8-row groups) |
+//   [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N=128 (n_dim=16 @17), M=128 (m_dim=8 @24)
+constexpr unsigned UMMA_IDESC = (1u << 4) | (16u << 17) | (8u << 24);
+
+// byte offset of element (row r, k) inside one 128-row x 256-k split buffer (four 16 KB K-blocks)
+__device__ __forceinline__ unsigned a_off(int r, int k) {
+    return (unsigned)((k >> 6) * STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + ((k & 7) << 1));
+}
+
+struct __align__(1024) TcSmem {
+    unsigned char A1[A_SPLIT_BYTES];
+    unsigned char A2[A_SPLIT_BYTES];
+    unsigned char Wst[TC_NS * STAGE_BYTES];
+    unsigned long long full_bar[TC_NS], empty_bar[TC_NS], d_ready, a_ready;
+    unsigned tmem_base;
+    float X[3 * TC_TM];
+    float V[3 * TC_TM];
+    float PART[2 * 4 * TC_TM];           // column-half partial sums of the narrow heads
+    long long OIDX[TC_TM];
+};
+
+// split 8 consecutive fp32 values (already x ACT_SCALE) into hi/lo fp16 and store 16 B + 16 B
+__device__ __forceinline__ void store8(unsigned char* A1, unsigned char* A2, int r, int k0, const float (&h)[8]) {
+    __half2 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hi[i] = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+        const float2 back = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(h[2 * i] - back.x, h[2 * i + 1] - back.y);
+    }
+    const unsigned off = a_off(r, k0);
+    *reinterpret_cast<uint4*>(A1 + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(A2 + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// scratch planes: value (plane p, column k, row r) lives at float index ((p*64 + k/4)*128 + r)*4 + k%4
+__device__ __forceinline__ float4* plane_ptr(float* sp, int p, int k4, int r) {
+    return reinterpret_cast<float4*>(sp) + ((size_t)(p * 64 + k4) * TC_TM + r);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wtc,
+              const float* __restrict__ unscale, const TcProgram prog, float* __restrict__ scratch) {
+    extern __shared__ unsigned char smem_raw_[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool explicit_pts = job.x != nullptr;
+    const long long total = explicit_pts ? job.m
+                          : (long long)(job.n_rows_dev ? min(*job.n_rows_dev, job.n_rows) : job.n_rows) * job.P;
+    const long long n_tiles = (total + TC_TM - 1) / TC_TM;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NS; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
+        mbar_init(smem_u32(&S.d_ready), 1);
+        mbar_init(smem_u32(&S.a_ready), TC_EPI_THREADS);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_d = S.tmem_base;
+
+    if (warp == 0) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            unsigned it = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int g = 0; g < prog.n_gemm; ++g) {
+                    const unsigned char* src = wtc + (size_t)prog.g[g].w_stage0 * STAGE_BYTES;
+                    const int n_st = prog.g[g].n_nh * prog.g[g].n_kb * 2;
+                    for (int st = 0; st < n_st; ++st, ++it) {
+                        const unsigned slot = it % TC_NS, ph = (it / TC_NS) & 1;
+                        mbar_wait(smem_u32(&S.empty_bar[slot]), ph ^ 1);
+                        mbar_expect_tx(smem_u32(&S.full_bar[slot]), STAGE_BYTES);
+                        bulk_g2s(smem_u32(S.Wst + slot * STAGE_BYTES), src + (size_t)st * STAGE_BYTES, STAGE_BYTES, smem_u32(&S.full_bar[slot]));
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            unsigned it = 0, a_phase = 0;
+            const unsigned a1 = smem_u32(S.A1), a2 = smem_u32(S.A2), wst = smem_u32(S.Wst);
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int g = 0; g < prog.n_gemm; ++g) {
+                    mbar_wait(smem_u32(&S.a_ready), a_phase); a_phase ^= 1;
+                    tc_fence_after();
+                    const int n_kb = prog.g[g].n_kb, n_nh = prog.g[g].n_nh;
+                    for (int nh = 0; nh < n_nh; ++nh)
+                        for (int kb = 0; kb < n_kb; ++kb)
+                            for (int s = 0; s < 2; ++s, ++it) {
+                                const unsigned slot = it % TC_NS, ph = (it / TC_NS) & 1;
+                                mbar_wait(smem_u32(&S.full_bar[slot]), ph);
+                                tc_fence_after();
+                                const unsigned d = tmem_d + nh * 128;
+                                const unsigned long long bd = umma_desc(wst + slot * STAGE_BYTES);
+                                const unsigned long long ad1 = umma_desc(a1 + kb * STAGE_BYTES);
+                                const unsigned long long ad2 = umma_desc(a2 + kb * STAGE_BYTES);
+                                if (s == 0) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, (kb | ks) != 0);   // hi * hi
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad2 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                // lo * hi
+                                } else {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                // hi * lo
+                                }
+                                umma_commit(smem_u32(&S.empty_bar[slot]));
+                            }
+                    umma_commit(smem_u32(&S.d_ready));
+                }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3, ch = (warp - 2) >> 2;
+        const int r = 32 * q + lane;                       // sample row == TMEM lane
+        const int e = tid - 64;                            // 0..255 epilogue thread index
+        const unsigned t_row = tmem_d + ((unsigned)(32 * q) << 16);
+        float* sp = scratch + (size_t)blockIdx.x * (10 * 256 * TC_TM);     // planes 0..7 softplus', 8 feature, 9 misc rows
+        float* misc = sp + (size_t)9 * 256 * TC_TM;                        // [row][80]: d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
+        const int sdim = small_dim(job.multires_view);
+        unsigned d_phase = 0;
+        const bool full = job.want_full != 0, has_rad = job.rad != nullptr;
+
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // ---- tile inputs: point, encoding (x ACT_SCALE, hi/lo) into K-block 0 ----------------------------------
+            if (ch == 0) {
+                const long long w = tile * TC_TM + r;
+                float x0 = 0.f, x1 = 0.f, x2 = 0.f, v0 = 0.f, v1 = 0.f, v2 = 1.f;
+                long long oidx = -1;
+                if (w < total) {
+                    if (explicit_pts) {
+                        x0 = job.x[w * 3]; x1 = job.x[w * 3 + 1]; x2 = job.x[w * 3 + 2];
+                        if (job.view) { v0 = job.view[w * 3]; v1 = job.view[w * 3 + 1]; v2 = job.view[w * 3 + 2]; }
+                        oidx = w;
+                    } else {
+                        const long long row = w / job.P; const int j = (int)(w - row * job.P);
+                        const long long ray = job.row_ids ? job.row_ids[row] : row;
+                        const float* tp = job.t + ray * job.t_stride + job.t_off + j;
+                        float t = tp[0];
+                        if (job.midpoints) t = __fmul_rn(0.5f, __fadd_rn(tp[1], t));
+                        v0 = job.rays_d[ray * 3]; v1 = job.rays_d[ray * 3 + 1]; v2 = job.rays_d[ray * 3 + 2];
+                        x0 = __fadd_rn(job.rays_o[ray * 3], __fmul_rn(v0, t));
+                        x1 = __fadd_rn(job.rays_o[ray * 3 + 1], __fmul_rn(v1, t));
+                        x2 = __fadd_rn(job.rays_o[ray * 3 + 2], __fmul_rn(v2, t));
+                        oidx = ray * job.o_stride + job.o_off + j;
+                    }
+                }
+                S.OIDX[r] = oidx;
+                S.X[r] = x0; S.X[TC_TM + r] = x1; S.X[2 * TC_TM + r] = x2;
+                S.V[r] = v0; S.V[TC_TM + r] = v1; S.V[2 * TC_TM + r] = v2;
+                float emb[64];
+                const float xs[3] = {x0, x1, x2};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) emb[c] = xs[c] * ACT_SCALE;
+#pragma unroll
+                for (int f = 0; f < 6; ++f)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float sn, cs; sincosf(__fmul_rn(xs[c], (float)(1 << f)), &sn, &cs);
+                        emb[3 + 6 * f + c] = sn * ACT_SCALE; emb[6 + 6 * f + c] = cs * ACT_SCALE;
+                    }
+#pragma unroll
+                for (int k = EMB; k < 64; ++k) emb[k] = 0.f;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float h8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h8[i] = emb[8 * c8 + i];
+                    store8(S.A1, S.A2, r, 8 * c8, h8);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&S.a_ready));
+
+            float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
+            for (int g = 0; g < prog.n_gemm; ++g) {
+                mbar_wait(smem_u32(&S.d_ready), d_phase); d_phase ^= 1;
+                tc_fence_after();
+                const float us = unscale[g];                      // 2^-(weight shift) / ACT_SCALE
+                // which epilogue?  program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
+                const bool is_fwd = g < 8, is_feat = g == 8, is_bwd = g >= 9 && g <= 15, is_bwd0 = g == 16, is_rad = g >= 17;
+                const int rl = g - 17;                            // radiance layer
+                const int bl = 16 - g;                            // backward: d sdf / d (input of layer bl)
+                const float* bias = is_fwd ? pk + L.sdf_b[g] : is_feat ? pk + L.b8_feat : is_rad ? pk + L.rad_b[rl] : nullptr;
+                float small_in[36];
+                if (is_rad && rl == 0) {
+#pragma unroll
+                    for (int j = 0; j < 36; ++j) small_in[j] = j < sdim ? misc[r * 80 + 40 + j] : 0.f;
+                }
+                if (is_bwd0) epi_bar_sync();
+                if (!(is_bwd0 && ch == 1)) {
+#pragma unroll 1
+                    for (int c32 = 0; c32 < 4; ++c32) {
+                        const int col0 = ch * 128 + c32 * 32;
+                        unsigned v[32];
+                        tmem_ld32(t_row + col0, v);
+                        float o[32];
+                        if (is_fwd) {
+                            // z16 = 16 z ; softplus_100(z) = max(z,0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e))
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
+                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                                float dh[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int j = 4 * j4 + i;
+                                    const float z16 = fmaf(__uint_as_float(v[j]), us * ACT_SCALE, bb[i] * ACT_SCALE);
+                                    const float t = ex2_approx(-fabsf(z16) * (100.f * 1.4426950408889634f / ACT_SCALE));
+                                    const float u = 1.f + t;
+                                    o[j] = fmaf(lg2_approx(u), ACT_SCALE * 0.6931471805599453f / 100.f, fmaxf(z16, 0.f));
+                                    const float ru = rcp_approx(u);
+                                    dh[i] = z16 >= 0.f ? ru : t * ru;
+                                }
+                                if (g == 3 && col0 + 4 * j4 + 3 >= SKIP_H) {
+                                    // skip connection columns: h = emb[k-217] (x16), softplus' = 0
+                                    const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int k = col0 + 4 * j4 + i;
+                                        if (k >= SKIP_H) {
+                                            const int ei = k - SKIP_H;
+                                            float val;
+                                            if (ei < 3) val = xs[ei];
+                                            else { const int f = (ei - 3) / 6, rem = (ei - 3) % 6; float sn, cs; sincosf(__fmul_rn(xs[rem % 3], (float)(1 << f)), &sn, &cs); val = rem < 3 ? sn : cs; }
+                                            o[4 * j4 + i] = val * ACT_SCALE; dh[i] = 0.f;
+                                        }
+                                    }
+                                }
+                                if (full) *plane_ptr(sp, g, (col0 >> 2) + j4, r) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+                            }
+                            if (g == 7) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; ++j4) {
+                                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(pk + L.w8_sdf + col0) + j4);
+                                    sdf_part = fmaf(o[4 * j4], w4.x, sdf_part); sdf_part = fmaf(o[4 * j4 + 1], w4.y, sdf_part);
+                                    sdf_part = fmaf(o[4 * j4 + 2], w4.z, sdf_part); sdf_part = fmaf(o[4 * j4 + 3], w4.w, sdf_part);
+                                }
+                            }
+                        } else if (is_feat) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
+                                const float4 f4 = make_float4(fmaf(__uint_as_float(v[4 * j4]), us, b4.x), fmaf(__uint_as_float(v[4 * j4 + 1]), us, b4.y),
+                                                              fmaf(__uint_as_float(v[4 * j4 + 2]), us, b4.z), fmaf(__uint_as_float(v[4 * j4 + 3]), us, b4.w));
+                                *plane_ptr(sp, 8, (col0 >> 2) + j4, r) = f4;
+                                if (job.feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(job.feat + S.OIDX[r] * 256 + col0) + j4) = f4;
+                                // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
+                                const float4 w4 = __ldg(reinterpret_cast<const float4*>(pk + L.w8_sdf + col0) + j4);
+                                const float4 d4 = *plane_ptr(sp, 7, (col0 >> 2) + j4, r);
+                                o[4 * j4] = w4.x * d4.x * ACT_SCALE; o[4 * j4 + 1] = w4.y * d4.y * ACT_SCALE;
+                                o[4 * j4 + 2] = w4.z * d4.z * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4.w * ACT_SCALE;
+                            }
+                        } else if (is_bwd) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 d4 = *plane_ptr(sp, bl - 1, (col0 >> 2) + j4, r);
+                                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float gval = __uint_as_float(v[4 * j4 + i]) * us;
+                                    const int k = col0 + 4 * j4 + i;
+                                    if (bl == 4 && k >= SKIP_H) misc[r * 80 + (k - SKIP_H)] = gval;      // embedding branch of the skip
+                                    o[4 * j4 + i] = gval * dd[i] * ACT_SCALE;
+                                }
+                            }
+                        } else if (is_bwd0) {
+                            // d sdf / d emb: 39 useful columns, all inside the first 64
+                            if (c32 < 2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) { const int k = col0 + j; if (k < EMB) misc[r * 80 + k] += __uint_as_float(v[j]) * us; }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
+                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int k = col0 + 4 * j4 + i;
+                                    float z = fmaf(__uint_as_float(v[4 * j4 + i]), us, bb[i]);
+                                    if (rl == 0) {
+                                        // small inputs [x | embed(view) | nabla] in fp32: rows 256.. of the packed layer-0 plane
+                                        const float* wsm = pk + L.rad_wt[0] + (size_t)256 * 256 + k;
+                                        if (sdim == 9) {
+#pragma unroll
+                                            for (int j = 0; j < 9; ++j) z = fmaf(small_in[j], __ldg(wsm + j * 256), z);
+                                        } else {
+#pragma unroll
+                                            for (int j = 0; j < 33; ++j) z = fmaf(small_in[j], __ldg(wsm + j * 256), z);
+                                        }
+                                    }
+                                    o[4 * j4 + i] = fmaxf(z, 0.f);
+                                }
+                            }
+                            if (rl == 3) {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) rgb_part[c] = fmaf(o[j], __ldg(pk + L.rad_w4 + c * 256 + col0 + j), rgb_part[c]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[j] *= ACT_SCALE;
+                        }
+                        if (!is_bwd0 && !(is_rad && rl == 3) && !(g == 7 && !full && !job.feat)) {
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                float h8[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) h8[i] = o[8 * c8 + i];
+                                store8(S.A1, S.A2, r, col0 + 8 * c8, h8);
+                            }
+                        }
+                    }
+                }
+                // ---- per-GEMM tails ------------------------------------------------------------------------
+                if (g == 7) {
+                    // fwd layer 7 stored h8 x16: undo in the head.  sdf = <h8, W8[0]> + b8[0]
+                    S.PART[ch * TC_TM + r] = sdf_part * (1.f / ACT_SCALE); sdf_part = 0.f;
+                    epi_bar_sync();
+                    if (ch == 0) {
+                        float sdf = S.PART[r] + S.PART[TC_TM + r] + __ldg(pk + L.b8_sdf);
+                        if (job.apply_bg) {
+                            const float x0 = S.X[r], x1 = S.X[TC_TM + r], x2 = S.X[2 * TC_TM + r];
+                            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+                            sdf = fminf(sdf, job.bound_r - nrm);
+                        }
+                        if (S.OIDX[r] >= 0 && job.sdf) job.sdf[S.OIDX[r]] = sdf;
+                    }
+                }
+                if (is_bwd0) {
+                    if (ch == 0) {
+                        // nabla and the fp32 small radiance inputs
+                        const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
+                        float nb[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float n = misc[r * 80 + c];
+#pragma unroll
+                            for (int f = 0; f < 6; ++f) {
+                                const float fr = (float)(1 << f);
+                                float sn, cs; sincosf(__fmul_rn(xs[c], fr), &sn, &cs);
+                                n += fr * (misc[r * 80 + 3 + 6 * f + c] * cs - misc[r * 80 + 6 + 6 * f + c] * sn);
+                            }
+                            nb[c] = n;
+                        }
+                        const long long oo = S.OIDX[r];
+                        if (oo >= 0 && job.nab) { job.nab[oo * 3] = nb[0]; job.nab[oo * 3 + 1] = nb[1]; job.nab[oo * 3 + 2] = nb[2]; }
+                        if (has_rad) {
+                            float* sm = misc + r * 80 + 40;
+                            int qn = 0;
+                            for (int c = 0; c < 3; ++c) sm[qn++] = xs[c];
+                            const float vs[3] = {S.V[r], S.V[TC_TM + r], S.V[2 * TC_TM + r]};
+                            for (int c = 0; c < 3; ++c) sm[qn++] = vs[c];
+                            for (int f = 0; f < job.multires_view; ++f) {
+                                float sn[3], cs[3];
+                                for (int c = 0; c < 3; ++c) sincosf(__fmul_rn(vs[c], (float)(1 << f)), &sn[c], &cs[c]);
+                                for (int c = 0; c < 3; ++c) sm[qn++] = sn[c];
+                                for (int c = 0; c < 3; ++c) sm[qn++] = cs[c];
+                            }
+                            for (int c = 0; c < 3; ++c) sm[qn++] = nb[c];
+                        }
+                    }
+                    if (has_rad) {
+                        // A <- geometry feature (x16) for radiance layer 0
+#pragma unroll 1
+                        for (int c32 = 0; c32 < 4; ++c32) {
+                            const int col0 = ch * 128 + c32 * 32;
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                const float4 f0 = *plane_ptr(sp, 8, (col0 >> 2) + 2 * c8, r), f1 = *plane_ptr(sp, 8, (col0 >> 2) + 2 * c8 + 1, r);
+                                const float h8[8] = {f0.x * ACT_SCALE, f0.y * ACT_SCALE, f0.z * ACT_SCALE, f0.w * ACT_SCALE,
+                                                     f1.x * ACT_SCALE, f1.y * ACT_SCALE, f1.z * ACT_SCALE, f1.w * ACT_SCALE};
+                                store8(S.A1, S.A2, r, col0 + 8 * c8, h8);
+                            }
+                        }
+                        epi_bar_sync();                       // small inputs written by ch==0 threads are read by both halves next
+                    }
+                }
+                if (is_rad && rl == 3) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { S.PART[(ch * 4 + c) * TC_TM + r] = rgb_part[c]; rgb_part[c] = 0.f; }
+                    epi_bar_sync();
+                    if (ch == 0 && S.OIDX[r] >= 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float z = S.PART[c * TC_TM + r] + S.PART[(4 + c) * TC_TM + r] + __ldg(pk + L.rad_b4 + c);
+                            job.rad[S.OIDX[r] * 3 + c] = __fdiv_rn(1.f, 1.f + expf(-z));
+                        }
+                    }
+                }
+                if (g + 1 < prog.n_gemm) {
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(smem_u32(&S.a_ready));
+                } else {
+                    tc_fence_before();
+                    epi_bar_sync();                           // X / OIDX / PART are rewritten by the next tile's input stage
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 256); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing for the tensor-core path: fp32 plane P[r][c] (r = contraction index, c = output column; exactly the planes
+// the fp32 path uses) -> stages [nh][kb][split][128 rows c][64 k r] in the UMMA K-major SWIZZLE_128B smem image, scaled by
+// 2^shift so that max|W| lands in [256, 512), split into hi/lo fp16.
+// ------------------------------------------------------------------------------------------------
+__global__ void plane_absmax_kernel(const float* __restrict__ pk, const size_t* __restrict__ offs, const int* __restrict__ rows, float* __restrict__ out) {
+    const int g = blockIdx.x;
+    const float* p = pk + offs[g];
+    const int n = rows[g] * 256;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+    __shared__ float red[256];
+    red[threadIdx.x] = m; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    if (threadIdx.x == 0) out[g] = red[0];
+}
+
+__global__ void tc_pack_kernel(const float* __restrict__ pk, const size_t* __restrict__ offs, const int* __restrict__ rows,
+                               const int* __restrict__ n_kb_, const int* __restrict__ n_nh_, const unsigned* __restrict__ stage0,
+                               const float* __restrict__ absmax, unsigned char* __restrict__ wtc, float* __restrict__ unscale) {
+    const int g = blockIdx.y;
+    const float* p = pk + offs[g];
+    const int R = rows[g], n_kb = n_kb_[g], n_nh = n_nh_[g];
+    const float mx = absmax[g];
+    int shift = 0;
+    if (mx > 0.f) { int e; frexpf(mx, &e); shift = 9 - e; }           // mx * 2^shift in [256, 512)
+    const float sc = ldexpf(1.f, shift);
+    if (blockIdx.x == 0 && threadIdx.x == 0) unscale[g] = ldexpf(1.f, -shift) / ACT_SCALE;
+    const int n_el = n_nh * n_kb * 128 * 64;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_el; idx += gridDim.x * blockDim.x) {
+        const int kk = idx & 63, nl = (idx >> 6) & 127, blk = idx >> 13;         // blk = nh * n_kb + kb
+        const int kb = blk % n_kb, nh = blk / n_kb;
+        const int rr = kb * 64 + kk, c = nh * 128 + nl;
+        const float w = rr < R ? p[(size_t)rr * 256 + c] * sc : 0.f;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        const size_t st = (size_t)stage0[g] + (size_t)blk * 2;
+        const unsigned off = (unsigned)((nl >> 3) * 1024 + (nl & 7) * 128 + (((kk >> 3) ^ (nl & 7)) << 4) + ((kk & 7) << 1));
+        *reinterpret_cast<__half*>(wtc + st * STAGE_BYTES + off) = hi;
+        *reinterpret_cast<__half*>(wtc + (st + 1) * STAGE_BYTES + off) = lo;
+    }
+}
+
+// program: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
+constexpr int TC_N_PLANES = 21;
+struct TcPackLayout { size_t wtc_off, unscale_off, meta_off, total; unsigned stage0[TC_N_PLANES]; int n_kb[TC_N_PLANES], n_nh[TC_N_PLANES]; unsigned n_stages; };
+
+TcPackLayout tc_pack_layout(size_t f32_bytes) {
+    TcPackLayout T;
+    unsigned st = 0;
+    for (int g = 0; g < TC_N_PLANES; ++g) {
+        T.n_kb[g] = (g == 0) ? 1 : 4;
+        T.n_nh[g] = (g == 16) ? 1 : 2;
+        T.stage0[g] = st; st += (unsigned)(T.n_kb[g] * T.n_nh[g] * 2);
+    }
+    T.n_stages = st;
+    T.wtc_off = (f32_bytes + 1023) & ~(size_t)1023;
+    T.unscale_off = T.wtc_off + (size_t)st * STAGE_BYTES;
+    T.meta_off = T.unscale_off + 256;
+    T.total = T.meta_off + 4096;
+    return T;
+}
+
+int tc_pack(const float* pk_f32, const PackF32& L, unsigned char* base, const TcPackLayout& T, cudaStream_t stream) {
+    size_t offs[TC_N_PLANES]; int rows[TC_N_PLANES];
+    for (int i = 0; i < 8; ++i) { offs[i] = L.sdf_wt[i]; rows[i] = i == 0 ? EMB_PAD : 256; }
+    offs[8] = L.w8t_feat; rows[8] = 256;
+    for (int i = 0; i < 7; ++i) { offs[9 + i] = L.sdf_w[7 - i]; rows[9 + i] = 256; }
+    offs[16] = L.sdf_w[0]; rows[16] = 256;
+    for (int i = 0; i < 4; ++i) { offs[17 + i] = L.rad_wt[i]; rows[17 + i] = 256; }
+    unsigned char* meta = base + T.meta_off;
+    size_t* d_offs = (size_t*)meta; int* d_rows = (int*)(meta + 256); int* d_kb = (int*)(meta + 512); int* d_nh = (int*)(meta + 768);
+    unsigned* d_st = (unsigned*)(meta + 1024); float* d_absmax = (float*)(meta + 1280);
+    NA_TRY(check_cuda(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(d_rows, rows, sizeof(rows), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(d_kb, T.n_kb, sizeof(T.n_kb), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(d_nh, T.n_nh, sizeof(T.n_nh), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(d_st, T.stage0, sizeof(T.stage0), cudaMemcpyHostToDevice, stream)));
+    plane_absmax_kernel<<<TC_N_PLANES, 256, 0, stream>>>(pk_f32, d_offs, d_rows, d_absmax);
+    NA_CHECK_LAUNCH();
+    tc_pack_kernel<<<dim3(32, TC_N_PLANES), 256, 0, stream>>>(pk_f32, d_offs, d_rows, d_kb, d_nh, d_st, d_absmax, base + T.wtc_off,
+                                                                (float*)(base + T.unscale_off));
+    NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
+size_t mlp_tc_scratch_bytes(int grid) { return (size_t)grid * 10 * 256 * TC_TM * sizeof(float); }
+
+int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
+                  size_t scratch_bytes, cudaStream_t stream) {
+    static thread_local bool attr_set = false;
+    const size_t smem = sizeof(TcSmem) + 1024;
+    if (!attr_set) {
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        attr_set = true;
+    }
+    const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
+    if (total <= 0) return NA_OK;
+    const TcPackLayout T = tc_pack_layout(f32_bytes);
+    TcProgram prog; prog.n_gemm = 0;
+    auto add = [&](int g) { TcGemm t; t.w_stage0 = T.stage0[g]; t.n_kb = (unsigned char)T.n_kb[g]; t.n_nh = (unsigned char)T.n_nh[g]; t.pad0 = t.pad1 = 0; prog.g[prog.n_gemm++] = t; };
+    const int last = !job.want_full ? (job.feat ? 8 : 7) : (job.rad ? 20 : 16);
+    for (int g = 0; g <= last; ++g) add(g);
+    long long tiles = (total + TC_TM - 1) / TC_TM;
+    int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
+    if (scratch_bytes < mlp_tc_scratch_bytes(grid)) return NA_ERR_WORKSPACE;
+    mlp_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(job, (const float*)packed_base, L, packed_base + T.wtc_off,
+                                                       (const float*)(packed_base + T.unscale_off), prog, scratch);
+    NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
+}  // namespace na

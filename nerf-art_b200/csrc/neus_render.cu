@@ -5,8 +5,8 @@
 
 namespace na {
 
-int launch_mlp_simt(const EvalJob& job, const float* packed, const PackF32& L, float* scratch, size_t scratch_bytes, cudaStream_t stream);
-size_t mlp_simt_scratch_bytes(int grid);
+int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t mlp_scratch_bytes();
 int launch_normalize_dirs(const float* d_in, float* d_out, long long n, cudaStream_t stream);
 
 // near / far (rend_util.near_far_from_sphere, utils/rend_util.py:168-186) and the coarse depths (neus.py:235-236)
@@ -199,7 +199,7 @@ static NeusWs neus_ws_layout(const NaNeusCfg& c, long long n_rays) {
     w.sdf = o; o += nalign256((size_t)n_rays * P * 4);
     w.nab = o; o += nalign256((size_t)n_rays * P * 3 * 4);
     w.rad = o; o += nalign256((size_t)n_rays * (P - 1) * 3 * 4);
-    w.scratch = o; o += nalign256(mlp_simt_scratch_bytes(num_sms()));
+    w.scratch = o; o += nalign256(mlp_scratch_bytes());
     w.total = o;
     return w;
 }
@@ -220,7 +220,7 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     if (!desc || !packed || !cfg || !rays_o || !rays_d || !s_dev || !t_coarse || !u_imp || !out || !workspace || n_rays <= 0) return NA_ERR_BAD_ARG;
     if (!out->rgb || !out->depth || !out->acc) return NA_ERR_BAD_ARG;
     if (cfg->perturb && !u_rand) return NA_ERR_BAD_ARG;
-    if (cfg->precision != NA_PRECISION_FP32) return NA_ERR_UNSUPPORTED;
+    if (cfg->precision != NA_PRECISION_FP32 && cfg->precision != NA_PRECISION_TC) return NA_ERR_UNSUPPORTED;
     if (cfg->n_samples < 2 || cfg->n_upsample_iters < 1 || cfg->n_importance % cfg->n_upsample_iters != 0) return NA_ERR_BAD_ARG;
     const int P = cfg->n_samples + cfg->n_importance, n_new = cfg->n_importance / cfg->n_upsample_iters;
     if (P > 2048 || n_new > 64 || n_new < 1) return NA_ERR_UNSUPPORTED;
@@ -236,8 +236,6 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     float* rad_f = out->radiance ? out->radiance : (float*)(ws + w.rad);
     float* scratch = (float*)(ws + w.scratch);
     const size_t scratch_bytes = w.total - w.scratch;
-    const PackF32 L = pack_layout_f32(desc->multires_view);
-    const float* pk = (const float*)packed;
 
     NA_TRY(launch_normalize_dirs(rays_d, dirs, n_rays, stream));
     {
@@ -249,7 +247,7 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     EvalJob job = {};
     job.rays_o = rays_o; job.rays_d = dirs; job.n_rows = (int)n_rays; job.P = cfg->n_samples; job.t = T; job.t_stride = P; job.t_off = 0;
     job.o_stride = P; job.o_off = 0; job.sdf = S; job.apply_bg = 0; job.want_full = 0; job.multires_view = desc->multires_view;
-    NA_TRY(launch_mlp_simt(job, pk, L, scratch, scratch_bytes, stream));                  // neus.py:276
+    NA_TRY(launch_mlp(job, packed, cfg->precision, scratch, scratch_bytes, stream));                  // neus.py:276
 
     NeusArgs na_ = {};
     na_.T = T; na_.S = S; na_.P = P; na_.n_samples = cfg->n_samples; na_.n_new = n_new; na_.n_iters = cfg->n_upsample_iters;
@@ -260,7 +258,7 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
         if (it > 0) {
             EvalJob uj = job;
             uj.P = n_new; uj.t_off = cfg->n_samples + (it - 1) * n_new; uj.o_off = uj.t_off;
-            NA_TRY(launch_mlp_simt(uj, pk, L, scratch, scratch_bytes, stream));          // neus.py:299
+            NA_TRY(launch_mlp(uj, packed, cfg->precision, scratch, scratch_bytes, stream));          // neus.py:299
         }
         neus_upsample_kernel<<<(unsigned)n_rays, SNT, smem, stream>>>(na_, it);
         NA_CHECK_LAUNCH();
@@ -268,10 +266,10 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     // sdf + nablas at the P depths (neus.py:320), radiance at the P-1 midpoints through a second SDF pass (324, 111-114)
     EvalJob fj = job;
     fj.P = P; fj.t_off = 0; fj.o_off = 0; fj.sdf = sdf_f; fj.nab = nab_f; fj.rad = nullptr; fj.want_full = 1;
-    NA_TRY(launch_mlp_simt(fj, pk, L, scratch, scratch_bytes, stream));
+    NA_TRY(launch_mlp(fj, packed, cfg->precision, scratch, scratch_bytes, stream));
     EvalJob mj = job;
     mj.P = P - 1; mj.t_off = 0; mj.midpoints = 1; mj.o_stride = P - 1; mj.o_off = 0; mj.sdf = nullptr; mj.nab = nullptr; mj.rad = rad_f; mj.want_full = 1;
-    NA_TRY(launch_mlp_simt(mj, pk, L, scratch, scratch_bytes, stream));
+    NA_TRY(launch_mlp(mj, packed, cfg->precision, scratch, scratch_bytes, stream));
     NeusCompositeArgs ca = {};
     ca.d_all = T; ca.sdf = sdf_f; ca.rad = rad_f; ca.nab = nab_f; ca.s_dev = s_dev; ca.P = P; ca.white_bkgd = cfg->white_bkgd; ca.n_rays = n_rays;
     ca.rgb = out->rgb; ca.depth = out->depth; ca.acc = out->acc; ca.normals = out->normals; ca.alpha_out = out->alpha; ca.w_out = out->weights;

@@ -8,8 +8,8 @@
 
 namespace na {
 
-int launch_mlp_simt(const EvalJob& job, const float* packed, const PackF32& L, float* scratch, size_t scratch_bytes, cudaStream_t stream);
-size_t mlp_simt_scratch_bytes(int grid);
+int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t mlp_scratch_bytes();
 
 // -----------------------------------------------------------------------------------------------
 __global__ void normalize_dirs_kernel(const float* __restrict__ d_in, float* __restrict__ d_out, long long n) {
@@ -271,7 +271,7 @@ static VolsdfWs volsdf_ws_layout(const NaVolsdfCfg& c, long long n_rays) {
     w.sdf = o; o += align256((size_t)n_rays * P * 4);
     w.rad = o; o += align256((size_t)n_rays * P * 3 * 4);
     w.nab = o; o += align256((size_t)n_rays * P * 3 * 4);
-    w.scratch = o; o += align256(mlp_simt_scratch_bytes(num_sms()));
+    w.scratch = o; o += align256(mlp_scratch_bytes());
     w.total = o;
     return w;
 }
@@ -295,7 +295,7 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
     if (!out->rgb || !out->depth || !out->acc || !out->beta_map || !out->iter_usage) return NA_ERR_BAD_ARG;
     if (cfg->perturb && !u_final) return NA_ERR_BAD_ARG;
     if (desc->framework != NA_FRAMEWORK_VOLSDF) return NA_ERR_BAD_ARG;
-    if (cfg->precision != NA_PRECISION_FP32) return NA_ERR_UNSUPPORTED;
+    if (cfg->precision != NA_PRECISION_FP32 && cfg->precision != NA_PRECISION_TC) return NA_ERR_UNSUPPORTED;
     if (cfg->n_samples < 2 || cfg->n_importance < 1 || cfg->max_upsample_steps < 0 || cfg->max_bisection_steps < 0) return NA_ERR_BAD_ARG;
     const int n0 = 4 * cfg->n_samples, n_up = n0, P = cfg->n_samples + cfg->n_importance;
     const long long cap = (long long)n0 * (1 + cfg->max_upsample_steps);
@@ -315,8 +315,6 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
     float* nab_f = out->nablas ? out->nablas : (float*)(ws + w.nab);
     float* scratch = (float*)(ws + w.scratch);
     const size_t scratch_bytes = w.total - w.scratch;
-    const PackF32 L = pack_layout_f32(desc->multires_view);
-    const float* pk = (const float*)packed;
 
     NA_TRY(launch_normalize_dirs(rays_d, dirs, n_rays, stream));
 
@@ -338,7 +336,7 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
         job.n_rows = (int)nr; job.P = n0; job.t = T; job.t_stride = cap; job.t_off = 0;
         job.o_stride = cap; job.o_off = 0; job.sdf = S;
         job.apply_bg = 1; job.bound_r = desc->bounding_radius; job.want_full = 0; job.multires_view = desc->multires_view;
-        NA_TRY(launch_mlp_simt(job, pk, L, scratch, scratch_bytes, stream));
+        NA_TRY(launch_mlp(job, packed, cfg->precision, scratch, scratch_bytes, stream));
 
         SamplerArgs sa = {};
         sa.T = T; sa.S = S; sa.cap = cap; sa.n0 = n0; sa.n_up = n_up; sa.n_imp = cfg->n_importance; sa.n_samples = cfg->n_samples; sa.P = P;
@@ -357,7 +355,7 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
                 EvalJob uj = job;
                 uj.row_ids = sa.list_in; uj.n_rows_dev = sa.count_in; uj.n_rows = (int)nr; uj.P = n_up;
                 uj.t_off = n0 + (it - 1) * n_up; uj.o_off = uj.t_off;
-                NA_TRY(launch_mlp_simt(uj, pk, L, scratch, scratch_bytes, stream));
+                NA_TRY(launch_mlp(uj, packed, cfg->precision, scratch, scratch_bytes, stream));
             }
             volsdf_sampler_kernel<<<it == 0 ? (unsigned)nr : (unsigned)grid_loop, SNT, samp_smem, stream>>>(sa, it);
             NA_CHECK_LAUNCH();
@@ -369,7 +367,7 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
         fj.rays_o = rays_o; fj.rays_d = dirs; fj.n_rows = (int)n_rays; fj.P = P; fj.t = d_all; fj.t_stride = P; fj.t_off = 0;
         fj.o_stride = P; fj.o_off = 0; fj.sdf = sdf_f; fj.rad = rad_f; fj.nab = nab_f;
         fj.apply_bg = 1; fj.bound_r = desc->bounding_radius; fj.want_full = 1; fj.multires_view = desc->multires_view;
-        NA_TRY(launch_mlp_simt(fj, pk, L, scratch, scratch_bytes, stream));
+        NA_TRY(launch_mlp(fj, packed, cfg->precision, scratch, scratch_bytes, stream));
         CompositeArgs ca = {};
         ca.d_all = d_all; ca.sdf = sdf_f; ca.rad = rad_f; ca.nab = out->normals ? nab_f : nullptr; ca.alpha_beta = alpha_beta;
         ca.P = P; ca.white_bkgd = cfg->white_bkgd; ca.n_rays = n_rays;

@@ -33,7 +33,8 @@ class NetEngine:
         self.packed = None
         self._ws = None
         self._dummy = None
-        self.precision = 'fp32'
+        from . import default_precision
+        self.precision = default_precision()
 
     # ------------------------------------------------------------------------------------------
     def _device(self):
