@@ -22,6 +22,9 @@ for s in $STEPS; do
     tccheck) timeout 600 python scripts/tc_check.py > $OUT/tc_check.log 2>&1; echo "tc check exit $?"; tail -30 $OUT/tc_check.log ;;
     testsfull) timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -40 $OUT/pytest_gpu.log ;;
     benchtc) NA_PRECISION=tc timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_tc.json 2> $OUT/bench_tc.err; echo "bench tc exit $?"; tail -c 3000 $OUT/bench_tc.json; tail -5 $OUT/bench_tc.err ;;
+    teststc) NA_PRECISION=tc timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu_tc.log 2>&1; echo "pytest tc exit $?"; tail -40 $OUT/pytest_gpu_tc.log ;;
+    ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_tc -c 2 -f -o $OUT/prof_mlp_tc python scripts/prof_mlp.py tc > $OUT/ncu_tc.log 2>&1; echo "ncu tc exit $?"; tail -3 $OUT/ncu_tc.log ;;
+    launchestc) NA_PRECISION=tc NA_BENCH_LIGHT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_tc.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_tc_bench.log 2>&1; echo "ncu launches exit $?"; tail -3 $OUT/launches_tc.csv ;;
     *) echo "unknown step $s" ;;
   esac
 done

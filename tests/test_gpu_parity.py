@@ -176,3 +176,41 @@ def test_volsdf_white_background_and_unbatched_layout():
     assert torch.equal(rgb0, rgb2[0])
     assert torch.allclose(rgb1, rgb0 + (1.0 - ex0['mask_volume'][..., None]), atol=1e-6)
     assert set(ex0.keys()) == {'rgb', 'depth_volume', 'mask_volume', 'normals_volume'}
+
+
+@pytest.mark.parametrize('name,bump', [('neus_det', 0.5), ('neus_basic', 0.0)])
+def test_neus_render_vs_reference_golden(name, bump):
+    """NeuS volume_render ('official_solution' upsampling) end to end.  The NeuS sampler has no threshold decisions, so
+    every ray must agree: rgb Linf 2e-4 (fp32 mode; 1e-3 in tensor-core mode), depth 2e-3, normals 2e-3, d_final median 2e-6."""
+    from nerfart_b200.models.frameworks.neus import volume_render
+    import nerfart_b200
+    G = golden(name)
+    m = make_neus(float(G['meta'][0]), bump, device=DEV)
+    with torch.no_grad():
+        rgb, depth, ex = volume_render(T(G['rays_o'])[None], T(G['rays_d'])[None], m, batched=True, obj_bounding_radius=1.0,
+                                       perturb=False, white_bkgd=False, calc_normal=True, detailed_output='d_final' in G,
+                                       rayschunk=2048, upsample_algo='official_solution', N_upsample_iters=4, N_outside=0)
+    out = {k: v[0].cpu().numpy() for k, v in ex.items()}
+    tc = nerfart_b200.default_precision() == 'tc'
+    rep = {k: linf(out[k], G[k]) for k in ('rgb', 'depth_volume', 'mask_volume', 'normals_volume')}
+    print(name, rep)
+    assert rep['rgb'] < (1e-3 if tc else 2e-4)
+    assert rep['depth_volume'] < (1e-2 if tc else 2e-3) and rep['mask_volume'] < (2e-3 if tc else 5e-4)
+    assert rep['normals_volume'] < (1e-2 if tc else 2e-3)
+    if 'd_final' in G:
+        assert np.median(np.abs(out['d_final'] - G['d_final'])) < (2e-5 if tc else 2e-6)
+        for k in ('implicit_surface', 'implicit_nablas', 'radiance', 'alpha', 'cdf', 'visibility_weights', 'd_final'):
+            assert out[k].shape == G[k].shape, k
+        assert linf(out['implicit_surface'], G['implicit_surface']) < (2e-3 if tc else 5e-4)
+
+
+def test_neus_render_is_ray_independent():
+    from nerfart_b200.models.frameworks.neus import volume_render
+    G = golden('neus_det')
+    m = make_neus(0.05, 0.5, device=DEV)
+    ro, rd = T(G['rays_o']), T(G['rays_d'])
+    with torch.no_grad():
+        a = volume_render(ro, rd, m, batched=False, calc_normal=True, detailed_output=False)[2]
+        b = volume_render(ro[11:222], rd[11:222], m, batched=False, calc_normal=True, detailed_output=False)[2]
+    for k in a:
+        assert torch.equal(a[k][11:222], b[k]), k
