@@ -17,17 +17,21 @@
 // as the A operand of the next layer.  Activations never leave the SM.
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace na {
 
 constexpr int TC_TM = 128;
-constexpr int TC_THREADS = 320;
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_THREADS = 576;
+constexpr int TC_EPI_THREADS = 512;
 constexpr int TC_NS = 4;                         // weight stages
 constexpr int STAGE_BYTES = 16384;               // 128 rows x 64 fp16
 constexpr int A_SPLIT_BYTES = 4 * STAGE_BYTES;   // 128 rows x 256 fp16
 constexpr float ACT_SCALE = 16.f;                // activations are stored x16 (keeps the lo term normal in fp16)
 constexpr int TC_MAX_GEMM = 24;
+#ifndef NA_TC_TWO_ACC
+#define NA_TC_TWO_ACC 1      // 1: hi*hi and the two correction products accumulate in separate TMEM accumulators (fewer truncations)
+#endif
 
 struct TcGemm { unsigned w_stage0; unsigned char n_kb, n_nh, pad0, pad1; };
 struct TcProgram { int n_gemm; TcGemm g[TC_MAX_GEMM]; };
@@ -90,7 +94,6 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -109,20 +112,37 @@ __device__ __forceinline__ unsigned a_off(int r, int k) {
     return (unsigned)((k >> 6) * STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + ((k & 7) << 1));
 }
 
+constexpr int N_BIAS_ROWS = 13;                  // 0..7 sdf fwd (x ACT_SCALE) | 8 feature (raw) | 9..12 radiance (x ACT_SCALE)
+
 struct __align__(1024) TcSmem {
     unsigned char A1[A_SPLIT_BYTES];
     unsigned char A2[A_SPLIT_BYTES];
     unsigned char Wst[TC_NS * STAGE_BYTES];
     unsigned long long full_bar[TC_NS], empty_bar[TC_NS], d_ready, a_ready;
     unsigned tmem_base;
+    __align__(16) float BIAS[N_BIAS_ROWS * 256];
+    __align__(16) float W8[256];                       // row 0 of SDF layer 8 (the sdf head)
+    __align__(16) float W4[3 * 256];     // radiance output layer
     float X[3 * TC_TM];
     float V[3 * TC_TM];
-    float PART[2 * 4 * TC_TM];           // column-half partial sums of the narrow heads
+    float PART[4 * 3 * TC_TM];           // per column-quarter partial sums of the narrow heads
     long long OIDX[TC_TM];
 };
 
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 // split 8 consecutive fp32 values (already x ACT_SCALE) into hi/lo fp16 and store 16 B + 16 B
-__device__ __forceinline__ void store8(unsigned char* A1, unsigned char* A2, int r, int k0, const float (&h)[8]) {
+__device__ __forceinline__ void store8(unsigned char* A1, unsigned char* A2, int r, int k0, const float* h) {
     __half2 hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -140,6 +160,147 @@ __device__ __forceinline__ float4* plane_ptr(float* sp, int p, int k4, int r) {
     return reinterpret_cast<float4*>(sp) + ((size_t)(p * 64 + k4) * TC_TM + r);
 }
 
+enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_RAD, K_RAD3 };
+
+struct EpiCtx {
+    TcSmem* S; float* sp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
+    unsigned t_row; int r, cq, g; float us; int sdim;
+};
+
+// one GEMM's epilogue for this thread's row and its 64 columns (4 chunks of 16)
+template <int KIND, bool FULL, bool TWO_ACC>
+__device__ __forceinline__ void epi_gemm(const EpiCtx& c, float& sdf_part, float (&rgb_part)[3], const float (&small_in)[36]) {
+    TcSmem& S = *c.S;
+    const int r = c.r;
+    const float us = c.us, us16 = c.us * ACT_SCALE;
+    const float* bias = S.BIAS + (KIND == K_FEAT ? 8 : (KIND >= K_RAD0 ? 9 + (c.g - 17) : c.g)) * 256;
+    const int bl = 16 - c.g;
+#pragma unroll 1
+    for (int c16 = 0; c16 < 4; ++c16) {
+        const int col0 = c.cq * 64 + c16 * 16;
+        if (KIND == K_BWD0 && col0 >= 48) break;                    // only 39 useful columns
+        unsigned v[16];
+        tmem_ld16(c.t_row + col0, v);
+        float acc[16];
+        if (TWO_ACC) {
+            unsigned v2[16];
+            tmem_ld16(c.t_row + 256 + col0, v2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+        } else {
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+        }
+        float o[16];
+        if (KIND == K_FWD || KIND == K_FWD3 || KIND == K_FWD7) {
+            // z16 = 16 z ; softplus_100(z) = max(z,0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e))
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                float dh[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = 4 * j4 + i;
+                    const float z16 = fmaf(acc[j], us16, bb[i]);
+                    const float t = ex2_approx(-fabsf(z16) * (100.f * 1.4426950408889634f / ACT_SCALE));
+                    const float u = 1.f + t;
+                    o[j] = fmaf(lg2_approx(u), ACT_SCALE * 0.6931471805599453f / 100.f, fmaxf(z16, 0.f));
+                    if (FULL) { const float ru = rcp_approx(u); dh[i] = z16 >= 0.f ? ru : t * ru; }
+                }
+                if (KIND == K_FWD3 && col0 + 4 * j4 + 3 >= SKIP_H) {
+                    // skip connection columns: h = emb[k-217] (x16), softplus' = 0
+                    const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = col0 + 4 * j4 + i;
+                        if (k >= SKIP_H) {
+                            const int ei = k - SKIP_H;
+                            float val;
+                            if (ei < 3) val = xs[ei];
+                            else { const int f = (ei - 3) / 6, rem = (ei - 3) % 6; float sn, cs; sincosf(__fmul_rn(xs[rem % 3], (float)(1 << f)), &sn, &cs); val = rem < 3 ? sn : cs; }
+                            o[4 * j4 + i] = val * ACT_SCALE; dh[i] = 0.f;
+                        }
+                    }
+                }
+                if (FULL) *plane_ptr(c.sp, c.g, (col0 >> 2) + j4, r) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+            }
+            if (KIND == K_FWD7) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sdf_part = fmaf(o[j], S.W8[col0 + j], sdf_part);
+            }
+        } else if (KIND == K_FEAT) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
+                const float4 f4 = make_float4(fmaf(acc[4 * j4], us, b4.x), fmaf(acc[4 * j4 + 1], us, b4.y),
+                                              fmaf(acc[4 * j4 + 2], us, b4.z), fmaf(acc[4 * j4 + 3], us, b4.w));
+                if (FULL) *plane_ptr(c.sp, 8, (col0 >> 2) + j4, r) = f4;
+                if (c.job->feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(c.job->feat + S.OIDX[r] * 256 + col0) + j4) = f4;
+                if (FULL) {
+                    // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
+                    const float4 d4 = *plane_ptr(c.sp, 7, (col0 >> 2) + j4, r);
+                    o[4 * j4] = S.W8[col0 + 4 * j4] * d4.x * ACT_SCALE; o[4 * j4 + 1] = S.W8[col0 + 4 * j4 + 1] * d4.y * ACT_SCALE;
+                    o[4 * j4 + 2] = S.W8[col0 + 4 * j4 + 2] * d4.z * ACT_SCALE; o[4 * j4 + 3] = S.W8[col0 + 4 * j4 + 3] * d4.w * ACT_SCALE;
+                }
+            }
+        } else if (KIND == K_BWD || KIND == K_BWD4) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 d4 = *plane_ptr(c.sp, bl - 1, (col0 >> 2) + j4, r);
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = col0 + 4 * j4 + i;
+                    if (KIND == K_BWD4 && k >= SKIP_H) c.misc[r * 80 + (k - SKIP_H)] = acc[4 * j4 + i] * us;      // embedding branch of the skip
+                    o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
+                }
+            }
+        } else if (KIND == K_BWD0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[r * 80 + k] += acc[j] * us; }
+        } else {
+            // radiance hidden layers: relu(16 z)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = col0 + 4 * j4 + i;
+                    float z = fmaf(acc[4 * j4 + i], us16, bb[i]);
+                    if (KIND == K_RAD0) {
+                        // small inputs [x | embed(view) | nabla] (x16) in fp32: rows 256.. of the packed layer-0 plane
+                        const float* wsm = c.pk + c.L->rad_wt[0] + (size_t)256 * 256 + k;
+                        if (c.sdim == 9) {
+#pragma unroll
+                            for (int j = 0; j < 9; ++j) z = fmaf(small_in[j], __ldg(wsm + j * 256), z);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 33; ++j) z = fmaf(small_in[j], __ldg(wsm + j * 256), z);
+                        }
+                    }
+                    o[4 * j4 + i] = fmaxf(z, 0.f);
+                }
+            }
+            if (KIND == K_RAD3) {
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rgb_part[cc] = fmaf(o[j], S.W4[cc * 256 + col0 + j], rgb_part[cc]);
+            }
+        }
+        const bool store = !(KIND == K_BWD0 || KIND == K_RAD3 || (KIND == K_FWD7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL));
+        if (store) {
+            store8(S.A1, S.A2, r, col0, o);
+            store8(S.A1, S.A2, r, col0 + 8, o + 8);
+        }
+    }
+}
+
+template <bool FULL, bool TWO_ACC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wtc,
               const float* __restrict__ unscale, const TcProgram prog, float* __restrict__ scratch) {
@@ -157,7 +318,18 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
         mbar_init(smem_u32(&S.a_ready), TC_EPI_THREADS);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), 256);
+    if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), TWO_ACC ? 512 : 256);
+    // bias rows and head weights -> shared memory (hidden-layer biases pre-multiplied by ACT_SCALE)
+    for (int i = tid; i < N_BIAS_ROWS * 256; i += TC_THREADS) {
+        const int row = i >> 8, k = i & 255;
+        float b;
+        if (row < 8) b = pk[L.sdf_b[row] + k] * ACT_SCALE;
+        else if (row == 8) b = pk[L.b8_feat + k];
+        else b = pk[L.rad_b[row - 9] + k] * ACT_SCALE;
+        S.BIAS[i] = b;
+    }
+    for (int i = tid; i < 256; i += TC_THREADS) S.W8[i] = pk[L.w8_sdf + i];
+    for (int i = tid; i < 768; i += TC_THREADS) S.W4[i] = pk[L.rad_w4 + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -196,17 +368,18 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
                                 mbar_wait(smem_u32(&S.full_bar[slot]), ph);
                                 tc_fence_after();
                                 const unsigned d = tmem_d + nh * 128;
+                                const unsigned dc = TWO_ACC ? d + 256 : d;        // accumulator of the two correction products
                                 const unsigned long long bd = umma_desc(wst + slot * STAGE_BYTES);
                                 const unsigned long long ad1 = umma_desc(a1 + kb * STAGE_BYTES);
                                 const unsigned long long ad2 = umma_desc(a2 + kb * STAGE_BYTES);
                                 if (s == 0) {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, (kb | ks) != 0);   // hi * hi
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, (kb | ks) != 0);                    // hi * hi
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad2 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                // lo * hi
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(dc, ad2 + 2 * ks, bd + 2 * ks, UMMA_IDESC, TWO_ACC ? (kb | ks) != 0 : 1);    // lo * hi
                                 } else {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                // hi * lo
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(dc, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                                 // hi * lo
                                 }
                                 umma_commit(smem_u32(&S.empty_bar[slot]));
                             }
@@ -215,19 +388,19 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
         }
     } else {
         // ================= epilogue warps =================
-        const int q = warp & 3, ch = (warp - 2) >> 2;
+        const int q = warp & 3, cq = (warp - 2) >> 2;
         const int r = 32 * q + lane;                       // sample row == TMEM lane
-        const int e = tid - 64;                            // 0..255 epilogue thread index
-        const unsigned t_row = tmem_d + ((unsigned)(32 * q) << 16);
         float* sp = scratch + (size_t)blockIdx.x * (10 * 256 * TC_TM);     // planes 0..7 softplus', 8 feature, 9 misc rows
-        float* misc = sp + (size_t)9 * 256 * TC_TM;                        // [row][80]: d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
-        const int sdim = small_dim(job.multires_view);
+        EpiCtx c;
+        c.S = &S; c.sp = sp; c.misc = sp + (size_t)9 * 256 * TC_TM;       // misc [row][80]: d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
+        c.pk = pk; c.L = &L; c.job = &job; c.t_row = tmem_d + ((unsigned)(32 * q) << 16); c.r = r; c.cq = cq;
+        c.sdim = small_dim(job.multires_view);
         unsigned d_phase = 0;
-        const bool full = job.want_full != 0, has_rad = job.rad != nullptr;
+        const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // ---- tile inputs: point, encoding (x ACT_SCALE, hi/lo) into K-block 0 ----------------------------------
-            if (ch == 0) {
+            if (cq == 0) {
                 const long long w = tile * TC_TM + r;
                 float x0 = 0.f, x1 = 0.f, x2 = 0.f, v0 = 0.f, v1 = 0.f, v2 = 1.f;
                 long long oidx = -1;
@@ -255,175 +428,59 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
                 float emb[64];
                 const float xs[3] = {x0, x1, x2};
 #pragma unroll
-                for (int c = 0; c < 3; ++c) emb[c] = xs[c] * ACT_SCALE;
+                for (int cc = 0; cc < 3; ++cc) emb[cc] = xs[cc] * ACT_SCALE;
 #pragma unroll
                 for (int f = 0; f < 6; ++f)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float sn, cs; sincosf(__fmul_rn(xs[c], (float)(1 << f)), &sn, &cs);
-                        emb[3 + 6 * f + c] = sn * ACT_SCALE; emb[6 + 6 * f + c] = cs * ACT_SCALE;
+                    for (int cc = 0; cc < 3; ++cc) {
+                        float sn, cs; sincosf(__fmul_rn(xs[cc], (float)(1 << f)), &sn, &cs);
+                        emb[3 + 6 * f + cc] = sn * ACT_SCALE; emb[6 + 6 * f + cc] = cs * ACT_SCALE;
                     }
 #pragma unroll
                 for (int k = EMB; k < 64; ++k) emb[k] = 0.f;
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    float h8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) h8[i] = emb[8 * c8 + i];
-                    store8(S.A1, S.A2, r, 8 * c8, h8);
-                }
+                for (int c8 = 0; c8 < 8; ++c8) store8(S.A1, S.A2, r, 8 * c8, emb + 8 * c8);
             }
             fence_proxy_async();
             mbar_arrive(smem_u32(&S.a_ready));
 
             float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
+            float small_in[36];
             for (int g = 0; g < prog.n_gemm; ++g) {
                 mbar_wait(smem_u32(&S.d_ready), d_phase); d_phase ^= 1;
                 tc_fence_after();
-                const float us = unscale[g];                      // 2^-(weight shift) / ACT_SCALE
-                // which epilogue?  program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
-                const bool is_fwd = g < 8, is_feat = g == 8, is_bwd = g >= 9 && g <= 15, is_bwd0 = g == 16, is_rad = g >= 17;
-                const int rl = g - 17;                            // radiance layer
-                const int bl = 16 - g;                            // backward: d sdf / d (input of layer bl)
-                const float* bias = is_fwd ? pk + L.sdf_b[g] : is_feat ? pk + L.b8_feat : is_rad ? pk + L.rad_b[rl] : nullptr;
-                float small_in[36];
-                if (is_rad && rl == 0) {
+                c.g = g; c.us = unscale[g];                      // us = 2^-(weight shift) / ACT_SCALE
+                // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
+                if (g < 8) {
+                    if (g == 3) epi_gemm<K_FWD3, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                    else if (g == 7) epi_gemm<K_FWD7, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                    else epi_gemm<K_FWD, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                } else if (g == 8) {
+                    epi_gemm<K_FEAT, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                } else if (FULL) {
+                    if (g <= 15) {
+                        if (g == 12) epi_gemm<K_BWD4, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                        else epi_gemm<K_BWD, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                    } else if (g == 16) {
+                        epi_bar_sync();                                   // embedding-branch gradients (written at g == 12 by other threads)
+                        if (cq == 0) epi_gemm<K_BWD0, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                    } else if (g == 17) {
 #pragma unroll
-                    for (int j = 0; j < 36; ++j) small_in[j] = j < sdim ? misc[r * 80 + 40 + j] : 0.f;
-                }
-                if (is_bwd0) epi_bar_sync();
-                if (!(is_bwd0 && ch == 1)) {
-#pragma unroll 1
-                    for (int c32 = 0; c32 < 4; ++c32) {
-                        const int col0 = ch * 128 + c32 * 32;
-                        unsigned v[32];
-                        tmem_ld32(t_row + col0, v);
-                        float o[32];
-                        if (is_fwd) {
-                            // z16 = 16 z ; softplus_100(z) = max(z,0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e))
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
-                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                                float dh[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int j = 4 * j4 + i;
-                                    const float z16 = fmaf(__uint_as_float(v[j]), us * ACT_SCALE, bb[i] * ACT_SCALE);
-                                    const float t = ex2_approx(-fabsf(z16) * (100.f * 1.4426950408889634f / ACT_SCALE));
-                                    const float u = 1.f + t;
-                                    o[j] = fmaf(lg2_approx(u), ACT_SCALE * 0.6931471805599453f / 100.f, fmaxf(z16, 0.f));
-                                    const float ru = rcp_approx(u);
-                                    dh[i] = z16 >= 0.f ? ru : t * ru;
-                                }
-                                if (g == 3 && col0 + 4 * j4 + 3 >= SKIP_H) {
-                                    // skip connection columns: h = emb[k-217] (x16), softplus' = 0
-                                    const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        const int k = col0 + 4 * j4 + i;
-                                        if (k >= SKIP_H) {
-                                            const int ei = k - SKIP_H;
-                                            float val;
-                                            if (ei < 3) val = xs[ei];
-                                            else { const int f = (ei - 3) / 6, rem = (ei - 3) % 6; float sn, cs; sincosf(__fmul_rn(xs[rem % 3], (float)(1 << f)), &sn, &cs); val = rem < 3 ? sn : cs; }
-                                            o[4 * j4 + i] = val * ACT_SCALE; dh[i] = 0.f;
-                                        }
-                                    }
-                                }
-                                if (full) *plane_ptr(sp, g, (col0 >> 2) + j4, r) = make_float4(dh[0], dh[1], dh[2], dh[3]);
-                            }
-                            if (g == 7) {
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; ++j4) {
-                                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(pk + L.w8_sdf + col0) + j4);
-                                    sdf_part = fmaf(o[4 * j4], w4.x, sdf_part); sdf_part = fmaf(o[4 * j4 + 1], w4.y, sdf_part);
-                                    sdf_part = fmaf(o[4 * j4 + 2], w4.z, sdf_part); sdf_part = fmaf(o[4 * j4 + 3], w4.w, sdf_part);
-                                }
-                            }
-                        } else if (is_feat) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
-                                const float4 f4 = make_float4(fmaf(__uint_as_float(v[4 * j4]), us, b4.x), fmaf(__uint_as_float(v[4 * j4 + 1]), us, b4.y),
-                                                              fmaf(__uint_as_float(v[4 * j4 + 2]), us, b4.z), fmaf(__uint_as_float(v[4 * j4 + 3]), us, b4.w));
-                                *plane_ptr(sp, 8, (col0 >> 2) + j4, r) = f4;
-                                if (job.feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(job.feat + S.OIDX[r] * 256 + col0) + j4) = f4;
-                                // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
-                                const float4 w4 = __ldg(reinterpret_cast<const float4*>(pk + L.w8_sdf + col0) + j4);
-                                const float4 d4 = *plane_ptr(sp, 7, (col0 >> 2) + j4, r);
-                                o[4 * j4] = w4.x * d4.x * ACT_SCALE; o[4 * j4 + 1] = w4.y * d4.y * ACT_SCALE;
-                                o[4 * j4 + 2] = w4.z * d4.z * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4.w * ACT_SCALE;
-                            }
-                        } else if (is_bwd) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 d4 = *plane_ptr(sp, bl - 1, (col0 >> 2) + j4, r);
-                                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float gval = __uint_as_float(v[4 * j4 + i]) * us;
-                                    const int k = col0 + 4 * j4 + i;
-                                    if (bl == 4 && k >= SKIP_H) misc[r * 80 + (k - SKIP_H)] = gval;      // embedding branch of the skip
-                                    o[4 * j4 + i] = gval * dd[i] * ACT_SCALE;
-                                }
-                            }
-                        } else if (is_bwd0) {
-                            // d sdf / d emb: 39 useful columns, all inside the first 64
-                            if (c32 < 2) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) { const int k = col0 + j; if (k < EMB) misc[r * 80 + k] += __uint_as_float(v[j]) * us; }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + j4);
-                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int k = col0 + 4 * j4 + i;
-                                    float z = fmaf(__uint_as_float(v[4 * j4 + i]), us, bb[i]);
-                                    if (rl == 0) {
-                                        // small inputs [x | embed(view) | nabla] in fp32: rows 256.. of the packed layer-0 plane
-                                        const float* wsm = pk + L.rad_wt[0] + (size_t)256 * 256 + k;
-                                        if (sdim == 9) {
-#pragma unroll
-                                            for (int j = 0; j < 9; ++j) z = fmaf(small_in[j], __ldg(wsm + j * 256), z);
-                                        } else {
-#pragma unroll
-                                            for (int j = 0; j < 33; ++j) z = fmaf(small_in[j], __ldg(wsm + j * 256), z);
-                                        }
-                                    }
-                                    o[4 * j4 + i] = fmaxf(z, 0.f);
-                                }
-                            }
-                            if (rl == 3) {
-#pragma unroll
-                                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) rgb_part[c] = fmaf(o[j], __ldg(pk + L.rad_w4 + c * 256 + col0 + j), rgb_part[c]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) o[j] *= ACT_SCALE;
-                        }
-                        if (!is_bwd0 && !(is_rad && rl == 3) && !(g == 7 && !full && !job.feat)) {
-#pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) {
-                                float h8[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) h8[i] = o[8 * c8 + i];
-                                store8(S.A1, S.A2, r, col0 + 8 * c8, h8);
-                            }
-                        }
+                        for (int j = 0; j < 36; ++j) small_in[j] = j < c.sdim ? c.misc[r * 80 + 40 + j] * ACT_SCALE : 0.f;
+                        epi_gemm<K_RAD0, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                    } else if (g == 20) {
+                        epi_gemm<K_RAD3, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                    } else {
+                        epi_gemm<K_RAD, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
                     }
                 }
                 // ---- per-GEMM tails ------------------------------------------------------------------------
                 if (g == 7) {
                     // fwd layer 7 stored h8 x16: undo in the head.  sdf = <h8, W8[0]> + b8[0]
-                    S.PART[ch * TC_TM + r] = sdf_part * (1.f / ACT_SCALE); sdf_part = 0.f;
+                    S.PART[cq * TC_TM + r] = sdf_part * (1.f / ACT_SCALE); sdf_part = 0.f;
                     epi_bar_sync();
-                    if (ch == 0) {
-                        float sdf = S.PART[r] + S.PART[TC_TM + r] + __ldg(pk + L.b8_sdf);
+                    if (cq == 0) {
+                        float sdf = S.PART[r] + S.PART[TC_TM + r] + S.PART[2 * TC_TM + r] + S.PART[3 * TC_TM + r] + __ldg(pk + L.b8_sdf);
                         if (job.apply_bg) {
                             const float x0 = S.X[r], x1 = S.X[TC_TM + r], x2 = S.X[2 * TC_TM + r];
                             const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
@@ -432,64 +489,67 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
                         if (S.OIDX[r] >= 0 && job.sdf) job.sdf[S.OIDX[r]] = sdf;
                     }
                 }
-                if (is_bwd0) {
-                    if (ch == 0) {
+                if (FULL && g == 16) {
+                    if (cq == 0) {
                         // nabla and the fp32 small radiance inputs
                         const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
                         float nb[3];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float n = misc[r * 80 + c];
+                        for (int cc = 0; cc < 3; ++cc) {
+                            float n = c.misc[r * 80 + cc];
 #pragma unroll
                             for (int f = 0; f < 6; ++f) {
                                 const float fr = (float)(1 << f);
-                                float sn, cs; sincosf(__fmul_rn(xs[c], fr), &sn, &cs);
-                                n += fr * (misc[r * 80 + 3 + 6 * f + c] * cs - misc[r * 80 + 6 + 6 * f + c] * sn);
+                                float sn, cs; sincosf(__fmul_rn(xs[cc], fr), &sn, &cs);
+                                n += fr * (c.misc[r * 80 + 3 + 6 * f + cc] * cs - c.misc[r * 80 + 6 + 6 * f + cc] * sn);
                             }
-                            nb[c] = n;
+                            nb[cc] = n;
                         }
                         const long long oo = S.OIDX[r];
                         if (oo >= 0 && job.nab) { job.nab[oo * 3] = nb[0]; job.nab[oo * 3 + 1] = nb[1]; job.nab[oo * 3 + 2] = nb[2]; }
                         if (has_rad) {
-                            float* sm = misc + r * 80 + 40;
+                            float* sm = c.misc + r * 80 + 40;
                             int qn = 0;
-                            for (int c = 0; c < 3; ++c) sm[qn++] = xs[c];
+                            for (int cc = 0; cc < 3; ++cc) sm[qn++] = xs[cc];
                             const float vs[3] = {S.V[r], S.V[TC_TM + r], S.V[2 * TC_TM + r]};
-                            for (int c = 0; c < 3; ++c) sm[qn++] = vs[c];
+                            for (int cc = 0; cc < 3; ++cc) sm[qn++] = vs[cc];
                             for (int f = 0; f < job.multires_view; ++f) {
                                 float sn[3], cs[3];
-                                for (int c = 0; c < 3; ++c) sincosf(__fmul_rn(vs[c], (float)(1 << f)), &sn[c], &cs[c]);
-                                for (int c = 0; c < 3; ++c) sm[qn++] = sn[c];
-                                for (int c = 0; c < 3; ++c) sm[qn++] = cs[c];
+                                for (int cc = 0; cc < 3; ++cc) sincosf(__fmul_rn(vs[cc], (float)(1 << f)), &sn[cc], &cs[cc]);
+                                for (int cc = 0; cc < 3; ++cc) sm[qn++] = sn[cc];
+                                for (int cc = 0; cc < 3; ++cc) sm[qn++] = cs[cc];
                             }
-                            for (int c = 0; c < 3; ++c) sm[qn++] = nb[c];
+                            for (int cc = 0; cc < 3; ++cc) sm[qn++] = nb[cc];
                         }
                     }
                     if (has_rad) {
                         // A <- geometry feature (x16) for radiance layer 0
 #pragma unroll 1
-                        for (int c32 = 0; c32 < 4; ++c32) {
-                            const int col0 = ch * 128 + c32 * 32;
+                        for (int c16 = 0; c16 < 4; ++c16) {
+                            const int col0 = cq * 64 + c16 * 16;
+                            float h[16];
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) {
-                                const float4 f0 = *plane_ptr(sp, 8, (col0 >> 2) + 2 * c8, r), f1 = *plane_ptr(sp, 8, (col0 >> 2) + 2 * c8 + 1, r);
-                                const float h8[8] = {f0.x * ACT_SCALE, f0.y * ACT_SCALE, f0.z * ACT_SCALE, f0.w * ACT_SCALE,
-                                                     f1.x * ACT_SCALE, f1.y * ACT_SCALE, f1.z * ACT_SCALE, f1.w * ACT_SCALE};
-                                store8(S.A1, S.A2, r, col0 + 8 * c8, h8);
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 f4 = *plane_ptr(sp, 8, (col0 >> 2) + j4, r);
+                                h[4 * j4] = f4.x * ACT_SCALE; h[4 * j4 + 1] = f4.y * ACT_SCALE; h[4 * j4 + 2] = f4.z * ACT_SCALE; h[4 * j4 + 3] = f4.w * ACT_SCALE;
                             }
+                            store8(S.A1, S.A2, r, col0, h);
+                            store8(S.A1, S.A2, r, col0 + 8, h + 8);
                         }
-                        epi_bar_sync();                       // small inputs written by ch==0 threads are read by both halves next
+                        epi_bar_sync();                       // small inputs written by cq == 0 threads are read by all four next
                     }
                 }
-                if (is_rad && rl == 3) {
+                if (FULL && g == 20) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) { S.PART[(ch * 4 + c) * TC_TM + r] = rgb_part[c]; rgb_part[c] = 0.f; }
+                    for (int cc = 0; cc < 3; ++cc) { S.PART[(cq * 3 + cc) * TC_TM + r] = rgb_part[cc]; rgb_part[cc] = 0.f; }
                     epi_bar_sync();
-                    if (ch == 0 && S.OIDX[r] >= 0) {
+                    if (cq == 0 && S.OIDX[r] >= 0) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float z = S.PART[c * TC_TM + r] + S.PART[(4 + c) * TC_TM + r] + __ldg(pk + L.rad_b4 + c);
-                            job.rad[S.OIDX[r] * 3 + c] = __fdiv_rn(1.f, 1.f + expf(-z));
+                        for (int cc = 0; cc < 3; ++cc) {
+                            // radiance layer 3 stored relu x16: undo in the head
+                            const float z = (S.PART[cc * TC_TM + r] + S.PART[(3 + cc) * TC_TM + r] + S.PART[(6 + cc) * TC_TM + r] + S.PART[(9 + cc) * TC_TM + r])
+                                            * (1.f / ACT_SCALE) + __ldg(pk + L.rad_b4 + cc);
+                            job.rad[S.OIDX[r] * 3 + cc] = __fdiv_rn(1.f, 1.f + expf(-z));
                         }
                     }
                 }
@@ -506,7 +566,7 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 256); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, TWO_ACC ? 512 : 256); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,9 +660,13 @@ size_t mlp_tc_scratch_bytes(int grid) { return (size_t)grid * 10 * 256 * TC_TM *
 int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
                   size_t scratch_bytes, cudaStream_t stream) {
     static thread_local bool attr_set = false;
+    static const bool two = []{ const char* e = getenv("NA_TC_TWO_ACC"); return e ? atoi(e) != 0 : (NA_TC_TWO_ACC != 0); }();
     const size_t smem = sizeof(TcSmem) + 1024;
     if (!attr_set) {
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_set = true;
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
@@ -615,8 +679,15 @@ int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f
     long long tiles = (total + TC_TM - 1) / TC_TM;
     int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
     if (scratch_bytes < mlp_tc_scratch_bytes(grid)) return NA_ERR_WORKSPACE;
-    mlp_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(job, (const float*)packed_base, L, packed_base + T.wtc_off,
-                                                       (const float*)(packed_base + T.unscale_off), prog, scratch);
+    const float* pkf = (const float*)packed_base; const unsigned char* wtc = packed_base + T.wtc_off;
+    const float* usc = (const float*)(packed_base + T.unscale_off);
+    if (job.want_full) {
+        if (two) mlp_tc_kernel<true, true><<<grid, TC_THREADS, smem, stream>>>(job, pkf, L, wtc, usc, prog, scratch);
+        else     mlp_tc_kernel<true, false><<<grid, TC_THREADS, smem, stream>>>(job, pkf, L, wtc, usc, prog, scratch);
+    } else {
+        if (two) mlp_tc_kernel<false, true><<<grid, TC_THREADS, smem, stream>>>(job, pkf, L, wtc, usc, prog, scratch);
+        else     mlp_tc_kernel<false, false><<<grid, TC_THREADS, smem, stream>>>(job, pkf, L, wtc, usc, prog, scratch);
+    }
     NA_CHECK_LAUNCH();
     return NA_OK;
 }

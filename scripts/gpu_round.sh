@@ -19,7 +19,8 @@ for s in $STEPS; do
     ncu) NA_BENCH_LIGHT=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_ -s 4 -c 2 -f -o $OUT/prof_mlp python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "ncu full exit $?"; ls -la $OUT/ ;;
     tcsmall) timeout 180 python scripts/tc_check.py small > $OUT/tc_small.log 2>&1; echo "tc small exit $?"; tail -20 $OUT/tc_small.log ;;
     tcsan) timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/tc_check.py small > $OUT/tc_san.log 2>&1; echo "tc sanitize exit $?"; tail -30 $OUT/tc_san.log ;;
-    tccheck) timeout 600 python scripts/tc_check.py > $OUT/tc_check.log 2>&1; echo "tc check exit $?"; tail -30 $OUT/tc_check.log ;;
+    tccheck) timeout 600 python scripts/tc_check.py > $OUT/tc_check.log 2>&1; echo "tc check exit $?"; tail -14 $OUT/tc_check.log ;;
+    tccheck1) NA_TC_TWO_ACC=0 timeout 600 python scripts/tc_check.py > $OUT/tc_check_oneacc.log 2>&1; echo "tc check (one acc) exit $?"; tail -14 $OUT/tc_check_oneacc.log ;;
     testsfull) timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -40 $OUT/pytest_gpu.log ;;
     benchtc) NA_PRECISION=tc timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_tc.json 2> $OUT/bench_tc.err; echo "bench tc exit $?"; tail -c 3000 $OUT/bench_tc.json; tail -5 $OUT/bench_tc.err ;;
     teststc) NA_PRECISION=tc timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu_tc.log 2>&1; echo "pytest tc exit $?"; tail -40 $OUT/pytest_gpu_tc.log ;;
