@@ -178,10 +178,9 @@ def main():
     c2w_h, K_h = make_inputs()
     c2w_pin, K_pin = c2w_h[None].pin_memory(), K_h[None].pin_memory()
     n_rays = H * W
-    per = (n_rays + world - 1) // world
-    lo, hi = min(rank * per, n_rays), min((rank + 1) * per, n_rays)
+    from nerfart_b200 import parallel
+    lo, hi, per = parallel.ray_block(n_rays, rank, world)
     rgb_host = torch.empty(n_rays, 3, dtype=torch.float32).pin_memory()
-    gathered = torch.empty(world * per, 3, device=dev)
 
     def step(e2e):
         with torch.no_grad():
@@ -191,12 +190,7 @@ def main():
                 step.rays = (ro, rd)
             ro, rd = step.rays
             rgb, depth, ex = volume_render(ro[:, lo:hi], rd[:, lo:hi], model, **RENDER_KW)
-            if world > 1:
-                tile = torch.zeros(per, 3, device=dev); tile[:hi - lo] = rgb[0]
-                dist.all_gather_into_tensor(gathered, tile)
-                img = gathered[:n_rays]
-            else:
-                img = rgb[0]
+            img = parallel.gather_tiles(rgb[0], n_rays)        # NCCL all-gather of the RGB tiles (no-op at world 1)
             if e2e:
                 rgb_host.copy_(img, non_blocking=True)
         return img
@@ -284,7 +278,7 @@ def main():
         samples = n_rays * P * args.steps
         line = {'metric': 'MLP samples/sec (VolSDF 480x270x128)', 'value': samples / t_dev, 'unit': 'samples/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
-                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16x3-split (fp32-equivalent) / f32 accumulate',
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'f16x2-split operands (22-bit), f32 accumulate',
                 'data': 'synthetic', 'config': workload_config(args),
                 'all_evals_per_s': n_rays * (4 * N_SAMPLES + P) * args.steps / t_dev,
                 'e2e': {'value': samples / t_e2e, 'unit': 'samples/s', 'ms_per_step': 1e3 * t_e2e / args.steps,

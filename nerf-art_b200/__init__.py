@@ -15,4 +15,4 @@ from ._lib import build, lib, launch_count           # noqa: F401
 def default_precision():
     """Arithmetic mode of the per-sample networks: 'tc' (tcgen05 tensor cores, split-fp16 operands, fp32 accumulate) or
     'fp32' (CUDA cores).  Override with NA_PRECISION=fp32|tc."""
-    return os.environ.get('NA_PRECISION', 'fp32')
+    return os.environ.get('NA_PRECISION', 'tc')
