@@ -116,7 +116,8 @@ typedef struct NaNeusOut {                /* neus.py:385-407 */
 int         na_version(void);
 const char* na_error_string(int code);
 int         na_last_cuda_error(void);                 /* cudaError_t of the last NA_ERR_CUDA on this thread */
-int64_t     na_kernel_launch_count(void);             /* kernels launched by this library since load (bench "gpu_launches") */
+int64_t     na_kernel_launch_count(void);
+int         na_debug_set_buffer(void* dev_int64x8);   /* diagnostics: cycle counters of CTA 0 of the tensor-core MLP kernel */             /* kernels launched by this library since load (bench "gpu_launches") */
 
 /* ---- weights: replaces nn.utils.weight_norm's per-forward W = g*v/||v|| (models/base.py:226-227,365-366) */
 size_t na_packed_weights_bytes(const NaNetDesc* desc);

@@ -30,6 +30,7 @@ int tc_pack(const float* pk_f32, const PackF32& L, unsigned char* base, const Tc
 int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
                   size_t scratch_bytes, cudaStream_t stream);
 size_t mlp_tc_scratch_bytes(int grid);
+extern long long* g_tc_dbg;
 
 size_t packed_f32_bytes(int multires_view) {
     const PackF32 L = pack_layout_f32(multires_view);
@@ -106,6 +107,8 @@ __global__ void pack_fill_kernel(const NaRawParams raw, const FillTable tab, con
 using namespace na;
 
 extern "C" int na_version(void) { return 100; }
+// diagnostics only: device buffer of >= 8 int64 that mlp_tc_kernel fills with cycle counters of CTA 0 (NULL disables)
+extern "C" int na_debug_set_buffer(void* dev_ptr) { g_tc_dbg = (long long*)dev_ptr; return NA_OK; }
 extern "C" const char* na_error_string(int code) {
     switch (code) {
         case NA_OK: return "ok";

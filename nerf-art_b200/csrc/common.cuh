@@ -89,6 +89,7 @@ struct EvalJob {
     int   apply_bg;  float bound_r;                  // VolSDF sphere background
     int   want_full;                                 // 0: SDF only; 1: + nablas (+ radiance if rad != nullptr)
     int   multires_view;
+    long long* dbg;                                  // optional cycle counters (na_debug_set_buffer), else nullptr
 };
 
 }  // namespace na

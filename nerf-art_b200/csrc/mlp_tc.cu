@@ -94,6 +94,11 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -118,7 +123,7 @@ struct __align__(1024) TcSmem {
     unsigned char A1[A_SPLIT_BYTES];
     unsigned char A2[A_SPLIT_BYTES];
     unsigned char Wst[TC_NS * STAGE_BYTES];
-    unsigned long long full_bar[TC_NS], empty_bar[TC_NS], d_ready, a_ready;
+    unsigned long long full_bar[TC_NS], empty_bar[TC_NS], d_ready, kb_ready[4];   // kb_ready[k]: A K-block k written AND D columns [64k,64k+64) drained
     unsigned tmem_base;
     __align__(16) float BIAS[N_BIAS_ROWS * 256];
     __align__(16) float W8[256];                       // row 0 of SDF layer 8 (the sdf head)
@@ -141,6 +146,27 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ float lds32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts128(unsigned addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// split 8 consecutive fp32 values (already x ACT_SCALE) into hi/lo fp16 and store 16 B + 16 B into the A operand.
+// a1 / a2: shared-space byte addresses of the hi / lo split buffers; row_off = (r/8)*1024 + (r%8)*128, sw = r%8
+__device__ __forceinline__ void store8s(unsigned a1, unsigned a2, unsigned row_off, unsigned sw, int k0, const float* h) {
+    __half2 hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hi[i] = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+        const float2 back = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(h[2 * i] - back.x, h[2 * i + 1] - back.y);
+    }
+    const unsigned off = (unsigned)(k0 >> 6) * STAGE_BYTES + row_off + (((unsigned)((k0 & 63) >> 3) ^ sw) << 4);
+    sts128(a1 + off, *reinterpret_cast<const uint4*>(hi));
+    sts128(a2 + off, *reinterpret_cast<const uint4*>(lo));
+}
 // split 8 consecutive fp32 values (already x ACT_SCALE) into hi/lo fp16 and store 16 B + 16 B
 __device__ __forceinline__ void store8(unsigned char* A1, unsigned char* A2, int r, int k0, const float* h) {
     __half2 hi[4], lo[4];
@@ -165,7 +191,17 @@ enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_R
 struct EpiCtx {
     TcSmem* S; float* sp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
     unsigned t_row; int r, cq, g; float us; int sdim;
+    unsigned a1, a2, row_off, sw, bias_s, w8_s, w4_s;      // shared-space byte addresses
+    unsigned kb_bar; int signal, lane;                     // kb_ready[0] address; arrive after every 64-column group?
 };
+
+// this warp's part of A K-block kb is written and its part of D columns [64kb, 64kb+64) is drained
+__device__ __forceinline__ void signal_kb(unsigned kb_bar, int kb, int lane) {
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(kb_bar + 8u * (unsigned)kb);
+}
 
 // one GEMM's epilogue for this thread's row and its 64 columns (4 chunks of 16)
 template <int KIND, bool FULL, bool TWO_ACC>
@@ -173,12 +209,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, float& sdf_part, float
     TcSmem& S = *c.S;
     const int r = c.r;
     const float us = c.us, us16 = c.us * ACT_SCALE;
-    const float* bias = S.BIAS + (KIND == K_FEAT ? 8 : (KIND >= K_RAD0 ? 9 + (c.g - 17) : c.g)) * 256;
+    const unsigned bias = c.bias_s + (unsigned)(KIND == K_FEAT ? 8 : (KIND >= K_RAD0 ? 9 + (c.g - 17) : c.g)) * 1024u;
     const int bl = 16 - c.g;
 #pragma unroll 1
     for (int c16 = 0; c16 < 4; ++c16) {
-        const int col0 = c.cq * 64 + c16 * 16;
-        if (KIND == K_BWD0 && col0 >= 48) break;                    // only 39 useful columns
+        // thread = (row, column quarter cq): in pass c16 it owns columns 64*c16 + 16*cq .. +16, i.e. every pass completes one
+        // 64-wide K-block of the next layer's A operand across the 16 epilogue warps
+        const int col0 = c16 * 64 + c.cq * 16;
+        if (KIND == K_BWD0 && c16 > 0) break;                       // only 39 useful columns, all in pass 0
         unsigned v[16];
         tmem_ld16(c.t_row + col0, v);
         float acc[16];
@@ -195,46 +233,61 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, float& sdf_part, float
         }
         float o[16];
         if (KIND == K_FWD || KIND == K_FWD3 || KIND == K_FWD7) {
-            // z16 = 16 z ; softplus_100(z) = max(z,0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e))
+            // z16 = 16 z ; softplus_100(z) = max(z,0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e)).  Written stage by stage over the 16
+            // columns so that 16 independent MUFU.EX2 / MUFU.LG2 are in flight per warp.
+            float z16[16], t[16];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                float dh[4];
+                const float4 b4 = lds128(bias + (unsigned)(col0 + 4 * j4) * 4u);
+                z16[4 * j4] = fmaf(acc[4 * j4], us16, b4.x); z16[4 * j4 + 1] = fmaf(acc[4 * j4 + 1], us16, b4.y);
+                z16[4 * j4 + 2] = fmaf(acc[4 * j4 + 2], us16, b4.z); z16[4 * j4 + 3] = fmaf(acc[4 * j4 + 3], us16, b4.w);
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int j = 4 * j4 + i;
-                    const float z16 = fmaf(acc[j], us16, bb[i]);
-                    const float t = ex2_approx(-fabsf(z16) * (100.f * 1.4426950408889634f / ACT_SCALE));
-                    const float u = 1.f + t;
-                    o[j] = fmaf(lg2_approx(u), ACT_SCALE * 0.6931471805599453f / 100.f, fmaxf(z16, 0.f));
-                    if (FULL) { const float ru = rcp_approx(u); dh[i] = z16 >= 0.f ? ru : t * ru; }
+            for (int j = 0; j < 16; ++j) t[j] = ex2_approx(-fabsf(z16[j]) * (100.f * 1.4426950408889634f / ACT_SCALE));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = lg2_approx(1.f + t[j]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = fmaf(o[j], ACT_SCALE * 0.6931471805599453f / 100.f, fmaxf(z16[j], 0.f));
+            if (FULL) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float dh[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const int j = 4 * j4 + i; const float ru = rcp_approx(1.f + t[j]); dh[i] = z16[j] >= 0.f ? ru : t[j] * ru; }
+                    if (KIND == K_FWD3) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (col0 + 4 * j4 + i >= SKIP_H) dh[i] = 0.f;
+                    }
+                    *plane_ptr(c.sp, c.g, (col0 >> 2) + j4, r) = make_float4(dh[0], dh[1], dh[2], dh[3]);
                 }
-                if (KIND == K_FWD3 && col0 + 4 * j4 + 3 >= SKIP_H) {
-                    // skip connection columns: h = emb[k-217] (x16), softplus' = 0
-                    const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
+            }
+            if (KIND == K_FWD3 && col0 + 15 >= SKIP_H) {
+                // skip connection columns: h = emb[k-217] (x16)
+                const float xs[3] = {S.X[r], S.X[TC_TM + r], S.X[2 * TC_TM + r]};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int k = col0 + 4 * j4 + i;
-                        if (k >= SKIP_H) {
-                            const int ei = k - SKIP_H;
-                            float val;
-                            if (ei < 3) val = xs[ei];
-                            else { const int f = (ei - 3) / 6, rem = (ei - 3) % 6; float sn, cs; sincosf(__fmul_rn(xs[rem % 3], (float)(1 << f)), &sn, &cs); val = rem < 3 ? sn : cs; }
-                            o[4 * j4 + i] = val * ACT_SCALE; dh[i] = 0.f;
-                        }
+                for (int j = 0; j < 16; ++j) {
+                    const int k = col0 + j;
+                    if (k >= SKIP_H) {
+                        const int ei = k - SKIP_H;
+                        float val;
+                        if (ei < 3) val = xs[ei];
+                        else { const int f = (ei - 3) / 6, rem = (ei - 3) % 6; float sn, cs; sincosf(__fmul_rn(xs[rem % 3], (float)(1 << f)), &sn, &cs); val = rem < 3 ? sn : cs; }
+                        o[j] = val * ACT_SCALE;
                     }
                 }
-                if (FULL) *plane_ptr(c.sp, c.g, (col0 >> 2) + j4, r) = make_float4(dh[0], dh[1], dh[2], dh[3]);
             }
             if (KIND == K_FWD7) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) sdf_part = fmaf(o[j], S.W8[col0 + j], sdf_part);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
+                    sdf_part = fmaf(o[4 * j4], w4.x, sdf_part); sdf_part = fmaf(o[4 * j4 + 1], w4.y, sdf_part);
+                    sdf_part = fmaf(o[4 * j4 + 2], w4.z, sdf_part); sdf_part = fmaf(o[4 * j4 + 3], w4.w, sdf_part);
+                }
             }
         } else if (KIND == K_FEAT) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
+                const float4 b4 = lds128(bias + (unsigned)(col0 + 4 * j4) * 4u);
                 const float4 f4 = make_float4(fmaf(acc[4 * j4], us, b4.x), fmaf(acc[4 * j4 + 1], us, b4.y),
                                               fmaf(acc[4 * j4 + 2], us, b4.z), fmaf(acc[4 * j4 + 3], us, b4.w));
                 if (FULL) *plane_ptr(c.sp, 8, (col0 >> 2) + j4, r) = f4;
@@ -242,8 +295,9 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, float& sdf_part, float
                 if (FULL) {
                     // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
                     const float4 d4 = *plane_ptr(c.sp, 7, (col0 >> 2) + j4, r);
-                    o[4 * j4] = S.W8[col0 + 4 * j4] * d4.x * ACT_SCALE; o[4 * j4 + 1] = S.W8[col0 + 4 * j4 + 1] * d4.y * ACT_SCALE;
-                    o[4 * j4 + 2] = S.W8[col0 + 4 * j4 + 2] * d4.z * ACT_SCALE; o[4 * j4 + 3] = S.W8[col0 + 4 * j4 + 3] * d4.w * ACT_SCALE;
+                    const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
+                    o[4 * j4] = w4.x * d4.x * ACT_SCALE; o[4 * j4 + 1] = w4.y * d4.y * ACT_SCALE;
+                    o[4 * j4 + 2] = w4.z * d4.z * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4.w * ACT_SCALE;
                 }
             }
         } else if (KIND == K_BWD || KIND == K_BWD4) {
@@ -265,7 +319,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, float& sdf_part, float
             // radiance hidden layers: relu(16 z)
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
+                const float4 b4 = lds128(bias + (unsigned)(col0 + 4 * j4) * 4u);
                 const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -289,14 +343,15 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, float& sdf_part, float
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) rgb_part[cc] = fmaf(o[j], S.W4[cc * 256 + col0 + j], rgb_part[cc]);
+                    for (int j = 0; j < 16; ++j) rgb_part[cc] = fmaf(o[j], lds32(c.w4_s + (unsigned)(cc * 256 + col0 + j) * 4u), rgb_part[cc]);
             }
         }
         const bool store = !(KIND == K_BWD0 || KIND == K_RAD3 || (KIND == K_FWD7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL));
         if (store) {
-            store8(S.A1, S.A2, r, col0, o);
-            store8(S.A1, S.A2, r, col0 + 8, o + 8);
+            store8s(c.a1, c.a2, c.row_off, c.sw, col0, o);
+            store8s(c.a1, c.a2, c.row_off, c.sw, col0 + 8, o + 8);
         }
+        if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar, c16, c.lane);
     }
 }
 
@@ -315,7 +370,7 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
     if (tid == 0) {
         for (int s = 0; s < TC_NS; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
         mbar_init(smem_u32(&S.d_ready), 1);
-        mbar_init(smem_u32(&S.a_ready), TC_EPI_THREADS);
+        for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.kb_ready[k]), TC_EPI_THREADS / 32);   // one arrive per epilogue warp
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), TWO_ACC ? 512 : 256);
@@ -353,38 +408,56 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // the whole warp walks the program (converged control flow, waits included); one elected lane issues tcgen05.mma / commit
+        {
             unsigned it = 0, a_phase = 0;
+            long long t_a = 0, t_full = 0, t_tot0 = clock64();
             const unsigned a1 = smem_u32(S.A1), a2 = smem_u32(S.A2), wst = smem_u32(S.Wst);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int g = 0; g < prog.n_gemm; ++g) {
-                    mbar_wait(smem_u32(&S.a_ready), a_phase); a_phase ^= 1;
-                    tc_fence_after();
                     const int n_kb = prog.g[g].n_kb, n_nh = prog.g[g].n_nh;
+                    int waited = 0;
                     for (int nh = 0; nh < n_nh; ++nh)
-                        for (int kb = 0; kb < n_kb; ++kb)
+                        for (int kb = 0; kb < n_kb; ++kb) {
+                            // N-half 0 overwrites D columns 0..127: needs K-blocks 0,1 of the previous epilogue (they drain those
+                            // columns) plus A K-block kb; N-half 1 needs everything
+                            const int need = nh == 0 ? (kb > 1 ? kb : 1) + 1 : 4;
+                            if (waited < need) {
+                                const long long t0 = clock64();
+                                for (; waited < need; ++waited) mbar_wait(smem_u32(&S.kb_ready[waited]), a_phase);
+                                t_a += clock64() - t0;
+                                tc_fence_after();
+                            }
                             for (int s = 0; s < 2; ++s, ++it) {
                                 const unsigned slot = it % TC_NS, ph = (it / TC_NS) & 1;
-                                mbar_wait(smem_u32(&S.full_bar[slot]), ph);
+                                { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot]), ph); t_full += clock64() - t0; }
                                 tc_fence_after();
-                                const unsigned d = tmem_d + nh * 128;
-                                const unsigned dc = TWO_ACC ? d + 256 : d;        // accumulator of the two correction products
-                                const unsigned long long bd = umma_desc(wst + slot * STAGE_BYTES);
-                                const unsigned long long ad1 = umma_desc(a1 + kb * STAGE_BYTES);
-                                const unsigned long long ad2 = umma_desc(a2 + kb * STAGE_BYTES);
-                                if (s == 0) {
+                                if (elect_one()) {
+                                    const unsigned d = tmem_d + nh * 128;
+                                    const unsigned dc = TWO_ACC ? d + 256 : d;        // accumulator of the two correction products
+                                    const unsigned long long bd = umma_desc(wst + slot * STAGE_BYTES);
+                                    const unsigned long long ad1 = umma_desc(a1 + kb * STAGE_BYTES);
+                                    const unsigned long long ad2 = umma_desc(a2 + kb * STAGE_BYTES);
+                                    if (s == 0) {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, (kb | ks) != 0);                    // hi * hi
+                                        for (int ks = 0; ks < 4; ++ks) umma_f16_ss(d, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, (kb | ks) != 0);                    // hi * hi
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(dc, ad2 + 2 * ks, bd + 2 * ks, UMMA_IDESC, TWO_ACC ? (kb | ks) != 0 : 1);    // lo * hi
-                                } else {
+                                        for (int ks = 0; ks < 4; ++ks) umma_f16_ss(dc, ad2 + 2 * ks, bd + 2 * ks, UMMA_IDESC, TWO_ACC ? (kb | ks) != 0 : 1);    // lo * hi
+                                    } else {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ss(dc, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                                 // hi * lo
+                                        for (int ks = 0; ks < 4; ++ks) umma_f16_ss(dc, ad1 + 2 * ks, bd + 2 * ks, UMMA_IDESC, 1);                                 // hi * lo
+                                    }
+                                    umma_commit(smem_u32(&S.empty_bar[slot]));
                                 }
-                                umma_commit(smem_u32(&S.empty_bar[slot]));
+                                __syncwarp();
                             }
-                    umma_commit(smem_u32(&S.d_ready));
+                        }
+                    for (; waited < 4; ++waited) mbar_wait(smem_u32(&S.kb_ready[waited]), a_phase);
+                    a_phase ^= 1;
+                    if (elect_one()) umma_commit(smem_u32(&S.d_ready));
+                    __syncwarp();
                 }
+            if (job.dbg && blockIdx.x == 0 && lane == 0) { job.dbg[0] = clock64() - t_tot0; job.dbg[1] = t_a; job.dbg[2] = t_full; }
         }
     } else {
         // ================= epilogue warps =================
@@ -395,7 +468,11 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
         c.S = &S; c.sp = sp; c.misc = sp + (size_t)9 * 256 * TC_TM;       // misc [row][80]: d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
         c.pk = pk; c.L = &L; c.job = &job; c.t_row = tmem_d + ((unsigned)(32 * q) << 16); c.r = r; c.cq = cq;
         c.sdim = small_dim(job.multires_view);
+        c.a1 = smem_u32(S.A1); c.a2 = smem_u32(S.A2); c.row_off = (unsigned)((r >> 3) * 1024 + (r & 7) * 128); c.sw = (unsigned)(r & 7);
+        c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4);
+        c.kb_bar = smem_u32(&S.kb_ready[0]); c.lane = lane; c.signal = 0;
         unsigned d_phase = 0;
+        long long t_d = 0, t_e0 = clock64();
         const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -439,17 +516,17 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
 #pragma unroll
                 for (int k = EMB; k < 64; ++k) emb[k] = 0.f;
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) store8(S.A1, S.A2, r, 8 * c8, emb + 8 * c8);
+                for (int c8 = 0; c8 < 8; ++c8) store8s(c.a1, c.a2, c.row_off, c.sw, 8 * c8, emb + 8 * c8);
             }
-            fence_proxy_async();
-            mbar_arrive(smem_u32(&S.a_ready));
+            for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
 
             float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
             float small_in[36];
             for (int g = 0; g < prog.n_gemm; ++g) {
-                mbar_wait(smem_u32(&S.d_ready), d_phase); d_phase ^= 1;
+                { const long long t0 = clock64(); mbar_wait(smem_u32(&S.d_ready), d_phase); d_phase ^= 1; t_d += clock64() - t0; }
                 tc_fence_after();
                 c.g = g; c.us = unscale[g];                      // us = 2^-(weight shift) / ACT_SCALE
+                c.signal = g + 1 < prog.n_gemm;
                 // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
                 if (g < 8) {
                     if (g == 3) epi_gemm<K_FWD3, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
@@ -463,7 +540,8 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
                         else epi_gemm<K_BWD, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
                     } else if (g == 16) {
                         epi_bar_sync();                                   // embedding-branch gradients (written at g == 12 by other threads)
-                        if (cq == 0) epi_gemm<K_BWD0, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                        epi_gemm<K_BWD0, FULL, TWO_ACC>(c, sdf_part, rgb_part, small_in);
+                        epi_bar_sync();                                   // all 39 d sdf/d emb entries complete
                     } else if (g == 17) {
 #pragma unroll
                         for (int j = 0; j < 36; ++j) small_in[j] = j < c.sdim ? c.misc[r * 80 + 40 + j] * ACT_SCALE : 0.f;
@@ -526,15 +604,15 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
                         // A <- geometry feature (x16) for radiance layer 0
 #pragma unroll 1
                         for (int c16 = 0; c16 < 4; ++c16) {
-                            const int col0 = cq * 64 + c16 * 16;
+                            const int col0 = c16 * 64 + cq * 16;
                             float h[16];
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
                                 const float4 f4 = *plane_ptr(sp, 8, (col0 >> 2) + j4, r);
                                 h[4 * j4] = f4.x * ACT_SCALE; h[4 * j4 + 1] = f4.y * ACT_SCALE; h[4 * j4 + 2] = f4.z * ACT_SCALE; h[4 * j4 + 3] = f4.w * ACT_SCALE;
                             }
-                            store8(S.A1, S.A2, r, col0, h);
-                            store8(S.A1, S.A2, r, col0 + 8, h + 8);
+                            store8s(c.a1, c.a2, c.row_off, c.sw, col0, h);
+                            store8s(c.a1, c.a2, c.row_off, c.sw, col0 + 8, h + 8);
                         }
                         epi_bar_sync();                       // small inputs written by cq == 0 threads are read by all four next
                     }
@@ -554,19 +632,19 @@ mlp_tc_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, 
                     }
                 }
                 if (g + 1 < prog.n_gemm) {
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(smem_u32(&S.a_ready));
+                    if (FULL && g == 16) for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);    // A was (re)written by the tail above
                 } else {
                     tc_fence_before();
                     epi_bar_sync();                           // X / OIDX / PART are rewritten by the next tile's input stage
                 }
             }
         }
+        if (job.dbg && blockIdx.x == 0 && tid == 64) { job.dbg[3] = clock64() - t_e0; job.dbg[4] = t_d; }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, TWO_ACC ? 512 : 256); }
+    (void)0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -657,8 +735,11 @@ int tc_pack(const float* pk_f32, const PackF32& L, unsigned char* base, const Tc
 
 size_t mlp_tc_scratch_bytes(int grid) { return (size_t)grid * 10 * 256 * TC_TM * sizeof(float); }
 
-int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
+long long* g_tc_dbg = nullptr;
+
+int launch_mlp_tc(const EvalJob& job_, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
                   size_t scratch_bytes, cudaStream_t stream) {
+    EvalJob job = job_; job.dbg = g_tc_dbg;
     static thread_local bool attr_set = false;
     static const bool two = []{ const char* e = getenv("NA_TC_TWO_ACC"); return e ? atoi(e) != 0 : (NA_TC_TWO_ACC != 0); }();
     const size_t smem = sizeof(TcSmem) + 1024;
