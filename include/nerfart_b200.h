@@ -34,11 +34,17 @@ extern "C" {
 #define NA_FRAMEWORK_NEUS     1
 
 /* MLP arithmetic mode (DESIGN.md "precision modes"):
- *   FP32   : CUDA-core fp32 FFMA everywhere (bit-for-bit reproducible, tightest parity)
- *   TC     : tcgen05 tensor cores; SDF net in 3-way bf16 split (fp32-equivalent products, fp32
- *            accumulate in TMEM), radiance net in 2-way bf16 split                                  */
+ *   FP32     : CUDA-core fp32 FFMA everywhere (bit-for-bit reproducible, tightest parity)
+ *   TC       : tcgen05 tensor cores, activations resident in TMEM; every GEMM as three fp16 products of two-term
+ *              operands (hi*hi + lo*hi + hi*lo: 22-bit operands, fp32 accumulate in TMEM)
+ *   TC2ACC   : tcgen05, activations in shared memory, the correction products in a second TMEM accumulator
+ *              (3x lower accumulation error than TC, slower)
+ *   TC_MIXED : TC for the SDF forward pass (what sample positions depend on); feature head, reverse sweep and
+ *              radiance layers with the hi*hi product only (11-bit operands, TF32-level)                          */
 #define NA_PRECISION_FP32     0
 #define NA_PRECISION_TC       1
+#define NA_PRECISION_TC2ACC   2
+#define NA_PRECISION_TC_MIXED 3
 
 /* Network geometry.  Mirrors what models/frameworks/volsdf.py:943-975 / neus.py:693-731 build:
  * SDF net  D=8, W=256, skip at layer 4, embed_multires=6 (39-d), W_geo_feat=256 (models/base.py:131-241)

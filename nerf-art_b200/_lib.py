@@ -13,13 +13,13 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libnerfart_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'mlp_tc.cu']
+SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--compiler-options', '-fPIC', '-shared']
 
 NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS = 0, 1
-NA_PRECISION_FP32, NA_PRECISION_TC = 0, 1
-PRECISIONS = {'fp32': NA_PRECISION_FP32, 'tc': NA_PRECISION_TC}
+NA_PRECISION_FP32, NA_PRECISION_TC, NA_PRECISION_TC2ACC, NA_PRECISION_TC_MIXED = 0, 1, 2, 3
+PRECISIONS = {'fp32': NA_PRECISION_FP32, 'tc': NA_PRECISION_TC, 'tc2acc': NA_PRECISION_TC2ACC, 'tc_mixed': NA_PRECISION_TC_MIXED}
 
 
 class NaNetDesc(C.Structure):

@@ -31,21 +31,31 @@ int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f
                   size_t scratch_bytes, cudaStream_t stream);
 size_t mlp_tc_scratch_bytes(int grid);
 extern long long* g_tc_dbg;
+size_t mlp_tmem_image_bytes();
+int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, const float* d_absmax, unsigned char* image, cudaStream_t stream);
+int launch_mlp_tmem(const EvalJob& job, const float* pk_f32, const unsigned char* image, const PackF32& L, int mixed,
+                    unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t mlp_tmem_scratch_bytes(int grid);
 
 size_t packed_f32_bytes(int multires_view) {
     const PackF32 L = pack_layout_f32(multires_view);
     return ((L.total + 63) / 64 * 64 + 14 * 260 + 64) * sizeof(float);
 }
-// one entry point for both arithmetic modes
+// the TMEM-resident kernel's weight image follows the two-accumulator kernel's image in the packed buffer
+size_t tmem_image_off(int multires_view) { return (tc_pack_layout(packed_f32_bytes(multires_view)).total + 1023) & ~(size_t)1023; }
+// one entry point for all arithmetic modes
 int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const PackF32 L = pack_layout_f32(job.multires_view);
     if (precision == NA_PRECISION_FP32) return launch_mlp_simt(job, (const float*)packed, L, scratch, scratch_bytes, stream);
-    if (precision == NA_PRECISION_TC) return launch_mlp_tc(job, (const unsigned char*)packed, packed_f32_bytes(job.multires_view), L, scratch, scratch_bytes, stream);
+    if (precision == NA_PRECISION_TC2ACC) return launch_mlp_tc(job, (const unsigned char*)packed, packed_f32_bytes(job.multires_view), L, scratch, scratch_bytes, stream);
+    if (precision == NA_PRECISION_TC || precision == NA_PRECISION_TC_MIXED)
+        return launch_mlp_tmem(job, (const float*)packed, (const unsigned char*)packed + tmem_image_off(job.multires_view), L,
+                               precision == NA_PRECISION_TC_MIXED, (unsigned char*)scratch, scratch_bytes, stream);
     return NA_ERR_UNSUPPORTED;
 }
 size_t mlp_scratch_bytes() {
-    const size_t a = mlp_simt_scratch_bytes(num_sms()), b = mlp_tc_scratch_bytes(num_sms());
-    return a > b ? a : b;
+    const size_t a = mlp_simt_scratch_bytes(num_sms()), b = mlp_tc_scratch_bytes(num_sms()), c = mlp_tmem_scratch_bytes(num_sms());
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -127,7 +137,7 @@ static size_t pack_dims_off(const PackF32& L) { return pack_scale_off(L) + 14 * 
 
 extern "C" size_t na_packed_weights_bytes(const NaNetDesc* desc) {
     if (!desc) return 0;
-    return tc_pack_layout(packed_f32_bytes(desc->multires_view)).total;
+    return tmem_image_off(desc->multires_view) + mlp_tmem_image_bytes();
 }
 
 extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, void* packed_, void* stream_) {
@@ -175,7 +185,12 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
     pack_fill_kernel<<<dim3(64, tab.n), 256, 0, stream>>>(*raw, tab, scale, packed);
     NA_CHECK_LAUNCH();
     // tensor-core operand image (hi/lo fp16, UMMA K-major SWIZZLE_128B stages) derived from the fp32 planes
-    return tc_pack(packed, L, (unsigned char*)packed_, tc_pack_layout(packed_f32_bytes(desc->multires_view)), stream);
+    const TcPackLayout T = tc_pack_layout(packed_f32_bytes(desc->multires_view));
+    NA_TRY(tc_pack(packed, L, (unsigned char*)packed_, T, stream));
+    // second image (TMEM-resident kernel: 256-row stages) from the same planes / per-plane scales (tables left by tc_pack)
+    unsigned char* meta = (unsigned char*)packed_ + T.meta_off;
+    return tmem_pack(packed, (const size_t*)meta, (const int*)(meta + 256), (const float*)(meta + 1280),
+                     (unsigned char*)packed_ + tmem_image_off(desc->multires_view), stream);
 }
 
 // -----------------------------------------------------------------------------------------------

@@ -220,7 +220,7 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     if (!desc || !packed || !cfg || !rays_o || !rays_d || !s_dev || !t_coarse || !u_imp || !out || !workspace || n_rays <= 0) return NA_ERR_BAD_ARG;
     if (!out->rgb || !out->depth || !out->acc) return NA_ERR_BAD_ARG;
     if (cfg->perturb && !u_rand) return NA_ERR_BAD_ARG;
-    if (cfg->precision != NA_PRECISION_FP32 && cfg->precision != NA_PRECISION_TC) return NA_ERR_UNSUPPORTED;
+    if (cfg->precision < NA_PRECISION_FP32 || cfg->precision > NA_PRECISION_TC_MIXED) return NA_ERR_UNSUPPORTED;
     if (cfg->n_samples < 2 || cfg->n_upsample_iters < 1 || cfg->n_importance % cfg->n_upsample_iters != 0) return NA_ERR_BAD_ARG;
     const int P = cfg->n_samples + cfg->n_importance, n_new = cfg->n_importance / cfg->n_upsample_iters;
     if (P > 2048 || n_new > 64 || n_new < 1) return NA_ERR_UNSUPPORTED;

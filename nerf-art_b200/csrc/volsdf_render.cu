@@ -295,7 +295,7 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
     if (!out->rgb || !out->depth || !out->acc || !out->beta_map || !out->iter_usage) return NA_ERR_BAD_ARG;
     if (cfg->perturb && !u_final) return NA_ERR_BAD_ARG;
     if (desc->framework != NA_FRAMEWORK_VOLSDF) return NA_ERR_BAD_ARG;
-    if (cfg->precision != NA_PRECISION_FP32 && cfg->precision != NA_PRECISION_TC) return NA_ERR_UNSUPPORTED;
+    if (cfg->precision < NA_PRECISION_FP32 || cfg->precision > NA_PRECISION_TC_MIXED) return NA_ERR_UNSUPPORTED;
     if (cfg->n_samples < 2 || cfg->n_importance < 1 || cfg->max_upsample_steps < 0 || cfg->max_bisection_steps < 0) return NA_ERR_BAD_ARG;
     const int n0 = 4 * cfg->n_samples, n_up = n0, P = cfg->n_samples + cfg->n_importance;
     const long long cap = (long long)n0 * (1 + cfg->max_upsample_steps);

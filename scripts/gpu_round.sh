@@ -17,6 +17,10 @@ for s in $STEPS; do
     benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; tail -c 600 $OUT/bench_ref.json ;;
     launches) NA_BENCH_LIGHT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1; echo "ncu launches exit $?"; tail -3 $OUT/launches.csv ;;
     ncu) NA_BENCH_LIGHT=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_ -s 4 -c 2 -f -o $OUT/prof_mlp python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1; echo "ncu full exit $?"; ls -la $OUT/ ;;
+    tmsmall) NA_CHECK_MODES=tc timeout 150 python scripts/tc_check.py small > $OUT/tm_small.log 2>&1; echo "tm small exit $?"; tail -12 $OUT/tm_small.log ;;
+    tmmixed) NA_CHECK_MODES=tc,tc_mixed timeout 150 python scripts/tc_check.py small > $OUT/tm_mixed.log 2>&1; echo "tm mixed exit $?"; tail -12 $OUT/tm_mixed.log ;;
+    tmcheck) NA_CHECK_MODES=${MODES:-tc,tc_mixed,tc2acc} timeout 600 python scripts/tc_check.py > $OUT/tm_check.log 2>&1; echo "tm check exit $?"; tail -24 $OUT/tm_check.log ;;
+    dram) NA_BENCH_LIGHT=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:mlp_t -c 70 --csv --log-file $OUT/dram.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/dram_bench.log 2>&1; echo "ncu dram exit $?"; tail -2 $OUT/dram.csv ;;
     tcsmall) timeout 180 python scripts/tc_check.py small > $OUT/tc_small.log 2>&1; echo "tc small exit $?"; tail -20 $OUT/tc_small.log ;;
     tcsan) timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/tc_check.py small > $OUT/tc_san.log 2>&1; echo "tc sanitize exit $?"; tail -30 $OUT/tc_san.log ;;
     tccheck) timeout 600 python scripts/tc_check.py > $OUT/tc_check.log 2>&1; echo "tc check exit $?"; tail -14 $OUT/tc_check.log ;;
@@ -24,7 +28,7 @@ for s in $STEPS; do
     testsfull) timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -40 $OUT/pytest_gpu.log ;;
     benchtc) NA_PRECISION=tc timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_tc.json 2> $OUT/bench_tc.err; echo "bench tc exit $?"; tail -c 3000 $OUT/bench_tc.json; tail -5 $OUT/bench_tc.err ;;
     teststc) NA_PRECISION=tc timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu_tc.log 2>&1; echo "pytest tc exit $?"; tail -40 $OUT/pytest_gpu_tc.log ;;
-    ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_tc -c 2 -f -o $OUT/prof_mlp_tc python scripts/prof_mlp.py tc > $OUT/ncu_tc.log 2>&1; echo "ncu tc exit $?"; tail -3 $OUT/ncu_tc.log ;;
+    ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_t -c 2 -f -o $OUT/prof_mlp_tc python scripts/prof_mlp.py tc > $OUT/ncu_tc.log 2>&1; echo "ncu tc exit $?"; tail -3 $OUT/ncu_tc.log ;;
     launchestc) NA_PRECISION=tc NA_BENCH_LIGHT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_tc.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_tc_bench.log 2>&1; echo "ncu launches exit $?"; tail -3 $OUT/launches_tc.csv ;;
     *) echo "unknown step $s" ;;
   esac

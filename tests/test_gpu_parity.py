@@ -112,11 +112,23 @@ def test_get_rays():
         assert linf(rd[0].cpu(), S[f'rays_{cam}_d']) < 1e-6
 
 
-def _render_volsdf(name, bump, **over):
+# rgb Linf tolerance of the beta=0.1 (BASELINE config) fixtures per arithmetic mode (include/nerfart_b200.h NA_PRECISION_*):
+# fp32 CUDA cores / two TMEM accumulators: 1e-4; TMEM-resident single accumulator (sdf error 1.5e-5): 3e-4;
+# mixed (TF32-level reverse sweep + radiance net): 4e-3 (< 1/255)
+RGB_TOL = {'fp32': 1e-4, 'tc2acc': 1e-4, 'tc': 3e-4, 'tc_mixed': 4e-3}
+VAL_SCALE = {'fp32': 1.0, 'tc2acc': 1.0, 'tc': 4.0, 'tc_mixed': 500.0}       # widening of compare_volsdf's value tolerances
+# share of reference-converged rays that must take the reference's sampler path (threshold decisions, beta <= 0.01 fixtures): the
+# single-accumulator modes carry a 1.5e-5 sdf error (3x the two-accumulator kernel) and may flip one ray of the 48-ray fixture
+MIN_SAME = {'fp32': 0.985, 'tc2acc': 0.985, 'tc': 0.95, 'tc_mixed': 0.95}
+
+
+def _render_volsdf(name, bump, prec=None, **over):
     from nerfart_b200.models.frameworks.volsdf import volume_render
     G = golden(name)
     beta_init, _, H, W, Ns, Ni = G['meta']
     m = make_volsdf(float(beta_init), bump, device=DEV)
+    if prec is not None:
+        m.engine().precision = prec
     M = G['rays_o'].shape[0]
     uf = T(np.broadcast_to(G['u0'], (M, int(Ni))).copy()) if 'u0' in G else None
     kw = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=uf is not None, white_bkgd=False,
@@ -133,14 +145,28 @@ def test_volsdf_render_vs_reference_golden(name, bump):
     """End to end through the reference-shaped API.  Tolerances: see compare_volsdf (rgb median 3e-6 / q98 3e-3 on
     path-consistent rays; every ray of the beta=0.1 BASELINE fixtures must be path-consistent)."""
     G, out = _render_volsdf(name, bump)
-    same = compare_volsdf(out, G, name)
+    import nerfart_b200
+    same = compare_volsdf(out, G, name, scale=VAL_SCALE[nerfart_b200.default_precision()],
+                          min_same=MIN_SAME[nerfart_b200.default_precision()])
     if G['meta'][0] >= 0.1:
         assert same.all()
-        assert linf(out['rgb'], G['rgb']) < 1e-4
+        assert linf(out['rgb'], G['rgb']) < RGB_TOL[nerfart_b200.default_precision()]
     if 'd_vals' in G:
         assert (np.diff(out['d_vals'], axis=-1) >= 0).all()                       # sortedness
         for k in ('implicit_surface', 'radiance', 'implicit_nablas', 'sigma', 'visibility_weights', 'alpha', 'p_i'):
             assert out[k].shape == G[k].shape, k
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tc2acc', 'tc', 'tc_mixed'])
+def test_volsdf_baseline_config_every_precision_mode(prec):
+    """BASELINE configs[0] fixture (64x64, 32+16 samples, beta=0.1) in every arithmetic mode: all rays follow the reference's
+    sampling path (the SDF forward pass is fp32-equivalent in every mode) and rgb stays within the mode's stated tolerance."""
+    G, out = _render_volsdf('volsdf_cfg1_b0.1', 0.0, prec=prec)
+    same = compare_volsdf(out, G, 'volsdf_cfg1_b0.1/' + prec, scale=VAL_SCALE[prec], min_same=MIN_SAME[prec])
+    assert same.all()
+    err = linf(out['rgb'], G['rgb'])
+    print(prec, 'rgb Linf', err, 'normals Linf', linf(out['normals_volume'], G['normals_volume']))
+    assert err < RGB_TOL[prec]
 
 
 def test_volsdf_render_is_deterministic_and_ray_independent():
@@ -191,7 +217,7 @@ def test_neus_render_vs_reference_golden(name, bump):
                                        perturb=False, white_bkgd=False, calc_normal=True, detailed_output='d_final' in G,
                                        rayschunk=2048, upsample_algo='official_solution', N_upsample_iters=4, N_outside=0)
     out = {k: v[0].cpu().numpy() for k, v in ex.items()}
-    tc = nerfart_b200.default_precision() == 'tc'
+    tc = nerfart_b200.default_precision() != 'fp32'
     rep = {k: linf(out[k], G[k]) for k in ('rgb', 'depth_volume', 'mask_volume', 'normals_volume')}
     print(name, rep)
     assert rep['rgb'] < (1e-3 if tc else 2e-4)

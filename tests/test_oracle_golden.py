@@ -100,7 +100,7 @@ VOLSDF_CASES = [('volsdf_cfg1_b0.1', 0.0), ('volsdf_det_b0.1', 0.5), ('volsdf_de
                 ('volsdf_n128_b0.01', 0.5), ('volsdf_n128_b0.1', 0.0), ('volsdf_perturb_b0.01', 0.5)]
 
 
-def compare_volsdf(out, G, name):
+def compare_volsdf(out, G, name, scale=1.0, min_same=0.985):
     """Shared by the oracle-vs-reference and the CUDA-vs-oracle tests.
 
     The error-bound sampler is discontinuous in its inputs: the 10-step bisection on `max bound <= eps`
@@ -109,7 +109,8 @@ def compare_volsdf(out, G, name):
     minority of *non-converged* rays, which moves their fine samples by O(1) (measured between the oracle and the
     reference themselves: ~10 % of the rays of the beta=0.01 fixture, none at the BASELINE beta=0.1).  Rays are therefore
     split into path-consistent rays (same iter_usage, same beta_map), which must agree tightly, and path-divergent rays,
-    whose share is bounded and whose images must still be close."""
+    whose share is bounded and whose images must still be close.  `scale` widens the value tolerances for the reduced-precision
+    arithmetic modes of the CUDA path (the sampler-path requirements stay as they are)."""
     rep = {k: linf(out[k], G[k]) for k in ('rgb', 'depth_volume', 'mask_volume', 'normals_volume') if k in out and k in G}
     n = G['rgb'].shape[0]
     if 'iter_usage' in G and 'iter_usage' in out:
@@ -121,14 +122,14 @@ def compare_volsdf(out, G, name):
     print(name, rep, 'path-divergent rays: %.3f' % frac_div)
     conv_g = (G['iter_usage'].reshape(n) >= 0) if 'iter_usage' in G else np.ones(n, dtype=bool)
     # rays the reference itself converged on must follow the same path almost always
-    assert (same | ~conv_g).mean() > 0.985, 'converged rays took a different sampler path'
+    assert (same | ~conv_g).mean() > min_same, 'converged rays took a different sampler path'
     assert frac_div < 0.75
     for k, tol_med, tol_max in (('rgb', 3e-6, 3e-3), ('depth_volume', 1e-5, 3e-2), ('mask_volume', 2e-6, 2e-4), ('normals_volume', 3e-5, 3e-2)):
         if k not in out or k not in G:
             continue
         err = np.abs(np.asarray(out[k]) - G[k]).reshape(n, -1).max(axis=1)
-        assert np.median(err[same]) < tol_med, (k, 'median', np.median(err[same]))
-        assert np.quantile(err[same], 0.98) < tol_max, (k, 'q98', np.quantile(err[same], 0.98))
+        assert np.median(err[same]) < tol_med * scale, (k, 'median', np.median(err[same]))
+        assert np.quantile(err[same], 0.98) < min(tol_max * scale, 0.05), (k, 'q98', np.quantile(err[same], 0.98))
     # path-divergent rays still render nearly the same image: the integral is insensitive to where the samples sit
     assert np.abs(np.asarray(out['rgb']) - G['rgb']).max() < 0.15
     if 'd_vals' in G and 'd_vals' in out:
