@@ -127,12 +127,13 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
 // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), both K-major, N>>3 @17, M>>4 @24 (M = 128)
 constexpr unsigned IDESC_N256 = (1u << 4) | (32u << 17) | (8u << 24);
 constexpr unsigned IDESC_N64 = (1u << 4) | (8u << 17) | (8u << 24);
+constexpr unsigned IDESC_N128 = (1u << 4) | (16u << 17) | (8u << 24);
 
 constexpr int N_BIAS_ROWS = 13;                  // 0..7 sdf fwd (x ACT_SCALE) | 8 feature (raw) | 9..12 radiance (x ACT_SCALE)
 
 struct __align__(1024) Smem {
     unsigned char Wst[NS * STAGE_BYTES];
-    unsigned long long full_bar[NS], empty_bar[NS], d_ready, kb_ready[4];   // kb_ready[k]: K-block k of the next A operand is in TMEM
+    unsigned long long full_bar[NS], empty_bar[NS], d_ready[2], kb_ready[4];   // d_ready[h]: N-half h of D is complete; kb_ready[k]: K-block k of the next A operand is in TMEM
     unsigned tmem_base;
     __align__(16) float BIAS[N_BIAS_ROWS * 256];
     __align__(16) float W8[256];                       // row 0 of SDF layer 8 (the sdf head)
@@ -154,8 +155,9 @@ enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_R
 struct EpiCtx {
     Smem* S; uint2* dh; float4* featp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
     unsigned t_lane; int r, cq, g; float us; int sdim;
-    unsigned bias_s, w8_s, w4_s, kb_bar;
+    unsigned bias_s, w8_s, w4_s, kb_bar, d_bar;
     int signal, need_lo, lane;
+    unsigned d_phase; long long* t_wait;
 };
 
 // this warp's part of K-block kb of the next A operand is in TMEM (and its part of D columns [64kb, 64kb+64) is consumed)
@@ -166,18 +168,23 @@ __device__ __forceinline__ void signal_kb(unsigned kb_bar, int kb, int lane) {
 }
 
 // 16 fp32 values (already x ACT_SCALE) -> 8 packed hi words + 8 packed lo words, stored over the 16 columns at taddr
+// (need_lo == 0: the consumer GEMM uses the hi*hi product only, the lo words are neither computed nor stored)
 __device__ __forceinline__ void store_a16(unsigned taddr, const float (&o)[16], int need_lo) {
-    unsigned hi[8], lo[8];
+    unsigned hi[8];
+    __half2 h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
-        const float2 back = __half22float2(h);
-        const __half2 l = __floats2half2_rn(o[2 * i] - back.x, o[2 * i + 1] - back.y);
-        hi[i] = *reinterpret_cast<const unsigned*>(&h);
-        lo[i] = *reinterpret_cast<const unsigned*>(&l);
-    }
+    for (int i = 0; i < 8; ++i) { h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]); hi[i] = *reinterpret_cast<const unsigned*>(&h[i]); }
     tmem_st8(taddr, hi);
-    if (need_lo) tmem_st8(taddr + 8, lo);
+    if (need_lo) {
+        unsigned lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 back = __half22float2(h[i]);
+            const __half2 l = __floats2half2_rn(o[2 * i] - back.x, o[2 * i + 1] - back.y);
+            lo[i] = *reinterpret_cast<const unsigned*>(&l);
+        }
+        tmem_st8(taddr + 8, lo);
+    }
     tmem_wait_st();
 }
 
@@ -213,6 +220,12 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         // 64-wide K-block of the next layer's A operand across the 16 epilogue warps
         const int col0 = c16 * 64 + c.cq * 16;
         uint2 q[4];
+        if ((c16 & 1) == 0) {                                       // passes 0,1 read N-half 0 of D, passes 2,3 N-half 1
+            const long long t0 = clock64();
+            mbar_wait(c.d_bar + 8u * (unsigned)(c16 >> 1), c.d_phase);
+            *c.t_wait += clock64() - t0;
+            tc_fence_after();
+        }
         if (USES_DH) {                                              // issued before the TMEM load: both latencies overlap
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) q[j4] = dhp[(size_t)((col0 >> 2) + j4) * TM];
@@ -359,6 +372,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar, c16, c.lane);
     }
+    if (N_PASS < 3) { mbar_wait(c.d_bar + 8u, c.d_phase); tc_fence_after(); }      // keep the second barrier's phase in step
 }
 
 // encoding entries k in [16 CG, 16 CG + 16) of [x, sin(2^f x), cos(2^f x)]_f (models/base.py:46-64), x ACT_SCALE; zero beyond 39
@@ -398,7 +412,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
-        mbar_init(smem_u32(&S.d_ready), 1);
+        mbar_init(smem_u32(&S.d_ready[0]), 1); mbar_init(smem_u32(&S.d_ready[1]), 1);
         for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.kb_ready[k]), EPI_THREADS / 32);   // one arrive per epilogue warp
         fence_barrier_init();
     }
@@ -451,44 +465,71 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 for (int kb = 0; kb < n_kb; ++kb) {
                     { const long long t0 = clock64(); mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase); t_a += clock64() - t0; }
                     tc_fence_after();
-                    {
-                        const unsigned slot = it % NS, ph = (it / NS) & 1;
-                        { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot]), ph); t_full += clock64() - t0; }
+                    const unsigned slot0 = it % NS, ph0 = (it / NS) & 1;
+                    const unsigned slot1 = (it + 1) % NS, ph1 = ((it + 1) / NS) & 1;
+                    const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
+                    if (kb + 1 < n_kb || prog.g[g].n64) {
+                        // 256-wide MMAs, stage by stage
+                        { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot0]), ph0); t_full += clock64() - t0; }
                         tc_fence_after();
                         if (elect_one()) {
-                            const unsigned long long bd = umma_desc(wst + slot * STAGE_BYTES);
+                            const unsigned long long bd = umma_desc(wst + slot0 * STAGE_BYTES);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)                                                      // hi * hi
-                                umma_f16_ts(t_out, t_in + (unsigned)(kb * 4 + ks) * 16u, bd + 2 * ks, idesc, (kb | ks) != 0);
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd + 2 * ks, idesc, (kb | ks) != 0);          // hi * hi
                             if (prods == 3) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)                                                  // lo * hi
-                                    umma_f16_ts(t_out, t_in + (unsigned)(kb * 4 + ks) * 16u + 8u, bd + 2 * ks, idesc, 1);
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks + 8u, bd + 2 * ks, idesc, 1);              // lo * hi
                             }
-                            umma_commit(smem_u32(&S.empty_bar[slot]));
+                            umma_commit(smem_u32(&S.empty_bar[slot0]));
                         }
                         __syncwarp();
                         ++it;
-                    }
-                    if (prods == 3) {
-                        const unsigned slot = it % NS, ph = (it / NS) & 1;
-                        { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot]), ph); t_full += clock64() - t0; }
+                        if (prods == 3) {
+                            { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot1]), ph1); t_full += clock64() - t0; }
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const unsigned long long bd = umma_desc(wst + slot1 * STAGE_BYTES);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd + 2 * ks, idesc, 1);                   // hi * lo
+                                umma_commit(smem_u32(&S.empty_bar[slot1]));
+                            }
+                            __syncwarp();
+                            ++it;
+                        }
+                    } else {
+                        // last K-block: N-half 0 first (its own commit), so that the epilogue's first two passes overlap N-half 1
+                        { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot0]), ph0); t_full += clock64() - t0; }
+                        if (prods == 3) { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot1]), ph1); t_full += clock64() - t0; }
                         tc_fence_after();
                         if (elect_one()) {
-                            const unsigned long long bd = umma_desc(wst + slot * STAGE_BYTES);
+                            const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES), bd1 = umma_desc(wst + slot1 * STAGE_BYTES);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)                                                      // hi * lo
-                                umma_f16_ts(t_out, t_in + (unsigned)(kb * 4 + ks) * 16u, bd + 2 * ks, idesc, 1);
-                            umma_commit(smem_u32(&S.empty_bar[slot]));
+                            for (int nh = 0; nh < 2; ++nh) {
+                                const unsigned t_dn = t_out + 128u * nh;
+                                const unsigned long long b0 = bd0 + (unsigned long long)(nh * (STAGE_BYTES / 2 / 16)), b1 = bd1 + (unsigned long long)(nh * (STAGE_BYTES / 2 / 16));
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b0 + 2 * ks, IDESC_N128, (kb | ks) != 0);  // hi * hi
+                                if (prods == 3) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks + 8u, b0 + 2 * ks, IDESC_N128, 1);      // lo * hi
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b1 + 2 * ks, IDESC_N128, 1);           // hi * lo
+                                }
+                                umma_commit(smem_u32(&S.d_ready[nh]));
+                            }
+                            umma_commit(smem_u32(&S.empty_bar[slot0]));
+                            if (prods == 3) umma_commit(smem_u32(&S.empty_bar[slot1]));
                         }
                         __syncwarp();
-                        ++it;
+                        it += prods == 3 ? 2 : 1;
                     }
                 }
                 for (int kb = n_kb; kb < 4; ++kb) mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase);     // keep the phases in step
                 a_phase ^= 1;
-                if (elect_one()) umma_commit(smem_u32(&S.d_ready));
-                __syncwarp();
+                if (prog.g[g].n64) {
+                    if (elect_one()) { umma_commit(smem_u32(&S.d_ready[0])); umma_commit(smem_u32(&S.d_ready[1])); }
+                    __syncwarp();
+                }
             }
         if (job.dbg && blockIdx.x == 0 && lane == 0) { job.dbg[0] = clock64() - t_tot0; job.dbg[1] = t_a; job.dbg[2] = t_full; }
     } else {
@@ -502,9 +543,10 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.pk = pk; c.L = &L; c.job = &job; c.t_lane = tmem_d + ((unsigned)(32 * q) << 16); c.r = r; c.cq = cq;
         c.sdim = small_dim(job.multires_view);
         c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4);
-        c.kb_bar = smem_u32(&S.kb_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
-        unsigned d_phase = 0;
+        c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
+        c.d_phase = 0;
         long long t_d = 0, t_e0 = clock64();
+        c.t_wait = &t_d;
         const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -549,8 +591,6 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
             float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
             float small_in[36];
             for (int g = 0; g < prog.n_gemm; ++g) {
-                { const long long t0 = clock64(); mbar_wait(smem_u32(&S.d_ready), d_phase); d_phase ^= 1; t_d += clock64() - t0; }
-                tc_fence_after();
                 c.g = g; c.us = unscale[g];                      // us = 2^-(weight shift) / ACT_SCALE
                 c.signal = g + 1 < prog.n_gemm;
                 c.need_lo = c.signal ? (prog.g[g + 1].prods == 3) : 0;
@@ -580,6 +620,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         epi_gemm<K_RAD, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
                     }
                 }
+                c.d_phase ^= 1;
                 // ---- per-GEMM tails ------------------------------------------------------------------------
                 if (g == 7) {
                     // fwd layer 7 stored h8 x16: undo in the head.  sdf = <h8, W8[0]> + b8[0]
