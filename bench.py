@@ -169,8 +169,14 @@ def main():
     import torch.distributed as dist
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
+        dist.barrier()
     if args.precision == 'auto':
         args.precision = nerfart_b200.default_precision() if hasattr(nerfart_b200, 'default_precision') else 'fp32'
     model = make_volsdf(0.1, 0.0, device=dev)
@@ -211,6 +217,11 @@ def main():
         return float(t.item()) * 1e-3
 
     step(True)                                     # builds rays once, sizes the workspace
+    if saved_stdout is not None:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     for _ in range(args.warmup):
         step(False)
     clocks = ClockSampler(local_rank)

@@ -180,7 +180,7 @@ def run_neus(out, name, var_init, bump, cam, H, W, detailed):
     print(name, 'rgb', S['rgb'].min(), S['rgb'].max(), 'acc', S['mask_volume'].min(), S['mask_volume'].max())
 
 
-if __name__ == '__main__':
+if __name__ == "__main__":
     out = HERE
     digest(out)
     stages(out)
