@@ -118,6 +118,31 @@ typedef struct NaNeusOut {                /* neus.py:385-407 */
     float* weights;                       /* [n_rays,P-1] visibility_weights */
 } NaNeusOut;
 
+/* Surface rendering (models/ray_casting.py).  algo: NA_RAYCAST_ROOT_FINDING = root_finding_surface_points (35-160, secant refinement
+ * 11-30), NA_RAYCAST_SPHERE_TRACING = sphere_tracing_surface_points (163-184).  near / far are scalars (the reference also accepts
+ * per-ray tensors; render.py passes floats). */
+#define NA_RAYCAST_ROOT_FINDING   0
+#define NA_RAYCAST_SPHERE_TRACING 1
+typedef struct NaSurfaceCfg {
+    int32_t algo;
+    int32_t n_steps;                      /* N_steps (256): marching samples per ray (root finding)   */
+    int32_t n_secant_steps;               /* N_secant_steps (8)                                       */
+    int32_t n_iters;                      /* N_iters (20): sphere-tracing steps                       */
+    float   near, far;                    /* 0.0, 6.0                                                 */
+    float   logit_tau;                    /* 0.0                                                      */
+    int32_t fill_inf;                     /* 1: depth = inf where nothing is hit, 0: far              */
+    int32_t use_view_dirs;                /* surface_render(use_view_dirs=True)                       */
+    int32_t precision;                    /* NA_PRECISION_*                                           */
+} NaSurfaceCfg;
+
+typedef struct NaSurfaceOut {             /* return values of ray_casting.surface_render, 241-263 */
+    float*   rgb;                         /* [n_rays,3]  colours, 0 where mask is false */
+    float*   depth;                       /* [n_rays]    */
+    uint8_t* mask;                        /* [n_rays]    mask_surface */
+    float*   nablas;                      /* [n_rays,3]  implicit_nablas (may be NULL)  */
+    float*   normals;                     /* [n_rays,3]  normals_surface (may be NULL)  */
+} NaSurfaceOut;
+
 /* ---- capability / errors ------------------------------------------------------------------- */
 int         na_version(void);
 const char* na_error_string(int code);
@@ -170,6 +195,17 @@ int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, const NaNeusCf
                        const float* rays_o, const float* rays_d, int64_t n_rays, const float* s_dev /*[1] = NeuS.forward_s()*/,
                        const float* t_coarse, const float* u_imp, const float* u_rand,
                        const NaNeusOut* out, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- surface rendering: models/ray_casting.py ------------------------------------------------------------- */
+/* root_finding_surface_points (35-160) / sphere_tracing_surface_points (163-184) on ImplicitSurface.forward: rays_d_unit normalised,
+ * t_steps = torch.linspace(0,1,n_steps) (root finding; NULL for sphere tracing) -> depth [n], pts [n,3], mask [n], mask_sign_change [n] (NULL ok) */
+size_t na_surface_workspace_bytes(const NaSurfaceCfg* cfg, int64_t n_rays);
+int na_ray_cast(const NaNetDesc* desc, const void* packed, const NaSurfaceCfg* cfg, const float* rays_o, const float* rays_d_unit,
+                int64_t n_rays, const float* t_steps, float* depth, float* pts, uint8_t* mask, uint8_t* mask_sign_change,
+                void* workspace, size_t ws_bytes, void* stream);
+/* surface_render (187-263): rays_d un-normalised; normalise -> ray cast -> model.forward at the hit points -> masked colours / normals */
+int na_surface_render_fwd(const NaNetDesc* desc, const void* packed, const NaSurfaceCfg* cfg, const float* rays_o, const float* rays_d,
+                          int64_t n_rays, const float* t_steps, const NaSurfaceOut* out, void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

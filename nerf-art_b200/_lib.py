@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libnerfart_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu']
+SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--compiler-options', '-fPIC', '-shared']
 
@@ -51,6 +51,19 @@ class NaNeusCfg(C.Structure):
 class NaNeusOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ('rgb', 'depth', 'acc', 'normals', 'd_all', 'sdf', 'nablas', 'radiance',
                                           'alpha', 'weights')]
+
+
+NA_RAYCAST_ROOT_FINDING, NA_RAYCAST_SPHERE_TRACING = 0, 1
+
+
+class NaSurfaceCfg(C.Structure):
+    _fields_ = [('algo', C.c_int32), ('n_steps', C.c_int32), ('n_secant_steps', C.c_int32), ('n_iters', C.c_int32),
+                ('near', C.c_float), ('far', C.c_float), ('logit_tau', C.c_float), ('fill_inf', C.c_int32),
+                ('use_view_dirs', C.c_int32), ('precision', C.c_int32)]
+
+
+class NaSurfaceOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ('rgb', 'depth', 'mask', 'nablas', 'normals')]
 
 
 def build(verbose=False):
@@ -110,6 +123,12 @@ def lib():
             L.na_neus_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaNeusCfg), C.c_void_p, C.c_void_p,
                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(NaNeusOut), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_surface_workspace_bytes.restype = C.c_size_t
+        L.na_surface_workspace_bytes.argtypes = [C.POINTER(NaSurfaceCfg), C.c_int64]
+        L.na_ray_cast.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaSurfaceCfg), C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_surface_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaSurfaceCfg), C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_void_p, C.POINTER(NaSurfaceOut), C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = L
     return _lib
 
@@ -131,6 +150,7 @@ def ptr(t):
         raise RuntimeError('nerfart_b200 kernels need CUDA tensors (there is no CPU path)')
     assert t.is_contiguous(), 'tensor must be contiguous'
     return C.c_void_p(t.data_ptr())
+
 
 
 def stream_ptr(device=None):

@@ -7,8 +7,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (NaNetDesc, NaRawParams, NaVolsdfCfg, NaVolsdfOut, NaNeusCfg, NaNeusOut, check, ptr, stream_ptr,
-                   NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS, PRECISIONS)
+from ._lib import (NaNetDesc, NaRawParams, NaVolsdfCfg, NaVolsdfOut, NaNeusCfg, NaNeusOut, NaSurfaceCfg, NaSurfaceOut, check, ptr,
+                   stream_ptr, NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS, NA_RAYCAST_ROOT_FINDING, NA_RAYCAST_SPHERE_TRACING, PRECISIONS)
 
 _LINSPACE_CACHE = {}
 
@@ -184,4 +184,58 @@ class NetEngine:
             check(L.na_neus_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
                                        ptr(s_dev), ptr(tc), ptr(ui), ptr(u_rand.contiguous()) if u_rand is not None else None,
                                        C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_neus_render_fwd')
+        return o
+
+    # ------------------------------------------------------------------------------------------
+    def _surface_cfg(self, algo, near, far, N_steps, N_secant_steps, N_iters, logit_tau, fill_inf):
+        if isinstance(near, torch.Tensor) or isinstance(far, torch.Tensor):
+            raise NotImplementedError('per-ray near / far tensors are not used by render.py and are not implemented')
+        if algo not in ('root_finding', 'sphere_tracing'):
+            raise NotImplementedError                       # ray_casting.py:233
+        return NaSurfaceCfg(NA_RAYCAST_ROOT_FINDING if algo == 'root_finding' else NA_RAYCAST_SPHERE_TRACING, int(N_steps),
+                            int(N_secant_steps), int(N_iters), float(near), float(far), float(logit_tau), int(bool(fill_inf)), 1,
+                            PRECISIONS[self.precision])
+
+    def ray_cast(self, rays_o, rays_d_unit, algo, *, near=0.0, far=6.0, N_steps=256, N_secant_steps=8, N_iters=20, logit_tau=0.0,
+                 fill_inf=True):
+        """root_finding_surface_points / sphere_tracing_surface_points (ray_casting.py:35-184) on flat [N,3] rays with unit directions."""
+        L = _lib.lib()
+        dev = rays_o.device
+        n = rays_o.shape[0]
+        cfg = self._surface_cfg(algo, near, far, N_steps, N_secant_steps, N_iters, logit_tau, fill_inf)
+        depth = torch.empty(n, device=dev, dtype=torch.float32)
+        pts = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        mask = torch.empty(n, device=dev, dtype=torch.uint8)
+        msc = torch.empty(n, device=dev, dtype=torch.uint8)
+        self.pack()
+        ws = self.workspace(L.na_surface_workspace_bytes(C.byref(cfg), n))
+        ts = cpu_linspace(N_steps, dev) if algo == 'root_finding' else None
+        with torch.cuda.device(dev):
+            check(L.na_ray_cast(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d_unit), n, ptr(ts),
+                                ptr(depth), ptr(pts), C.c_void_p(mask.data_ptr()), C.c_void_p(msc.data_ptr()), ptr(ws), ws.numel(),
+                                stream_ptr(dev)), 'na_ray_cast')
+        return depth, pts, mask.bool(), msc.bool()
+
+    def surface_render(self, rays_o, rays_d, algo, calc_normal=True, **cfgs):
+        """ray_casting.surface_render (187-263) on flat [N,3] rays (directions un-normalised)."""
+        L = _lib.lib()
+        dev = rays_o.device
+        n = rays_o.shape[0]
+        kw = dict(near=0.0, far=6.0, N_steps=256, N_secant_steps=8, N_iters=20, logit_tau=0.0, fill_inf=True)
+        for k, v in cfgs.items():
+            if k not in kw:
+                raise TypeError(f'unexpected ray-casting option {k!r}')
+            kw[k] = v
+        cfg = self._surface_cfg(algo, kw['near'], kw['far'], kw['N_steps'], kw['N_secant_steps'], kw['N_iters'], kw['logit_tau'], kw['fill_inf'])
+        f32 = dict(device=dev, dtype=torch.float32)
+        o = dict(rgb=torch.empty(n, 3, **f32), depth=torch.empty(n, **f32), mask=torch.empty(n, device=dev, dtype=torch.uint8),
+                 nablas=torch.empty(n, 3, **f32), normals=torch.empty(n, 3, **f32) if calc_normal else None)
+        out = NaSurfaceOut(ptr(o['rgb']), ptr(o['depth']), C.c_void_p(o['mask'].data_ptr()), ptr(o['nablas']), ptr(o['normals']))
+        self.pack()
+        ws = self.workspace(L.na_surface_workspace_bytes(C.byref(cfg), n))
+        ts = cpu_linspace(kw['N_steps'], dev) if algo == 'root_finding' else None
+        with torch.cuda.device(dev):
+            check(L.na_surface_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n, ptr(ts),
+                                          C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_surface_render_fwd')
+        o['mask'] = o['mask'].bool()
         return o

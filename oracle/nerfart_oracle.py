@@ -600,3 +600,85 @@ def neus_render(net, rays_o, rays_d, obj_bounding_radius=1.0, N_samples=64, N_im
             ret['d_all'] = d_all
         outs.append(ret)
     return OrderedDict((k, np.concatenate([o_[k] for o_ in outs], axis=0)) for k in outs[0])
+
+
+# ----------------------------------------------------------------------------------------------
+# surface rendering  (models/ray_casting.py)
+# ----------------------------------------------------------------------------------------------
+def _secant_point(f_low, f_high, d_low, d_high):
+    return (-f_low * (d_high - d_low) / (f_high - f_low) + d_low).astype(F32)          # ray_casting.py:16,29
+
+
+def root_finding_surface_points(query_fn, rays_o, rays_d, near=0.0, far=6.0, N_steps=256, logit_tau=0.0, N_secant_steps=8, fill_inf=True):
+    """root_finding_surface_points (ray_casting.py:35-160) + run_secant_method (11-30) on flat rays [N,3] with unit directions.
+    query_fn: points [M,3] -> sdf [M] (ImplicitSurface.forward).  -> d_pred_out [N], pt_pred [N,3], mask [N], mask_sign_change [N]."""
+    o = rays_o.astype(F32); dd = rays_d.astype(F32)
+    N = o.shape[0]
+    t = _linspace(0.0, 1.0, N_steps)[None, :]
+    near_ = np.full((N, 1), near, F32); far_ = np.full((N, 1), far, F32)
+    d = (near_ * (F32(1.0) - t) + far_ * t).astype(F32)                                 # 77
+    p = (o[:, None, :] + d[:, :, None] * dd[:, None, :]).astype(F32)                   # 80
+    tau = F32(logit_tau)
+    val = (query_fn(p.reshape(-1, 3)).reshape(N, N_steps) - tau).astype(F32)            # 87-89
+    m0 = val[:, 0] > 0                                                                  # 93
+    sign = np.concatenate([np.sign(val[:, :-1] * val[:, 1:]), np.ones((N, 1), F32)], axis=-1).astype(F32)   # 96-101
+    cost = sign * np.arange(N_steps, 0, -1).astype(F32)                                 # 104
+    idx = np.argmin(cost, axis=-1); values = cost[np.arange(N), idx]                    # 106
+    msc = values < 0                                                                    # 109
+    mp2n = val[np.arange(N), idx] > 0                                                   # 112
+    mask = msc & mp2n & m0                                                              # 114
+    idx2 = np.minimum(idx + 1, N_steps - 1)                                             # 126
+    d_high = d[np.arange(N), idx][mask]; f_high = val[np.arange(N), idx][mask]
+    d_low = d[np.arange(N), idx2][mask]; f_low = val[np.arange(N), idx2][mask]
+    om, dm = o[mask], dd[mask]
+    if mask.sum() > 0:
+        d_pred = _secant_point(f_low, f_high, d_low, d_high)
+        for _ in range(N_secant_steps):
+            p_mid = (om + d_pred[:, None] * dm).astype(F32)
+            f_mid = (query_fn(p_mid) - tau).astype(F32)
+            low = f_mid < 0
+            d_low = np.where(low, d_pred, d_low); f_low = np.where(low, f_mid, f_low)
+            d_high = np.where(~low, d_pred, d_high); f_high = np.where(~low, f_mid, f_high)
+            d_pred = _secant_point(f_low, f_high, d_low, d_high)
+    else:
+        d_pred = np.ones(0, F32)
+    pt = np.ones((N, 3), F32)
+    pt[mask] = (om + d_pred[:, None] * dm).astype(F32)                                  # 142
+    d_out = np.ones(N, F32)
+    d_out[mask] = d_pred
+    d_out[~mask] = np.inf if fill_inf else F32(far)                                     # 150
+    d_out[~m0] = 0                                                                      # 151
+    return d_out, pt, mask, msc
+
+
+def sphere_tracing_surface_points(query_fn, rays_o, rays_d, near=0.0, far=6.0, N_iters=20):
+    """sphere_tracing_surface_points (ray_casting.py:163-184)."""
+    o = rays_o.astype(F32); dd = rays_d.astype(F32)
+    d = (np.ones(o.shape[0], F32) * F32(near)).astype(F32)
+    mask = np.ones(o.shape[0], bool)
+    for _ in range(N_iters):
+        val = query_fn((o + dd * d[:, None]).astype(F32))
+        d[mask] = (d[mask] + val[mask]).astype(F32)
+        mask[d > far] = False
+        mask[d < 0] = False
+    return d, (o + dd * d[:, None]).astype(F32), mask
+
+
+def surface_render(net, rays_o, rays_d, algo, **cfg):
+    """surface_render (ray_casting.py:187-263) on flat rays; rays_d un-normalised."""
+    dirs = _normalize(rays_d.astype(F32))
+    q = lambda x: sdf_net(net, x)[0]
+    if algo == 'root_finding':
+        d, pt, mask, _ = root_finding_surface_points(q, rays_o, dirs, **cfg)
+    elif algo == 'sphere_tracing':
+        d, pt, mask = sphere_tracing_surface_points(q, rays_o, dirs, **cfg)
+    else:
+        raise NotImplementedError
+    if net.framework == 'volsdf':
+        col, _, nab = volsdf_forward(net, pt, dirs)
+    else:
+        sdf, feat, nab = sdf_net(net, pt, with_nablas=True)
+        col = radiance_net(net, pt, dirs, nab, feat)
+    col = col.copy(); col[~mask] = 0
+    normals = _normalize(nab); normals[~mask] = 0
+    return OrderedDict(rgb=col, depth=d, implicit_nablas=nab, mask_surface=mask, normals_surface=normals)

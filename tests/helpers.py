@@ -38,4 +38,6 @@ def oracle_net(model, framework):
 
 
 def linf(a, b):
+    if np.asarray(a).size == 0:
+        return 0.0
     return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
