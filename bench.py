@@ -33,6 +33,8 @@ P = N_SAMPLES + N_IMPORTANCE
 # matmul MACs x 2.  SDF-only evaluations skip the unused 256-wide feature head (918 016 instead of 1 049 088).
 F_SDF = 2 * (39 * 256 + 256 * 256 * 2 + 256 * 217 + 256 * 256 * 4 + 256)
 F_FULL = 2 * (524544 + 459008 + 265216)
+# measured DRAM bytes per sample (SDF-only, full) of the MLP kernel by precision mode -- profiles/r1n_tmem_v2.md
+TRAFFIC_B_PER_SAMPLE = {'tc': (14587392 / 1048576, (350204416 + 1091515000) / 262144)}
 RENDER_KW = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=False, white_bkgd=False,
                  max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, epsilon=0.1, max_bisection_steps=10,
                  require_nablas=True, calc_normal=True, detailed_output=False)
@@ -264,10 +266,14 @@ def main():
         t_f = e0.elapsed_time(e1) * 1e-3 / reps
         ach = m * F_SDF / t_k / 1e12
         peak = pk['bf16_tflops']
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/r1n_tmem_v2.md:
+        # dram__bytes_read.sum + dram__bytes_write.sum = 13.9 B/sample SDF-only, 5.5 KB/sample full), scaled to this launch size.
+        traffic = TRAFFIC_B_PER_SAMPLE.get(os.environ.get('NA_PRECISION', 'tc'))
         roof = {'bound': 'tensor', 'kernel': 'mlp kernel, SDF-only mode', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': ach / peak, 'traffic': None, 'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
+                'frac': ach / peak, 'traffic': None if traffic is None else traffic[0] * m,
+                'traffic_src': 'profiles/r1n_tmem_v2.md (ncu --set full, bytes/sample x samples_per_launch)', 'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
                 'flop_per_sample': F_SDF, 'samples_per_launch': m, 'launch_ms': t_k * 1e3,
-                'full_mode': {'achieved': (m // 4) * F_FULL / t_f / 1e12, 'flop_per_sample': F_FULL, 'launch_ms': t_f * 1e3,
+                'full_mode': {'traffic': None if traffic is None else traffic[1] * (m // 4), 'achieved': (m // 4) * F_FULL / t_f / 1e12, 'flop_per_sample': F_FULL, 'launch_ms': t_f * 1e3,
                               'frac': (m // 4) * F_FULL / t_f / 1e12 / peak},
                 'frame_flop': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL),
                 'frame_frac_of_peak': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL) / (t_dev / args.steps) / 1e12 / peak / world}
