@@ -207,6 +207,55 @@ int na_ray_cast(const NaNetDesc* desc, const void* packed, const NaSurfaceCfg* c
 int na_surface_render_fwd(const NaNetDesc* desc, const void* packed, const NaSurfaceCfg* cfg, const float* rays_o, const float* rays_d,
                           int64_t n_rays, const float* t_steps, const NaSurfaceOut* out, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Backward of the render: the second pass of the CLIP fine-tune step.
+ * Replaces what autograd does for   rgb_pred.backward(gradient[:, i:i+batch_size, :], retain_graph=True);
+ *                                   eikonal_loss.backward()
+ * in Trainer.forward (models/frameworks/volsdf.py:769-783; models/frameworks/neus.py:551-563), with
+ * calc_eikonal_loss = w_eikonal * mse(||extras['implicit_nablas']||, 1) over all points of the patch
+ * (volsdf.py:917-939; neus.py:667-690).  The sample depths are constants of the backward (the samplers run under
+ * torch.no_grad: volsdf.py:113, neus.py:275-303), so the inputs are the detailed outputs of the forward render of the
+ * same ray patch (na_volsdf_render_fwd / na_neus_render_fwd with cfg.detailed = 1).
+ * Gradients accumulate (+=) into `grad_pack`, a buffer of na_grad_pack_bytes() that the caller zeroes at
+ * optimizer.zero_grad() time (volsdf.py:753); na_unpack_grads maps it to d loss / d (bias, weight_g, weight_v) of the
+ * reference's parameters through the weight-norm Jacobian (models/base.py:226-227,365-366) once per step.          */
+typedef struct NaTrainCfg {
+    int32_t points_per_ray;       /* P = N_samples + N_importance of the forward render                                 */
+    float   w_eikonal;            /* args.finetune.w_eikonal; 0 disables the eikonal term (finetune.use_eikonal False)  */
+    int32_t eikonal_count;        /* number of points the eikonal mean runs over = rays in the reference's patch * P    */
+    int32_t white_bkgd;
+    float   speed_factor;         /* ln_beta / ln_s speed factor (volsdf.py:337-339, neus.py:116-117)                   */
+    int32_t train_surface;        /* 0: implicit_surface is frozen (fix_module): no SDF-net weight gradients            */
+    int32_t train_radiance;       /* 0: radiance_net is frozen (NeuS fine-tune, neus.py:28)                             */
+    int32_t reserved;
+} NaTrainCfg;
+
+typedef struct NaRawGrads {       /* where na_unpack_grads writes; same layer order as NaRawParams; NULL = skip layer   */
+    float* bias[NA_NUM_SDF_LAYERS + NA_NUM_RAD_LAYERS];
+    float* weight_g[NA_NUM_SDF_LAYERS + NA_NUM_RAD_LAYERS];
+    float* weight_v[NA_NUM_SDF_LAYERS + NA_NUM_RAD_LAYERS];
+} NaRawGrads;
+
+size_t na_grad_pack_bytes(const NaNetDesc* desc);
+size_t na_train_workspace_bytes(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray);
+
+/* rays [n,3] (directions un-normalised, as passed to the forward), alpha_beta = {1/beta, beta} (forward_ab),
+ * d_all / sdf [n,P], radiance / nablas [n,P,3] = extras d_vals, implicit_surface, radiance, implicit_nablas of the forward
+ * (volsdf.py:578-594), grad_rgb [n,3].  scalars (float64[2], accumulated): [0] d loss / d ln_beta, [1] eikonal loss.  */
+int na_volsdf_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o, const float* rays_d,
+                         int64_t n_rays, const float* alpha_beta, const float* d_all, const float* sdf, const float* radiance,
+                         const float* nablas, const float* grad_rgb, void* grad_pack, double* scalars, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* NeuS: s = {forward_s()}; d_all / sdf [n,P], nablas [n,P,3] at the sample points, radiance [n,P-1,3] at the midpoints
+ * (extras of neus.py:397-407).  scalars: [0] d loss / d ln_s, [1] eikonal loss.                                      */
+int na_neus_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o, const float* rays_d,
+                       int64_t n_rays, const float* s, const float* d_all, const float* sdf, const float* radiance,
+                       const float* nablas, const float* grad_rgb, void* grad_pack, double* scalars, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+int na_unpack_grads(const NaNetDesc* desc, const NaRawParams* raw, const void* grad_pack, const NaRawGrads* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libnerfart_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu']
+SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu', 'train.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--compiler-options', '-fPIC', '-shared']
 
@@ -64,6 +64,15 @@ class NaSurfaceCfg(C.Structure):
 
 class NaSurfaceOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ('rgb', 'depth', 'mask', 'nablas', 'normals')]
+
+
+class NaTrainCfg(C.Structure):
+    _fields_ = [('points_per_ray', C.c_int32), ('w_eikonal', C.c_float), ('eikonal_count', C.c_int32), ('white_bkgd', C.c_int32),
+                ('speed_factor', C.c_float), ('train_surface', C.c_int32), ('train_radiance', C.c_int32), ('reserved', C.c_int32)]
+
+
+class NaRawGrads(C.Structure):
+    _fields_ = [('bias', C.c_void_p * 14), ('weight_g', C.c_void_p * 14), ('weight_v', C.c_void_p * 14)]
 
 
 def build(verbose=False):
@@ -129,6 +138,15 @@ def lib():
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.na_surface_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaSurfaceCfg), C.c_void_p, C.c_void_p,
                                             C.c_int64, C.c_void_p, C.POINTER(NaSurfaceOut), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_grad_pack_bytes.restype = C.c_size_t
+        L.na_grad_pack_bytes.argtypes = [C.POINTER(NaNetDesc)]
+        L.na_train_workspace_bytes.restype = C.c_size_t
+        L.na_train_workspace_bytes.argtypes = [C.POINTER(NaNetDesc), C.c_int64, C.c_int32]
+        for fn in (L.na_volsdf_render_bwd, L.na_neus_render_bwd):
+            fn.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaTrainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                           C.c_size_t, C.c_void_p]
+        L.na_unpack_grads.argtypes = [C.POINTER(NaNetDesc), C.POINTER(NaRawParams), C.c_void_p, C.POINTER(NaRawGrads), C.c_void_p]
         _lib = L
     return _lib
 

@@ -43,6 +43,7 @@ size_t packed_f32_bytes(int multires_view) {
 }
 // the TMEM-resident kernel's weight image follows the two-accumulator kernel's image in the packed buffer
 size_t tmem_image_off(int multires_view) { return (tc_pack_layout(packed_f32_bytes(multires_view)).total + 1023) & ~(size_t)1023; }
+size_t train_pack_off(int multires_view) { return (tmem_image_off(multires_view) + mlp_tmem_image_bytes() + 1023) & ~(size_t)1023; }
 // one entry point for all arithmetic modes
 int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const PackF32 L = pack_layout_f32(job.multires_view);
@@ -69,7 +70,7 @@ struct FillDesc {
     int mode;                   // 0: dst[r][c] = Weff[c+out0][inmap(r)]   1: dst[r][c] = Weff[r+out0][c]   2: dst[c] = bias[c+out0]
     int out0, out_n;            // valid source rows [out0, out0+out_n)
     int in_dim;                 // source columns
-    int map;                    // 0 identity; 1 radiance layer 0 (feat rows first, then the small inputs)
+    int map;                    // 0 identity; 1 radiance layer 0 (feat rows first, then the small inputs); 2 identity below `small`, else 0
     int small;                  // small_dim for map 1
     float mult;
 };
@@ -102,6 +103,7 @@ __global__ void pack_fill_kernel(const NaRawParams raw, const FillTable tab, con
             if (f.mode == 0) { o = c; i = r; } else { o = r; i = c; }
             int src_in = -1;
             if (f.map == 0) { if (i < f.in_dim) src_in = i; }
+            else if (f.map == 2) { if (i < f.small) src_in = i; }
             else { if (i < 256) src_in = f.small + i; else if (i - 256 < f.small) src_in = i - 256; }
             if (o < f.out_n && src_in >= 0) {
                 const int so = o + f.out0;
@@ -137,7 +139,7 @@ static size_t pack_dims_off(const PackF32& L) { return pack_scale_off(L) + 14 * 
 
 extern "C" size_t na_packed_weights_bytes(const NaNetDesc* desc) {
     if (!desc) return 0;
-    return tmem_image_off(desc->multires_view) + mlp_tmem_image_bytes();
+    return train_pack_off(desc->multires_view) + pack_layout_train().total * sizeof(float);
 }
 
 extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, void* packed_, void* stream_) {
@@ -184,6 +186,17 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
     add(L.rad_b4, 1, 4, 13, 2, 0, 3, 0, 1.f);
     pack_fill_kernel<<<dim3(64, tab.n), 256, 0, stream>>>(*raw, tab, scale, packed);
     NA_CHECK_LAUNCH();
+    {   // backward-only planes (train.cu): destination offsets are relative to the train pack
+        const PackTrain TP = pack_layout_train();
+        float* tp = (float*)((unsigned char*)packed_ + train_pack_off(desc->multires_view));
+        tab.n = 0;
+        add(TP.rad_w[0], W, W, 9, 1, 0, W, 1, 1.f);                     // dst[r][c] = W0[r][small + c]  (feature columns)
+        for (int l = 1; l < 4; ++l) add(TP.rad_w[l], W, W, 9 + l, 1, 0, W, 0, 1.f);
+        add(TP.rad_w0_small, W, W, 9, 1, 0, W, 2, 1.f);                 // dst[r][c] = W0[r][c], c < small_dim
+        add(TP.w8_feat, W, W, 8, 1, 1, W, 0, 1.f);                      // dst[r][c] = W8[1 + r][c]
+        pack_fill_kernel<<<dim3(64, tab.n), 256, 0, stream>>>(*raw, tab, scale, tp);
+        NA_CHECK_LAUNCH();
+    }
     // tensor-core operand image (hi/lo fp16, UMMA K-major SWIZZLE_128B stages) derived from the fp32 planes
     const TcPackLayout T = tc_pack_layout(packed_f32_bytes(desc->multires_view));
     NA_TRY(tc_pack(packed, L, (unsigned char*)packed_, T, stream));

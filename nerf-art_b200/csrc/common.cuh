@@ -68,6 +68,24 @@ __host__ inline PackF32 pack_layout_f32(int multires_view) {
     return L;
 }
 
+// Extra fp32 planes only the backward pass needs ("train pack"; follows the tensor-core images in the packed buffer,
+// offset train_pack_off()).  Offsets in floats from the start of the train pack.  All planes [256][256], row stride 256.
+struct PackTrain {
+    size_t rad_w[4];                // [0]: layer 0, feature columns  B[r=out][c=feat]; [1..3]: B[r=out][c=in]
+    size_t rad_w0_small;            // layer 0, small-input columns   B[r=out][c=small idx] (zero beyond small_dim)
+    size_t w8_feat;                 // SDF head rows 1..256           B[r=feat][c=in]
+    size_t total;
+};
+__host__ inline PackTrain pack_layout_train() {
+    PackTrain T; size_t o = 0;
+    for (int i = 0; i < 4; ++i) { T.rad_w[i] = o; o += (size_t)W * W; }
+    T.rad_w0_small = o; o += (size_t)W * W;
+    T.w8_feat = o; o += (size_t)W * W;
+    T.total = o;
+    return T;
+}
+size_t train_pack_off(int multires_view);           // bytes from the start of the packed buffer (api.cu)
+
 // ---------------------------------------------------------------------------------------------
 // where the points of one MLP launch come from, and where results go
 // ---------------------------------------------------------------------------------------------

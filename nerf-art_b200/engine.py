@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (NaNetDesc, NaRawParams, NaVolsdfCfg, NaVolsdfOut, NaNeusCfg, NaNeusOut, NaSurfaceCfg, NaSurfaceOut, check, ptr,
+from ._lib import (NaTrainCfg, NaRawGrads, NaNetDesc, NaRawParams, NaVolsdfCfg, NaVolsdfOut, NaNeusCfg, NaNeusOut, NaSurfaceCfg, NaSurfaceOut, check, ptr,
                    stream_ptr, NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS, NA_RAYCAST_ROOT_FINDING, NA_RAYCAST_SPHERE_TRACING, PRECISIONS)
 
 _LINSPACE_CACHE = {}
@@ -185,6 +185,63 @@ class NetEngine:
                                        ptr(s_dev), ptr(tc), ptr(ui), ptr(u_rand.contiguous()) if u_rand is not None else None,
                                        C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_neus_render_fwd')
         return o
+
+    # ------------------------------------------------------------------------------------------
+    # backward of the render (second pass of the fine-tune step; include/nerfart_b200.h "Backward of the render")
+    def grad_zero(self):
+        """Fresh gradient accumulators: GradPack (effective-weight gradients) and the float64 scalars
+        [d loss/d ln_beta or ln_s, eikonal loss].  The counterpart of optimizer.zero_grad() (volsdf.py:753)."""
+        L = _lib.lib()
+        dev = self._device()
+        n = L.na_grad_pack_bytes(C.byref(self.desc)) // 4
+        if getattr(self, '_gpack', None) is None or self._gpack.device != dev:
+            self._gpack = torch.zeros(n, dtype=torch.float32, device=dev)
+            self._gscal = torch.zeros(2, dtype=torch.float64, device=dev)
+        else:
+            self._gpack.zero_(); self._gscal.zero_()
+
+    def render_bwd(self, rays_o, rays_d, scal, fwd, grad_rgb, *, w_eikonal, eikonal_count, white_bkgd, speed_factor,
+                   train_surface=True, train_radiance=True):
+        """Accumulate the gradients of one ray patch.  `fwd` = the flat detailed outputs of `volsdf_render` / `neus_render`
+        for the same rays; `scal` = {alpha, beta} (VolSDF) or {s} (NeuS) on the device; grad_rgb [n,3]."""
+        L = _lib.lib()
+        dev = rays_o.device
+        n = rays_o.shape[0]
+        neus = self.framework != 'volsdf'
+        d_all = fwd['d_all'] if neus else fwd['d_vals']
+        P = d_all.shape[-1]
+        cfg = NaTrainCfg(int(P), float(w_eikonal), int(eikonal_count), int(bool(white_bkgd)), float(speed_factor),
+                         int(bool(train_surface)), int(bool(train_radiance)), 0)
+        nbytes = L.na_train_workspace_bytes(C.byref(self.desc), n, P)
+        if getattr(self, '_tws', None) is None or self._tws.device != dev or self._tws.numel() < nbytes:
+            self._tws = None
+            self._tws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        g = grad_rgb.reshape(-1, 3).float().contiguous()
+        fn = L.na_neus_render_bwd if neus else L.na_volsdf_render_bwd
+        with torch.cuda.device(dev):
+            check(fn(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n, ptr(scal), ptr(d_all),
+                     ptr(fwd['sdf']), ptr(fwd['radiance']), ptr(fwd['nablas']), ptr(g), ptr(self._gpack),
+                     C.c_void_p(self._gscal.data_ptr()), ptr(self._tws), self._tws.numel(), stream_ptr(dev)),
+                  'na_neus_render_bwd' if neus else 'na_volsdf_render_bwd')
+
+    def unpack_grads(self, train_surface=True, train_radiance=True):
+        """GradPack -> list of (parameter, gradient) for bias / weight_g / weight_v of the trained layers, plus the scalars."""
+        L = _lib.lib()
+        dev = self._device()
+        raw, keep = self._raw_params()
+        out = NaRawGrads()
+        pairs = []
+        layers = list(self.surface.surface_fc_layers) + (list(self.radiance.layers) if self.radiance is not None else [])
+        for i, l in enumerate(layers):
+            if (i < 9 and not train_surface) or (i >= 9 and not train_radiance):
+                continue
+            gb, gg, gv = torch.zeros_like(l.bias), torch.zeros_like(l.weight_g), torch.zeros_like(l.weight_v)
+            out.bias[i], out.weight_g[i], out.weight_v[i] = gb.data_ptr(), gg.data_ptr(), gv.data_ptr()
+            pairs += [(l.bias, gb), (l.weight_g, gg), (l.weight_v, gv)]
+        with torch.cuda.device(dev):
+            check(L.na_unpack_grads(C.byref(self.desc), C.byref(raw), ptr(self._gpack), C.byref(out), stream_ptr(dev)), 'na_unpack_grads')
+        del keep
+        return pairs, self._gscal
 
     # ------------------------------------------------------------------------------------------
     def _surface_cfg(self, algo, near, far, N_steps, N_secant_steps, N_iters, logit_tau, fill_inf):

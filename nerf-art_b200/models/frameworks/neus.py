@@ -12,6 +12,8 @@ import torch.nn as nn
 from ..base import ImplicitSurface, RadianceNet
 from ...engine import NetEngine
 
+FIX_MODULE = "radiance_net"          # neus.py:28
+
 
 class NeuS(nn.Module):
     def __init__(self, variance_init=0.05, speed_factor=1.0, input_ch=3, W_geo_feat=-1, use_outside_nerf=False,
@@ -101,19 +103,50 @@ class SingleRenderer(nn.Module):
         return volume_render(rays_o, rays_d, self.model, **kwargs)
 
 
-class Trainer(nn.Module):
-    """See volsdf.Trainer: the stylisation step (neus.py:493-628) needs backward + CLIP kernels (later SURVEY.md 8 rows)."""
+def render_patch(model, ro, rd, obj_bounding_radius=1.0, perturb=False, white_bkgd=False, N_samples=64, N_importance=64,
+                 N_upsample_iters=4, u_rand=None, **dummy_kwargs):
+    """Forward render of one flat ray patch with the detailed outputs the backward needs (defaults of neus.py:142-170).
+    Returns (flat outputs, {s} on the device)."""
+    s = model.forward_s().detach().reshape(1).float().contiguous()
+    o = model.engine().neus_render(ro, rd, s, obj_bounding_radius=obj_bounding_radius, N_samples=N_samples,
+                                   N_importance=N_importance, N_upsample_iters=N_upsample_iters, white_bkgd=white_bkgd,
+                                   perturb=perturb, detailed_output=True, u_rand=u_rand)
+    return o, s
 
-    def __init__(self, model: NeuS, device_ids=[0], batched=True, is_finetune=False, target_hw: list = None):
+
+class Trainer(nn.Module):
+    """The reference's Trainer (neus.py:427-628): `forward` implements the CLIP fine-tune branch (520-576) on the CUDA
+    backward kernels (radiance_net frozen, neus.py:28,455-456); the reconstruction branch raises.  See volsdf.Trainer."""
+
+    def __init__(self, model: NeuS, device_ids=[0], batched=True, is_finetune=False, target_hw: list = None, loss_dict=None):
         super().__init__()
         self.model = model
         self.renderer = SingleRenderer(model)
         self.device = device_ids[0] if isinstance(device_ids, (list, tuple)) and len(device_ids) else 0
         self.is_finetune = is_finetune
+        self.neg_texts = None
         self.target_hw = target_hw if target_hw is not None else [960, 540]
+        self.loss_dict = loss_dict
+        if is_finetune:
+            self.model.fix_module(FIX_MODULE)
 
-    def forward(self, args, indices, model_input, ground_truth, render_kwargs_train: dict, it: int, optimizer=None):
-        raise NotImplementedError('nerfart_b200: Trainer.forward needs the backward + CLIP kernels (SURVEY.md 8a rows a17-a21)')
+    def _losses(self):
+        if self.loss_dict is None:
+            from ...criteria import build_loss_dict
+            self.loss_dict = build_loss_dict(self.target_hw, next(self.model.parameters()).device)
+        return self.loss_dict
+
+    def forward(self, args, indices, model_input, ground_truth, render_kwargs_train: dict, it: int, device='cuda', optimizer=None):
+        if not args.training.is_finetune:
+            raise NotImplementedError('nerfart_b200: only the CLIP fine-tune branch of Trainer.forward (neus.py:520-576) is built')
+        from ._finetune import finetune_forward
+        self._losses()
+        losses, select_inds = finetune_forward(self, 'neus', args, model_input, ground_truth, render_kwargs_train, optimizer,
+                                               lambda ro, rd, **kw: render_patch(self.model, ro, rd, **kw))
+        extras = {}
+        extras['scalars'] = {'1/s': 1. / self.model.forward_s().data}
+        extras['select_inds'] = select_inds
+        return OrderedDict([('losses', losses), ('extras', extras)])
 
 
 def get_model(args, render_target=None):

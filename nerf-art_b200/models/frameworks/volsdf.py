@@ -18,6 +18,8 @@ import torch.nn as nn
 from ..base import ImplicitSurface, RadianceNet
 from ...engine import NetEngine
 
+FIX_MODULE = None          # volsdf.py:7-8
+
 
 class VolSDF(nn.Module):
     def __init__(self, beta_init=0.1, speed_factor=1.0, input_ch=3, W_geo_feat=-1, obj_bounding_radius=3.0,
@@ -81,8 +83,6 @@ def volume_render(rays_o, rays_d, model: VolSDF, near=0.0, far=6.0, obj_bounding
     `u_final` [N_rays, N_importance] optionally injects the uniform draws used when perturb=True (rend_util.py:307)."""
     if use_nerfplusplus or not use_view_dirs:
         raise NotImplementedError('nerf++ background / use_view_dirs=False are not shipped configurations')
-    if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()) and dummy_kwargs.get('_need_grad', False):
-        raise NotImplementedError('backward kernels are a "next" row (SURVEY.md 8a a17)')
     B = rays_d.shape[0] if batched else None
     ro = rays_o.reshape(-1, 3).float().contiguous()
     rd = rays_d.reshape(-1, 3).float().contiguous()
@@ -129,22 +129,56 @@ class SingleRenderer(nn.Module):
         return volume_render(rays_o, rays_d, self.model, **kwargs)
 
 
-class Trainer(nn.Module):
-    """Holds the renderer like the reference's Trainer (volsdf.py:627-647).  `forward` (the training / CLIP fine-tune
-    step, volsdf.py:689-837) needs the backward kernels and the CLIP encoder, which are later rows of SURVEY.md 8
-    (a17-a21); it raises until they exist rather than silently running something else."""
+def render_patch(model: VolSDF, ro, rd, near=0.0, far=6.0, perturb=False, white_bkgd=False, max_upsample_steps=5, N_samples=128,
+                 N_importance=64, max_bisection_steps=10, epsilon=0.1, u_final=None, **dummy_kwargs):
+    """Forward render of one flat ray patch with the detailed per-sample outputs the backward needs (volume_render's
+    defaults, volsdf.py:389-424).  Returns (flat outputs, {alpha, beta} on the device)."""
+    alpha, beta = model.forward_ab()
+    ab = torch.cat([alpha.detach().reshape(1), beta.detach().reshape(1)]).float().contiguous()
+    o = model.engine().volsdf_render(ro, rd, ab, near=near, far=far, N_samples=N_samples, N_importance=N_importance,
+                                     max_upsample_steps=max_upsample_steps, max_bisection_steps=max_bisection_steps,
+                                     epsilon=epsilon, white_bkgd=white_bkgd, perturb=perturb, calc_normal=False,
+                                     detailed_output=True, u_final=u_final)
+    return o, ab
 
-    def __init__(self, model: VolSDF, device_ids=[0], batched=True, is_finetune=False, target_hw: list = None):
+
+class Trainer(nn.Module):
+    """The reference's Trainer (volsdf.py:627-837).  `forward` implements the CLIP fine-tune branch (719-786) on the CUDA
+    backward kernels; the from-scratch reconstruction branch (787-823) is outside the hot path and raises.
+    `loss_dict` (extension): the four style losses; by default they are built from nerfart_b200.criteria like the
+    reference builds them from criteria/ (volsdf.py:639-645)."""
+
+    def __init__(self, model: VolSDF, device_ids=[0], batched=True, is_finetune=False, target_hw: list = None, loss_dict=None):
         super().__init__()
         self.model = model
         self.renderer = SingleRenderer(model)
         self.device = device_ids[0] if isinstance(device_ids, (list, tuple)) and len(device_ids) else 0
         self.is_finetune = is_finetune
+        self.neg_texts = None
         self.target_hw = target_hw if target_hw is not None else [960, 540]
+        self.loss_dict = loss_dict
+        if is_finetune:
+            self.model.fix_module(FIX_MODULE)                           # volsdf.py:8,646-647: nothing is frozen for VolSDF
+
+    def _losses(self):
+        if self.loss_dict is None:
+            from ...criteria import build_loss_dict
+            self.loss_dict = build_loss_dict(self.target_hw, next(self.model.parameters()).device)
+        return self.loss_dict
 
     def forward(self, args, indices, model_input, ground_truth, render_kwargs_train: dict, it: int, optimizer=None):
-        raise NotImplementedError('nerfart_b200: Trainer.forward needs the backward + CLIP kernels (SURVEY.md 8a rows a17-a21), '
-                                  'not built in this round; the render path (render_fn / volume_render) is.')
+        if not args.training.is_finetune:
+            raise NotImplementedError('nerfart_b200: only the CLIP fine-tune branch of Trainer.forward (volsdf.py:719-786) is '
+                                      'built; from-scratch reconstruction (787-823) is outside the accelerated hot path')
+        from ._finetune import finetune_forward
+        self._losses()
+        losses, select_inds = finetune_forward(self, 'volsdf', args, model_input, ground_truth, render_kwargs_train, optimizer,
+                                               lambda ro, rd, **kw: render_patch(self.model, ro, rd, **kw))
+        extras = {}
+        alpha, beta = self.model.forward_ab()
+        extras['scalars'] = {'beta': beta.data, 'alpha': alpha.data}
+        extras['select_inds'] = select_inds
+        return OrderedDict([('losses', losses), ('extras', extras)])
 
 
 def get_model(args, render_target=None):

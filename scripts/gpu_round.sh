@@ -30,6 +30,9 @@ for s in $STEPS; do
     teststc) NA_PRECISION=tc timeout 1500 python -m pytest tests -m gpu -q -s > $OUT/pytest_gpu_tc.log 2>&1; echo "pytest tc exit $?"; tail -40 $OUT/pytest_gpu_tc.log ;;
     ncutc) timeout 900 ncu --set full --clock-control none --import-source on -k regex:mlp_t -c 2 -f -o $OUT/prof_mlp_tc python scripts/prof_mlp.py tc > $OUT/ncu_tc.log 2>&1; echo "ncu tc exit $?"; tail -3 $OUT/ncu_tc.log ;;
     launchestc) NA_PRECISION=tc NA_BENCH_LIGHT=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_tc.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/launches_tc_bench.log 2>&1; echo "ncu launches exit $?"; tail -3 $OUT/launches_tc.csv ;;
+    traintests) timeout 900 python -m pytest tests/test_gpu_train.py -m gpu -q -s -x > $OUT/pytest_train.log 2>&1; echo "pytest train exit $?"; tail -40 $OUT/pytest_train.log ;;
+    trainsan) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_train.py -m gpu -q -s -x -k "noeik or neus_backward" > $OUT/train_san.log 2>&1; echo "train sanitize exit $?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" $OUT/train_san.log | head -20 ;;
+    benchtrain) timeout 900 python bench.py --workload train --steps 2 --warmup 1 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "bench train exit $?"; tail -c 2500 $OUT/bench_train.json; tail -5 $OUT/bench_train.err ;;
     *) echo "unknown step $s" ;;
   esac
 done

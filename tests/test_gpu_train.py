@@ -1,0 +1,266 @@
+"""GPU: backward of the render (csrc/train.cu through the C ABI) against
+  (1) parameter gradients from the UNMODIFIED reference's autograd (tests/golden/train_*.npz) and
+  (2) the float64 backward oracle on larger seeded inputs (several tiles, several sample splits, ragged last tile),
+and the fine-tune step `Trainer.forward` end to end with an injected style loss.
+
+Tolerances: the kernels compute in fp32 (CUDA cores) and sum over samples with atomics; every gradient tensor must agree
+with the reference within 2e-3 of its own largest entry (measured: see DESIGN.md section 9), scalars within 2e-3 relative.
+"""
+import types
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_volsdf, make_neus, golden, fx
+import nerfart_oracle_train as ot
+from test_oracle_train import compare_grads
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+REL_TOL = 2e-3
+
+
+def t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=DEV)
+
+
+def state(m):
+    return {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+
+
+def normalize(d):
+    return d / d.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+
+
+def volsdf_fwd_at(m, ro, rd, d_all):
+    """the detailed forward outputs at given depths, from the product's own network kernel (VolSDF.forward, volsdf.py:359-370)"""
+    n, P = d_all.shape
+    dn = normalize(rd)
+    pts = ro[:, None, :] + dn[:, None, :] * d_all[:, :, None]
+    with torch.no_grad():
+        rad, sdf, nab = m.forward(pts.reshape(-1, 3), dn[:, None, :].expand(n, P, 3).reshape(-1, 3))
+    return dict(d_vals=d_all.contiguous(), sdf=sdf.reshape(n, P).contiguous(), nablas=nab.reshape(n, P, 3).contiguous(),
+                radiance=rad.reshape(n, P, 3).contiguous())
+
+
+def neus_fwd_at(m, ro, rd, d_all):
+    n, P = d_all.shape
+    dn = normalize(rd)
+    pts = ro[:, None, :] + dn[:, None, :] * d_all[:, :, None]
+    d_mid = 0.5 * (d_all[:, 1:] + d_all[:, :-1])
+    pm = ro[:, None, :] + dn[:, None, :] * d_mid[:, :, None]
+    with torch.no_grad():
+        _, sdf, nab = m.forward(pts.reshape(-1, 3), dn[:, None, :].expand(n, P, 3).reshape(-1, 3))
+        rad = m.forward_radiance(pm.reshape(-1, 3), dn[:, None, :].expand(n, P - 1, 3).reshape(-1, 3))
+    return dict(d_all=d_all.contiguous(), sdf=sdf.reshape(n, P).contiguous(), nablas=nab.reshape(n, P, 3).contiguous(),
+                radiance=rad.reshape(n, P - 1, 3).contiguous())
+
+
+def product_grads(m, framework, ro, rd, fwd, G, w_eik, white, train_radiance=True, eik_count=None):
+    eng = m.engine()
+    eng.pack()
+    eng.grad_zero()
+    if framework == 'volsdf':
+        a, b = m.forward_ab()
+        scal = torch.cat([a.detach().reshape(1), b.detach().reshape(1)]).float().contiguous()
+        P = fwd['d_vals'].shape[1]
+    else:
+        scal = m.forward_s().detach().reshape(1).float().contiguous()
+        P = fwd['d_all'].shape[1]
+    eng.render_bwd(ro.contiguous(), rd.contiguous(), scal, fwd, G, w_eikonal=w_eik, eikonal_count=eik_count or ro.shape[0] * P,
+                   white_bkgd=white, speed_factor=m.speed_factor, train_surface=True, train_radiance=train_radiance)
+    pairs, scal_out = eng.unpack_grads(True, train_radiance)
+    torch.cuda.synchronize()
+    names = {id(p): k for k, p in m.named_parameters()}
+    grads = OrderedDict((names[id(p)], g.cpu().numpy()) for p, g in pairs)
+    return grads, scal_out.cpu().numpy()
+
+
+@pytest.mark.parametrize('name', ['train_volsdf_b0.1', 'train_volsdf_b0.01_white', 'train_volsdf_noeik'])
+def test_volsdf_backward_matches_reference_autograd(name):
+    g = golden(name)
+    m = make_volsdf(float(g['beta_init']), float(g['bump']), device=DEV)
+    m.engine().precision = 'fp32'
+    ro, rd = t(g['rays_o']), t(g['rays_d'])
+    fwd = volsdf_fwd_at(m, ro, rd, t(g['d_vals']))
+    grads, scal = product_grads(m, 'volsdf', ro, rd, fwd, t(g['G']), float(g['w_eikonal']), bool(g['white_bkgd']))
+    grads['ln_beta'] = np.array([scal[0]], np.float32)
+    assert compare_grads(grads, g, REL_TOL) == 9 * 3 + 5 * 3 + 1
+    assert abs(scal[1] - float(g['eikonal_loss'])) <= 1e-5 + 1e-4 * float(g['eikonal_loss'])
+    print(name, 'ln_beta grad', scal[0], float(g['grad.ln_beta'][0]), 'eik', scal[1], float(g['eikonal_loss']))
+
+
+def test_neus_backward_matches_reference_autograd():
+    g = golden('train_neus')
+    m = make_neus(float(g['variance_init']), float(g['bump']), device=DEV)
+    m.engine().precision = 'fp32'
+    ro, rd = t(g['rays_o']), t(g['rays_d'])
+    fwd = neus_fwd_at(m, ro, rd, t(g['d_all']))
+    grads, scal = product_grads(m, 'neus', ro, rd, fwd, t(g['G']), float(g['w_eikonal']), False, train_radiance=False)
+    grads['ln_s'] = np.array([scal[0]], np.float32)
+    assert compare_grads(grads, g, REL_TOL) == 9 * 3 + 1
+    assert abs(scal[1] - float(g['eikonal_loss'])) <= 1e-5 + 1e-4 * float(g['eikonal_loss'])
+
+
+def rel_err(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_volsdf_backward_vs_oracle_many_tiles(precision):
+    """333 rays x 48 points = 15 984 samples = 124.9 tiles (ragged), sample depths from the product's own sampler."""
+    m = make_volsdf(0.05, 0.5, device=DEV)
+    m.engine().precision = precision
+    from nerfart_b200.models.frameworks.volsdf import render_patch
+    from nerfart_b200.utils import rend_util
+    c2w, K = fx.tilted_camera(37, 9)
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(DEV), K[None].to(DEV), 37, 9)
+    ro, rd = ro[0].contiguous(), rd[0].contiguous()
+    fwd, _ = render_patch(m, ro, rd, N_samples=32, N_importance=16, max_upsample_steps=6)
+    gen = torch.Generator(device='cpu'); gen.manual_seed(3)
+    G = (0.05 * torch.randn(ro.shape[0], 3, generator=gen)).to(DEV)
+    grads, scal = product_grads(m, 'volsdf', ro, rd, fwd, G, 0.1, False)
+    net = ot.TrainNet(state(m), 'volsdf')
+    og, oeik, orgb = ot.volsdf_backward(net, ro.cpu().numpy(), rd.cpu().numpy(), fwd['d_vals'].cpu().numpy(), G.cpu().numpy(), 0.1, False)
+    worst = max(rel_err(grads[k], np.asarray(og[k]).reshape(grads[k].shape)) for k in grads)
+    print(precision, 'worst relative gradient error vs oracle', worst, 'ln_beta', scal[0], float(og['ln_beta'][0]), 'eik', scal[1], oeik)
+    assert worst < REL_TOL
+    assert abs(scal[0] - float(og['ln_beta'][0])) <= REL_TOL * abs(float(og['ln_beta'][0])) + 1e-6
+    assert abs(scal[1] - oeik) <= 1e-4 * oeik + 1e-6
+    assert np.abs(fwd['rgb'].cpu().numpy() - orgb).max() < (1e-4 if precision == 'fp32' else 1e-3)
+
+
+def test_backward_accumulates_over_patches_and_is_deterministic_in_structure():
+    """two half patches accumulate to the gradient of the whole patch (same eikonal normaliser): the GradPack is additive"""
+    g = golden('train_volsdf_b0.1')
+    m = make_volsdf(float(g['beta_init']), float(g['bump']), device=DEV)
+    m.engine().precision = 'fp32'
+    ro, rd, G = t(g['rays_o']), t(g['rays_d']), t(g['G'])
+    fwd = volsdf_fwd_at(m, ro, rd, t(g['d_vals']))
+    n, P = fwd['d_vals'].shape
+    whole, sw = product_grads(m, 'volsdf', ro, rd, fwd, G, 0.1, False)
+    eng = m.engine(); eng.grad_zero()
+    a, b = m.forward_ab()
+    scal = torch.cat([a.detach().reshape(1), b.detach().reshape(1)]).float().contiguous()
+    for sl in (slice(0, 20), slice(20, n)):
+        part = {k: v[sl].contiguous() for k, v in fwd.items()}
+        eng.render_bwd(ro[sl].contiguous(), rd[sl].contiguous(), scal, part, G[sl], w_eikonal=0.1, eikonal_count=n * P,
+                       white_bkgd=False, speed_factor=m.speed_factor)
+    pairs, sp = eng.unpack_grads()
+    names = {id(p): k for k, p in m.named_parameters()}
+    for p, gr in pairs:
+        ref = whole[names[id(p)]]
+        assert np.abs(gr.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, names[id(p)]
+    np.testing.assert_allclose(sp.cpu().numpy(), sw, rtol=1e-5, atol=1e-8)
+
+
+class _Args(dict):
+    __getattr__ = dict.__getitem__
+
+
+def test_trainer_forward_finetune_step_volsdf(monkeypatch):
+    """Trainer.forward (fine-tune branch) with an injected differentiable style loss: same protocol as the reference
+    (loss already back-propagated, .grad populated, optimizer.zero_grad() called inside), gradients equal to the oracle's."""
+    from nerfart_b200.models.frameworks import volsdf as pv, _finetune
+    monkeypatch.setattr(_finetune, 'BATCH_SIZE', 500)
+    m = make_volsdf(0.1, 0.5, device=DEV).train()
+    m.engine().precision = 'fp32'
+    H = W = 24
+    target = torch.full((1, H * W, 3), 0.25, device=DEV)
+    wts = torch.linspace(0.5, 1.5, H * W * 3, device=DEV).reshape(1, 3, H, W)
+
+    def clip_like(gt, s_text, pred, t_text):
+        return ((pred - gt) ** 2 * wts).mean()
+    zero = lambda *a, **k: torch.zeros((), device=DEV)
+    trainer = pv.Trainer(m, is_finetune=True, target_hw=[H, W],
+                         loss_dict={'clip': clip_like, 'perceptual': None, 'contrastive': zero, 'patchnce': zero})
+    trainer.neg_texts = ['a'] * 10
+    args = _Args(training=_Args(is_finetune=True), data=_Args(downscale=2),
+                 model=_Args(radiance=_Args(use_view_dirs=True)),
+                 finetune=_Args(use_eikonal=True, w_eikonal=0.1, w_clip=1.0, w_perceptual=2.0, w_contrastive=0.2, w_patchnce=0.1,
+                                src_text='photo', target_text='painting'))
+    c2w, K = fx.tilted_camera(H, W)
+    kw = dict(near=0.0, far=6.0, batched=True, perturb=False, white_bkgd=False, max_upsample_steps=6, use_nerfplusplus=False,
+              obj_bounding_radius=3.0, H=H, W=W, N_samples=32, N_importance=16)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)                                  # must be cleared by the zero_grad() inside
+    ret = trainer(args, None, {'intrinsics': K[None], 'c2w': c2w[None]}, {'rgb': target.cpu()}, kw, 0, optimizer=opt)
+    assert ret['losses'].dim() == 0 and set(ret['extras']) == {'scalars', 'select_inds'}
+    # oracle: same image gradient, same patches, depths from the product's deterministic sampler
+    from nerfart_b200.utils import rend_util
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(DEV), K[None].to(DEV), H, W)
+        rgb, _, _ = trainer.renderer(ro, rd, detailed_output=False, require_nablas=True, **kw)
+    rgb = rgb.detach().requires_grad_(True)
+    loss = clip_like(target.reshape(1, H, W, 3).permute(0, 3, 1, 2), '', rgb.reshape(1, H, W, 3).permute(0, 3, 1, 2), '')
+    loss.backward()
+    assert abs(float(loss) - float(ret['losses'])) < 1e-6
+    G = rgb.grad[0]
+    net = ot.TrainNet(state(m), 'volsdf')
+    total = None
+    for i in range(0, H * W, 500):
+        fwd, _ = pv.render_patch(m, ro[0, i:i + 500].contiguous(), rd[0, i:i + 500].contiguous(), **kw)
+        og, _, _ = ot.volsdf_backward(net, ro[0, i:i + 500].cpu().numpy(), rd[0, i:i + 500].cpu().numpy(), fwd['d_vals'].cpu().numpy(),
+                                      G[i:i + 500].cpu().numpy(), 0.1, False)
+        total = og if total is None else OrderedDict((k, total[k] + og[k]) for k in og)
+    worst = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        worst = max(worst, rel_err(p.grad.cpu().numpy(), np.asarray(total[k]).reshape(tuple(p.shape))))
+    print('Trainer.forward: worst relative parameter-gradient error vs oracle', worst)
+    assert worst < REL_TOL
+    opt.step()
+
+
+def test_trainer_forward_finetune_step_neus(monkeypatch):
+    from nerfart_b200.models.frameworks import neus as pn, _finetune
+    monkeypatch.setattr(_finetune, 'BATCH_SIZE', 300)
+    m = make_neus(0.05, 0.5, device=DEV).train()
+    m.engine().precision = 'fp32'
+    H = W = 20
+    target = torch.full((1, H * W, 3), 0.25, device=DEV)
+
+    def clip_like(gt, s_text, pred, t_text):
+        return ((pred - gt) ** 2).mean()
+    zero = lambda *a, **k: torch.zeros((), device=DEV)
+    trainer = pn.Trainer(m, is_finetune=True, target_hw=[H, W],
+                         loss_dict={'clip': clip_like, 'perceptual': None, 'contrastive': zero, 'patchnce': zero})
+    trainer.neg_texts = ['a'] * 10
+    assert not any(p.requires_grad for p in m.radiance_net.parameters())            # neus.py:28
+    args = _Args(training=_Args(is_finetune=True), data=_Args(downscale=2),
+                 model=_Args(radiance=_Args(use_view_dirs=True)),
+                 finetune=_Args(use_eikonal=True, w_eikonal=0.1, w_clip=1.0, w_perceptual=2.0, w_contrastive=0.2, w_patchnce=0.1,
+                                src_text='photo', target_text='painting'))
+    c2w, K = fx.tilted_camera(H, W)
+    c2w = c2w.clone(); c2w[:3, 3] *= 0.6
+    kw = dict(upsample_algo='official_solution', N_nograd_samples=2048, N_upsample_iters=4, N_outside=0, obj_bounding_radius=1.0,
+              batched=True, perturb=False, white_bkgd=False, H=H, W=W, N_samples=32, N_importance=16)
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4)
+    ret = trainer(args, None, {'intrinsics': K[None], 'c2w': c2w[None]}, {'rgb': target.cpu()}, kw, 0, optimizer=opt)
+    from nerfart_b200.utils import rend_util
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(DEV), K[None].to(DEV), H, W)
+        rgb, _, _ = trainer.renderer(ro, rd, detailed_output=False, **kw)
+    rgb = rgb.detach().requires_grad_(True)
+    ((rgb - target) ** 2).mean().backward()
+    G = rgb.grad[0]
+    net = ot.TrainNet(state(m), 'neus')
+    total = None
+    for i in range(0, H * W, 300):
+        fwd, _ = pn.render_patch(m, ro[0, i:i + 300].contiguous(), rd[0, i:i + 300].contiguous(), **kw)
+        og, _, _ = ot.neus_backward(net, ro[0, i:i + 300].cpu().numpy(), rd[0, i:i + 300].cpu().numpy(), fwd['d_all'].cpu().numpy(),
+                                    G[i:i + 300].cpu().numpy(), 0.1, False)
+        total = og if total is None else OrderedDict((k, total[k] + og[k]) for k in og)
+    worst = 0.0
+    for k, p in m.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None, k
+            continue
+        worst = max(worst, rel_err(p.grad.cpu().numpy(), np.asarray(total[k]).reshape(tuple(p.shape))))
+    print('NeuS Trainer.forward: worst relative parameter-gradient error vs oracle', worst)
+    assert worst < REL_TOL
+    opt.step()
