@@ -155,7 +155,12 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('NA_PRECISION', 'auto'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='render', choices=['render', 'train'],
+                    help="'render' (default): BASELINE configs[1]; 'train': the fine-tune step, see bench_train.py")
     args = ap.parse_args()
+    if args.workload == 'train':
+        import bench_train
+        return bench_train.main(args)
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':

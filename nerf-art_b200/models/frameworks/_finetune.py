@@ -17,6 +17,7 @@ import torch
 from einops import rearrange
 
 from ...utils import rend_util
+from ... import parallel
 
 BATCH_SIZE = 1200            # volsdf.py:754 / neus.py:541 ("hardcoded for 3090Ti")
 
@@ -106,7 +107,12 @@ def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *
     g = gradient.reshape(-1, 3).float().contiguous()
     n = ro.shape[0]
     n_patches = 0
-    for i in range(0, n, batch_size):
+    # one process per GPU: patches are dealt round-robin to the ranks, the packed gradient is summed once per step
+    # (replaces DDP's bucketed all-reduce, train.py:155)
+    world, rank = parallel.world_rank()
+    for pi, i in enumerate(range(0, n, batch_size)):
+        if pi % world != rank:
+            continue
         rop, rdp = ro[i:i + batch_size].contiguous(), rd[i:i + batch_size].contiguous()
         fwd, scal = render_patch(rop, rdp)
         P = (fwd['d_vals'] if framework == 'volsdf' else fwd['d_all']).shape[-1]
@@ -114,6 +120,7 @@ def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *
                        white_bkgd=white_bkgd, speed_factor=model.speed_factor, train_surface=train_surface,
                        train_radiance=train_radiance)
         n_patches += 1
+    parallel.allreduce_sum(eng._gpack, eng._gscal)
     scalar_param = model.ln_beta if framework == 'volsdf' else model.ln_s
     scal = _assign_grads(model, eng, scalar_param, train_surface, train_radiance)
     return scal, n_patches
@@ -133,9 +140,14 @@ def finetune_forward(trainer, framework, args, model_input, ground_truth, render
     rays_o, rays_d, select_inds = rend_util.get_rays(c2w, intrinsics, H, W, -1)     # fine-tune: all rays, not shuffled
     target_rgb = torch.gather(ground_truth['rgb'].to(device), 1, torch.stack(3 * [select_inds], -1))
     use_eik = bool(args.finetune.use_eikonal)
-    with torch.no_grad():                                                            # pass 1
-        rgb, depth_v, _ = trainer.renderer(rays_o, rays_d, detailed_output=False, use_view_dirs=args.model.radiance.use_view_dirs,
+    world, rank = parallel.world_rank()
+    n_rays = rays_o.shape[1]
+    lo, hi, _ = parallel.ray_block(n_rays, rank, world)
+    with torch.no_grad():                                                            # pass 1 (this rank's block of rays)
+        rgb, depth_v, _ = trainer.renderer(rays_o[:, lo:hi], rays_d[:, lo:hi], detailed_output=False,
+                                           use_view_dirs=args.model.radiance.use_view_dirs,
                                            require_nablas=use_eik or args.model.radiance.use_view_dirs, **render_kwargs_train)
+        rgb = parallel.gather_tiles(rgb[0], n_rays)[None]                            # every rank scores the whole image
     rgb = rgb.detach().requires_grad_(True)
     losses = calc_style_loss(trainer, rgb, target_rgb, args, H)
     losses.backward()

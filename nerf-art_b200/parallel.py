@@ -8,6 +8,19 @@ import torch
 import torch.distributed as dist
 
 
+def world_rank(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def allreduce_sum(*tensors, group=None):
+    """Sum the packed gradient accumulators over the ranks (one collective per tensor per training step)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
 def ray_block(n_rays, rank, world):
     """Contiguous block [lo, hi) of rank `rank` in row-major pixel order; every block has ceil(n/world) slots (the last
     ones may be short or empty) so the gathered buffer *is* the image."""

@@ -58,3 +58,67 @@ def test_sharded_render_equals_single_rank_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, *_ in res), res
+
+
+class _FakeEngine:
+    """stands in for NetEngine in backward_patches: the 'gradient' of a patch is a per-ray function summed over the patch"""
+    def __init__(self):
+        self.calls = []
+
+    def grad_zero(self):
+        self._gpack = torch.zeros(4, dtype=torch.float64); self._gscal = torch.zeros(2, dtype=torch.float64)
+
+    def render_bwd(self, ro, rd, scal, fwd, g, **kw):
+        self.calls.append((int(ro.shape[0]), kw['eikonal_count']))
+        self._gpack += torch.stack([ro.double().sum(), rd.double().sum(), (g.double() * ro.double()).sum(), torch.tensor(float(ro.shape[0]), dtype=torch.float64)])
+        self._gscal += torch.tensor([g.double().sum(), 1.0], dtype=torch.float64)
+
+    def unpack_grads(self, ts, tr):
+        return [], self._gscal
+
+
+class _FakeModel:
+    def __init__(self):
+        self.implicit_surface = torch.nn.Linear(1, 1); self.radiance_net = torch.nn.Linear(1, 1)
+        self.ln_beta = torch.nn.Parameter(torch.zeros(1)); self.speed_factor = 1.0
+        self._e = _FakeEngine()
+
+    def engine(self):
+        return self._e
+
+
+def _train_worker(rank, world, port, n, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from nerfart_b200.models.frameworks import _finetune
+    g = torch.Generator().manual_seed(5)
+    ro = torch.randn(1, n, 3, generator=g); rd = torch.randn(1, n, 3, generator=g); G = torch.randn(1, n, 3, generator=g)
+    m = _FakeModel()
+    fake_patch = lambda a, b: ({'d_vals': torch.zeros(a.shape[0], 6)}, None)
+    scal, _ = _finetune.backward_patches(m, 'volsdf', ro, rd, G, fake_patch, w_eikonal=0.1, white_bkgd=False, batch_size=100)
+    q.put((rank, m._e._gpack.tolist(), scal.tolist(), m._e.calls, m.ln_beta.grad.tolist()))
+    dist.destroy_process_group()
+
+
+def test_training_patches_round_robin_and_gradient_allreduce_gloo():
+    """N>1 training path: patches dealt round-robin, packed gradient + scalars summed once; every rank ends with the
+    single-process result (the per-patch eikonal normaliser is unchanged by the partition)."""
+    world, n = 2, 730                       # 8 patches of 100 rays, the last one short
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    g = torch.Generator().manual_seed(5)
+    ro = torch.randn(1, n, 3, generator=g); rd = torch.randn(1, n, 3, generator=g); G = torch.randn(1, n, 3, generator=g)
+    want = [ro.double().sum().item(), rd.double().sum().item(), (G.double() * ro.double()).sum().item(), float(n)]
+    for rank, gpack, scal, calls, lnb in res:
+        assert all(abs(a - b) < 1e-9 for a, b in zip(gpack, want)), (gpack, want)
+        assert abs(scal[0] - G.double().sum().item()) < 1e-9 and scal[1] == 8.0
+        assert abs(lnb[0] - G.double().sum().item()) < 1e-4
+    assert [c[0] for c in res[0][3]] == [100, 100, 100, 100] and [c[0] for c in res[1][3]] == [100, 100, 100, 30]
+    assert all(c[1] == c[0] * 6 for r in res for c in r[3])
