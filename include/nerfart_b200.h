@@ -256,6 +256,38 @@ int na_neus_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainC
 
 int na_unpack_grads(const NaNetDesc* desc, const NaRawParams* raw, const void* grad_pack, const NaRawGrads* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * CLIP ViT-B/32 image tower: replaces `self.model.encode_image(images)` (criteria/clip_loss.py:206-208,
+ * criteria/contrastive_loss.py:113-115, criteria/patchnce_loss.py:127-129; third-party openai/CLIP `model.visual`) and
+ * its autograd backward w.r.t. the image (the CLIP weights are frozen; NeRF-Art needs d loss / d rendered pixels only).
+ * Weights: fp32 device pointers in the openai/CLIP `visual.*` state-dict layout.                                     */
+typedef struct NaClipLayer {
+    const float *ln_1_w, *ln_1_b;            /* [768]                                                          */
+    const float *in_proj_w, *in_proj_b;      /* attn.in_proj_weight [2304,768] (q|k|v), in_proj_bias [2304]    */
+    const float *out_proj_w, *out_proj_b;    /* attn.out_proj [768,768], [768]                                 */
+    const float *ln_2_w, *ln_2_b;
+    const float *c_fc_w, *c_fc_b;            /* mlp.c_fc [3072,768], [3072]  (QuickGELU follows)               */
+    const float *c_proj_w, *c_proj_b;        /* mlp.c_proj [768,3072], [768]                                   */
+} NaClipLayer;
+typedef struct NaClipWeights {
+    const float* conv1;                      /* visual.conv1.weight [768,3,32,32] (no bias)                    */
+    const float* class_embedding;            /* [768]                                                          */
+    const float* positional_embedding;       /* [50,768]                                                       */
+    const float *ln_pre_w, *ln_pre_b;
+    NaClipLayer layers[12];                  /* visual.transformer.resblocks.{i}                               */
+    const float *ln_post_w, *ln_post_b;
+    const float* proj;                       /* visual.proj [768,512]                                          */
+} NaClipWeights;
+
+size_t na_clip_workspace_bytes(int32_t batch);
+/* images [B,3,224,224] (already resized + CLIP-normalised) -> feats [B,512].  The workspace keeps the activations of this
+ * forward; na_clip_vitb32_encode_bwd must be called with the same workspace and batch before the next forward.           */
+int na_clip_vitb32_encode_fwd(const NaClipWeights* weights, const float* images, int32_t batch, float* feats, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* grad_feats [B,512] -> grad_images [B,3,224,224] */
+int na_clip_vitb32_encode_bwd(const NaClipWeights* weights, const float* grad_feats, int32_t batch, float* grad_images,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

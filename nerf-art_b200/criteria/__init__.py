@@ -1,0 +1,39 @@
+"""Style losses of the CLIP fine-tune step (reference criteria/): one shared CLIP ViT-B/32 image tower on hand-written
+kernels (clip_vit.py), one text-feature cache (text.py), the three CLIP losses (losses.py).
+
+`build_loss_dict(target_hw, device)` returns what the reference's Trainer builds at volsdf.py:639-645.  It needs the
+third-party `clip` package and its ViT-B/32 weights (README.md:27; fetched by `clip.load` on first use) for the TEXT tower
+and as the source of the image-tower weights; offline neither exists, and this function raises instead of substituting
+anything.  `torchvision`'s pretrained VGG16 (criteria/perp_loss.py) is outside the kernel scope: it
+is used as is when its weights are available, else the perceptual term is dropped with a warning.
+"""
+import warnings
+
+from .clip_vit import ClipVisionB32
+from .text import TextFeatures
+from .losses import CLIPLoss, ContrastiveLoss, PatchNCELoss, DirectionLoss       # noqa: F401
+
+
+def make_loss_dict(tower, text, target_hw, perceptual=None):
+    return {'contrastive': ContrastiveLoss(tower, text), 'patchnce': PatchNCELoss(tower, text, target_hw),
+            'clip': CLIPLoss(tower, text), 'perceptual': perceptual}
+
+
+def build_loss_dict(target_hw, device):
+    try:
+        import clip                                            # openai/CLIP
+    except Exception as e:
+        raise RuntimeError('nerfart_b200.criteria: the CLIP losses need the `clip` package (pip install '
+                           'git+https://github.com/openai/CLIP.git, reference README.md:27) for the text tower and the '
+                           'ViT-B/32 weights; pass `loss_dict=` to Trainer to supply your own losses') from e
+    model, _ = clip.load("ViT-B/32", device=device)
+    model = model.float().eval()
+    tower = ClipVisionB32.from_openai(model, device)
+    text = TextFeatures(lambda strings: model.encode_text(clip.tokenize(strings).to(device)))
+    perceptual = None
+    try:
+        from criteria.perp_loss import VGGPerceptualLoss        # the reference's module, unchanged (out of kernel scope)
+        perceptual = VGGPerceptualLoss().to(device)
+    except Exception as e:                                       # pragma: no cover
+        warnings.warn(f'perceptual (VGG16) loss unavailable, term dropped: {e}')
+    return make_loss_dict(tower, text, target_hw, perceptual)

@@ -1,0 +1,154 @@
+"""GPU: the CLIP ViT-B/32 image tower kernels (csrc/clip_vit.cu) and the three style losses built on them.
+
+Parity is UNPINNED against the reference's own model: openai/CLIP and its weights are not available offline.
+The stand-in oracle is `transformers.CLIPVisionModelWithProjection(CLIPVisionConfig())` -- the same architecture
+(768/12/12/3072, patch 32, quick_gelu, proj 512) -- with seeded random weights, fp32, on the same GPU; forward features and
+d loss / d image must agree with its autograd.  Tolerances: 2e-4 relative to the largest entry (fp32 kernels; the stand-in's
+cuBLAS GEMMs may use a different summation order).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def towers():
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    import nerfart_b200  # noqa: F401
+    from nerfart_b200.criteria.clip_vit import ClipVisionB32
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    hf = CLIPVisionModelWithProjection(CLIPVisionConfig())
+    with torch.no_grad():                                   # HF's init is tiny (std 0.02): scale up so every block matters
+        for n, p in hf.named_parameters():
+            if p.dim() >= 2:
+                p.mul_(3.0)
+            elif 'bias' in n:
+                p.normal_(0, 0.1)
+    hf = hf.to(DEV).float().eval()
+    for p in hf.parameters():
+        p.requires_grad_(False)
+    return hf, ClipVisionB32.from_hf(hf, DEV)
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize('B', [1, 3, 14])
+def test_encode_image_forward_and_image_gradient(towers, B):
+    hf, tower = towers
+    g = torch.Generator(device='cpu'); g.manual_seed(B)
+    x = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
+    gf = torch.randn(B, 512, generator=g).to(DEV)
+    x1 = x.clone().requires_grad_(True)
+    ref = hf(pixel_values=x1).image_embeds
+    (ref * gf).sum().backward()
+    x2 = x.clone().requires_grad_(True)
+    out = tower.encode_image(x2)
+    (out * gf).sum().backward()
+    e_f, e_g = rel(out, ref), rel(x2.grad, x1.grad)
+    print(f'B={B}: features rel err {e_f:.2e} (max |f| {float(ref.abs().max()):.3f}), image-gradient rel err {e_g:.2e}')
+    assert e_f < 2e-4 and e_g < 2e-4
+
+
+def test_two_encodes_before_backward_keep_their_own_activations(towers):
+    hf, tower = towers
+    g = torch.Generator(device='cpu'); g.manual_seed(9)
+    xa = torch.randn(2, 3, 224, 224, generator=g).to(DEV).requires_grad_(True)
+    xb = torch.randn(1, 3, 224, 224, generator=g).to(DEV).requires_grad_(True)
+    fa, fb = tower.encode_image(xa), tower.encode_image(xb)
+    (fa.sum() * 2 + (fb ** 2).sum()).backward()
+    xa2, xb2 = xa.detach().clone().requires_grad_(True), xb.detach().clone().requires_grad_(True)
+    ra, rb = hf(pixel_values=xa2).image_embeds, hf(pixel_values=xb2).image_embeds
+    (ra.sum() * 2 + (rb ** 2).sum()).backward()
+    assert rel(xa.grad, xa2.grad) < 2e-4 and rel(xb.grad, xb2.grad) < 2e-4
+
+
+class _FakeText:
+    """deterministic stand-in for the text tower: class string -> normalised [5,512] features; counts encodes"""
+    def __init__(self):
+        self.n = 0
+
+    def encode(self, strings):
+        self.n += 1
+        out = []
+        for s in strings:
+            gen = torch.Generator(device='cpu'); gen.manual_seed(abs(hash(s)) % (2 ** 31))
+            out.append(torch.randn(512, generator=gen))
+        return torch.stack(out).to(DEV)
+
+
+def _restated_losses(hf, tf, target_hw, src_img, pred, s_text, t_text, negs, crops, is_full_res):
+    """the reference's formulas (clip_loss.py:248-254, contrastive_loss.py:139-153, patchnce_loss.py:146-220) written out with
+    plain torch ops and the stand-in model as `encode_image`"""
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711], device=DEV).view(1, 3, 1, 1)
+    enc = lambda x: F.normalize(hf(pixel_values=(x - mean) / std).image_embeds, dim=-1)
+    # directional
+    pre = lambda x: F.interpolate(x, size=(224, 224), mode='bicubic', align_corners=False)
+    tdir = F.normalize((tf(t_text) - tf(s_text)).mean(0, keepdim=True), dim=-1)
+    ed = F.normalize(enc(pre(pred)) - enc(pre(src_img)), dim=-1)
+    l_clip = (1 - F.cosine_similarity(ed, tdir)).mean()
+    # global contrastive (inputs are treated as [-1,1] images: (x+1)/2; resize short side to 224 bicubic; centre crop)
+    def pre2(x):
+        x = (x + 1) / 2
+        h, w = x.shape[-2:]
+        nh, nw = (int(224 * h / w), 224) if w <= h else (224, int(224 * w / h))
+        x = F.interpolate(x, size=(nh, nw), mode='bicubic', align_corners=False)
+        t, l = int(round((nh - 224) / 2.)), int(round((nw - 224) / 2.))
+        return x[..., t:t + 224, l:l + 224]
+    te, se = enc(pre2(pred)), enc(pre2(src_img))
+    d = lambda a, b: F.pairwise_distance(a, b, keepdim=True)
+    l_con = torch.mean(d(te, tf(t_text)) ** 2 + torch.clamp(2.0 - d(te, tf(negs[0])), min=0) ** 2 + torch.clamp(2.0 - d(te, se.detach()), min=0) ** 2)
+    # patch NCE
+    img = F.interpolate(F.pad(pred, (270, 270, 480, 480)), size=tuple(target_hw), mode='bicubic', align_corners=False)
+    th = 224 if is_full_res else 112
+    l_nce = 0
+    for (i, j) in crops:
+        c = img[..., i:i + th, j:j + th]
+        if not is_full_res:
+            c = F.interpolate(c, size=(224, 224), mode='bicubic', align_corners=False)
+        c = F.interpolate((c + 1) / 2, size=(224, 224), mode='bilinear', align_corners=False)
+        e = enc(c)
+        pos = torch.exp(F.cosine_similarity(e, tf(t_text)) / 0.07)
+        neg = sum(torch.exp(F.cosine_similarity(e, tf(n)) / 0.07) for n in negs)
+        l_nce = l_nce + torch.mean(-torch.log(pos / (pos + neg)))
+    return l_clip, l_con, l_nce
+
+
+def test_style_losses_match_restated_reference_formulas_and_cache_text(towers):
+    hf, tower = towers
+    from nerfart_b200.criteria import make_loss_dict, TextFeatures
+    fake = _FakeText()
+    text = TextFeatures(fake.encode, templates=['a photo of a {}.', 'a painting of a {}.', '{}', 'art of the {}.', 'the {} in a game.'])
+    H, W = 96, 54
+    target_hw = [480, 270]
+    ld = make_loss_dict(tower, text, target_hw)
+    g = torch.Generator(device='cpu'); g.manual_seed(4)
+    src = torch.rand(1, 3, H, W, generator=g).to(DEV)
+    pred = torch.rand(1, 3, H, W, generator=g).to(DEV).requires_grad_(True)
+    negs = [f'neg{i}' for i in range(8)]
+    torch.manual_seed(11)
+    crops = ld['patchnce'].sample_crops(480, 270, 112, 112, False)
+    torch.manual_seed(11)
+    l1 = ld['clip'](src, 'photo', pred, 'painting')
+    l2 = ld['contrastive'](src, negs[0], pred, 'painting')
+    l3 = ld['patchnce'](negs, pred, 'painting', False)
+    (l1 + 0.2 * l2 + 0.1 * l3).backward()
+    n_enc = fake.n
+    assert n_enc == 2 + 8                                   # 'photo', 'painting', 8 negatives: each class string encoded once
+    ld['patchnce'](negs, pred.detach(), 'painting', False); ld['contrastive'](src, negs[0], pred.detach(), 'painting')
+    assert fake.n == n_enc                                   # nothing re-encoded (the reference would run 2*79 + 12*9*79 text passes)
+    pred2 = pred.detach().clone().requires_grad_(True)
+    r1, r2, r3 = _restated_losses(hf, lambda s: text(s), target_hw, src, pred2, 'photo', 'painting', negs, crops, False)
+    (r1 + 0.2 * r2 + 0.1 * r3).backward()
+    print('losses', float(l1), float(r1), float(l2), float(r2), float(l3), float(r3), 'grad rel err', rel(pred.grad, pred2.grad))
+    for a, b in ((l1, r1), (l2, r2), (l3, r3)):
+        assert abs(float(a) - float(b)) <= 2e-4 * max(1.0, abs(float(b)))
+    assert rel(pred.grad, pred2.grad) < 1e-3
