@@ -35,6 +35,8 @@ for s in $STEPS; do
     benchtrain) timeout 900 python bench.py --workload train --steps 2 --warmup 1 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "bench train exit $?"; tail -c 2500 $OUT/bench_train.json; tail -5 $OUT/bench_train.err ;;
     launchestrain) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_train.csv python bench.py --workload train --steps 1 --warmup 1 --no-cpu-baseline > $OUT/launches_train_bench.log 2>&1; echo "ncu launches train exit $?"; tail -2 $OUT/launches_train.csv ;;
     ncutrain) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mlp_bwd|wgrad" -s 2 -c 2 -f -o $OUT/prof_train python scripts/prof_train.py > $OUT/ncu_train.log 2>&1; echo "ncu train exit $?"; tail -3 $OUT/ncu_train.log ;;
+    cliptests) timeout 900 python -m pytest tests/test_gpu_clip.py -m gpu -q -s -x > $OUT/pytest_clip.log 2>&1; echo "pytest clip exit $?"; tail -30 $OUT/pytest_clip.log ;;
+    clipsan) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_clip.py -m gpu -q -s -x -k "forward_and_image_gradient and 3" > $OUT/clip_san.log 2>&1; echo "clip sanitize exit $?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" $OUT/clip_san.log | head -20 ;;
     *) echo "unknown step $s" ;;
   esac
 done
