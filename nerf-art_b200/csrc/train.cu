@@ -14,6 +14,8 @@
 //      dW = sum_samples delta^T input, accumulated in the GradPack buffer; `unpack_grads_kernel` maps GradPack to the
 //      reference's parameters (weight_g, weight_v, bias) through the weight-norm Jacobian.
 #include "simt_tile.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace na {
 
@@ -595,6 +597,113 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     }
 }
 
+// Tensor-core variant (NA_WGRAD=tf32, default): the same tiling with `mma.sync.m16n8k8` TF32 products and fp32 accumulation.
+// out = L^T R: the mma A operand (row l, col k = sample) is Ls[k][l], the B operand (row k, col r) is Rs[k][r] -- both are the
+// shared-memory tiles as loaded (row stride 136 floats: the 4 k x 8 column lanes of a fragment load hit 32 distinct banks).
+// Operands are rounded to TF32 (cvt.rna) once, when they are staged.  8 warps = 2 (l) x 4 (r); a warp owns 64 x 32 outputs.
+// Weight gradients are linear in the upstream gradient, so 10-bit operand mantissas cost ~3e-4 relative error per tensor
+// (measured, tests/test_gpu_train.py), inside the parity bound; the fp32 kernel above stays selectable (NA_WGRAD=fp32).
+constexpr int WLD = 136;
+__device__ __forceinline__ float to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
+    __shared__ __align__(16) float Ls[2][WK][WLD];
+    __shared__ __align__(16) float Rs[2][WK][WLD];
+    int ti = 0;
+    while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
+    const WgradTask t = tab.t[ti];
+    const int b = blockIdx.x - t.blk0;
+    const int lb = (b / t.nbr) * 128, rb = (b % t.nbr) * 128;
+    const long long m0 = (long long)blockIdx.y * rows_per_split;
+    long long m1 = m0 + rows_per_split; if (m1 > m_total) m1 = m_total;
+    if (m0 >= m1) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    const int wl = (warp >> 2) * 64, wr = (warp & 3) * 32;
+    float acc[4][4][4];                                   // [l tile of 16][r tile of 8][fragment]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+    const int npair = t.L2 ? 2 : 1;
+    float4 lreg[2], rreg[2];
+    auto gload = [&](const float* Lp, const float* Rp, long long mm) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid * 2 + e, row = idx >> 5, c4 = (idx & 31) * 4;
+            const long long m = mm + row;
+            lreg[e] = make_float4(0.f, 0.f, 0.f, 0.f); rreg[e] = lreg[e];
+            if (m < m1) {
+                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + m * t.ldl + lb + c4);
+                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + m * t.ldr + rb + c4);
+            }
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid * 2 + e, row = idx >> 5, c4 = (idx & 31) * 4;
+            *reinterpret_cast<float4*>(&Ls[buf][row][c4]) = make_float4(to_tf32(lreg[e].x), to_tf32(lreg[e].y), to_tf32(lreg[e].z), to_tf32(lreg[e].w));
+            *reinterpret_cast<float4*>(&Rs[buf][row][c4]) = make_float4(to_tf32(rreg[e].x), to_tf32(rreg[e].y), to_tf32(rreg[e].z), to_tf32(rreg[e].w));
+        }
+    };
+    for (int pr = 0; pr < npair; ++pr) {
+        const float* Lp = pr ? t.L2 : t.L; const float* Rp = pr ? t.R2 : t.R;
+        int buf = 0;
+        gload(Lp, Rp, m0);
+        sstore(0);
+        __syncthreads();
+        for (long long mm = m0; mm < m1; mm += WK) {
+            const bool more = mm + WK < m1;
+            if (more) gload(Lp, Rp, mm + WK);
+#pragma unroll
+            for (int k0 = 0; k0 < WK; k0 += 8) {
+                unsigned bf[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bf[j][0] = __float_as_uint(Rs[buf][k0 + tq][wr + 8 * j + g]);
+                    bf[j][1] = __float_as_uint(Rs[buf][k0 + tq + 4][wr + 8 * j + g]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    unsigned af[4];
+                    af[0] = __float_as_uint(Ls[buf][k0 + tq][wl + 16 * i + g]);
+                    af[1] = __float_as_uint(Ls[buf][k0 + tq][wl + 16 * i + g + 8]);
+                    af[2] = __float_as_uint(Ls[buf][k0 + tq + 4][wl + 16 * i + g]);
+                    af[3] = __float_as_uint(Ls[buf][k0 + tq + 4][wl + 16 * i + g + 8]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma_tf32(acc[i][j], af, bf[j]);
+                }
+            }
+            if (more) sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const int l = lb + wl + 16 * i + g + (f >> 1) * 8;
+                const int r = rb + wr + 8 * j + 2 * tq + (f & 1);
+                if (l < t.nl && r < t.nr) atomicAdd(t.out + (size_t)l * t.ldo + r, acc[i][j][f]);
+            }
+}
+
 struct ColsumTask { const float* P; float* out; int ld, n; };
 constexpr int MAX_CTASKS = 24;
 struct ColsumTable { ColsumTask t[MAX_CTASKS]; int n; };
@@ -909,7 +1018,9 @@ static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int trai
     if (splits < 1) splits = 1;
     const int rows_per_split = (int)(((tiles + splits - 1) / splits) * TM);
     const long long m_total = tiles * TM;
-    wgrad_kernel<<<dim3(wt.total_blocks, splits), 256, 0, stream>>>(wt, m_total, rows_per_split);
+    static const bool fp32_wgrad = [] { const char* e = getenv("NA_WGRAD"); return e && strcmp(e, "fp32") == 0; }();
+    if (fp32_wgrad) wgrad_kernel<<<dim3(wt.total_blocks, splits), 256, 0, stream>>>(wt, m_total, rows_per_split);
+    else            wgrad_tf32_kernel<<<dim3(wt.total_blocks, splits), 256, 0, stream>>>(wt, m_total, rows_per_split);
     NA_CHECK_LAUNCH();
     int csplits = (int)(tiles < 64 ? tiles : 64);
     const int crows = (int)(((tiles + csplits - 1) / csplits) * TM);
