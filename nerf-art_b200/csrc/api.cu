@@ -73,6 +73,7 @@ struct FillDesc {
     int map;                    // 0 identity; 1 radiance layer 0 (feat rows first, then the small inputs); 2 identity below `small`, else 0
     int small;                  // small_dim for map 1
     float mult;
+    int tf32;                   // 1: round the value to TF32 (cvt.rna) -- operand planes of the mma.sync backward GEMMs
 };
 constexpr int MAX_FILL = 48;
 struct FillTable { FillDesc d[MAX_FILL]; int n; };
@@ -108,6 +109,7 @@ __global__ void pack_fill_kernel(const NaRawParams raw, const FillTable tab, con
             if (o < f.out_n && src_in >= 0) {
                 const int so = o + f.out0;
                 val = raw.weight_v[f.layer][(size_t)so * f.in_dim + src_in] * scale[f.layer * 260 + so] * f.mult;
+                if (f.tf32) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(val)); val = __uint_as_float(r); }
             }
         }
         packed[f.dst + idx] = val;
@@ -163,10 +165,11 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
     NA_CHECK_LAUNCH();
 
     FillTable tab; tab.n = 0;
+    int fill_tf32 = 0;
     auto add = [&](size_t dst, int R, int C, int layer, int mode, int out0, int out_n, int map, float mult) {
         FillDesc& f = tab.d[tab.n++];
         f.dst = dst; f.R = R; f.C = C; f.layer = layer; f.mode = mode; f.out0 = out0; f.out_n = out_n;
-        f.in_dim = dims[layer][1]; f.map = map; f.small = sdim; f.mult = mult;
+        f.in_dim = dims[layer][1]; f.map = map; f.small = sdim; f.mult = mult; f.tf32 = fill_tf32;
     };
     const float inv_sqrt2 = (float)(1.0 / sqrt(2.0));
     for (int l = 0; l < 8; ++l) {
@@ -194,6 +197,16 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
         for (int l = 1; l < 4; ++l) add(TP.rad_w[l], W, W, 9 + l, 1, 0, W, 0, 1.f);
         add(TP.rad_w0_small, W, W, 9, 1, 0, W, 2, 1.f);                 // dst[r][c] = W0[r][c], c < small_dim
         add(TP.w8_feat, W, W, 8, 1, 1, W, 0, 1.f);                      // dst[r][c] = W8[1 + r][c]
+        fill_tf32 = 1;
+        for (int l = 0; l < 8; ++l) {
+            const float mult = (l == 4) ? inv_sqrt2 : 1.f;
+            add(TP.sdf_wt_r[l], l == 0 ? EMB_PAD : W, W, l, 0, 0, dims[l][0], 0, mult);
+            add(TP.sdf_w_r[l], W, W, l, 1, 0, dims[l][0], 0, mult);
+        }
+        add(TP.rad_w_r[0], W, W, 9, 1, 0, W, 1, 1.f);
+        for (int l = 1; l < 4; ++l) add(TP.rad_w_r[l], W, W, 9 + l, 1, 0, W, 0, 1.f);
+        add(TP.w8_feat_r, W, W, 8, 1, 1, W, 0, 1.f);
+        fill_tf32 = 0;
         pack_fill_kernel<<<dim3(64, tab.n), 256, 0, stream>>>(*raw, tab, scale, tp);
         NA_CHECK_LAUNCH();
     }

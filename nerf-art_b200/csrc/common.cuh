@@ -74,6 +74,11 @@ struct PackTrain {
     size_t rad_w[4];                // [0]: layer 0, feature columns  B[r=out][c=feat]; [1..3]: B[r=out][c=in]
     size_t rad_w0_small;            // layer 0, small-input columns   B[r=out][c=small idx] (zero beyond small_dim)
     size_t w8_feat;                 // SDF head rows 1..256           B[r=feat][c=in]
+    // TF32-rounded (cvt.rna) copies for the mma.sync backward-data GEMMs of train.cu:
+    size_t sdf_wt_r[N_SDF_HID];     // forward planes  B[r=in][c=out]  ([40][256] for layer 0)   -> second-order sweep
+    size_t sdf_w_r[N_SDF_HID];      // backward planes B[r=out][c=in]  (1..7 used)               -> trunk backward
+    size_t rad_w_r[4];              // as rad_w
+    size_t w8_feat_r;
     size_t total;
 };
 __host__ inline PackTrain pack_layout_train() {
@@ -81,6 +86,10 @@ __host__ inline PackTrain pack_layout_train() {
     for (int i = 0; i < 4; ++i) { T.rad_w[i] = o; o += (size_t)W * W; }
     T.rad_w0_small = o; o += (size_t)W * W;
     T.w8_feat = o; o += (size_t)W * W;
+    for (int i = 0; i < N_SDF_HID; ++i) { T.sdf_wt_r[i] = o; o += (size_t)(i == 0 ? EMB_PAD : W) * W; }
+    for (int i = 0; i < N_SDF_HID; ++i) { T.sdf_w_r[i] = o; o += (size_t)W * W; }
+    for (int i = 0; i < 4; ++i) { T.rad_w_r[i] = o; o += (size_t)W * W; }
+    T.w8_feat_r = o; o += (size_t)W * W;
     T.total = o;
     return T;
 }

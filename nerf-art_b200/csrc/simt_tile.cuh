@@ -15,7 +15,7 @@ constexpr int TAIL0 = 256;         // first tail row
 struct __align__(16) MlpSmem {
     float A[A_ROWS * TM];
     float GE[EMB_PAD * TM];        // d sdf / d embedding accumulator
-    float Ws[3 * KC * 256];        // weight chunk ring
+    float Ws[3 * KC * 264];        // weight chunk ring (row stride 256 for the FFMA tiles, 264 for the TF32 mma tiles of train.cu)
     float X[3 * TM];
     float V[3 * TM];
     float RED[2 * 3 * TM];         // two-half partial sums of the narrow output layers

@@ -99,6 +99,92 @@ __device__ __forceinline__ void load_col_A(const float* A, int k, int ty, int tx
 }
 __device__ __forceinline__ float f4c(const float4& v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
 
+__device__ __forceinline__ float to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Tensor-core tile GEMM for the backward-data products (linear in the upstream gradient, so TF32 operands are enough):
+// OUT[m][c] = sum_{r<R} A[a_row0 + r][m] * B[r][c], c < 256, `mma.sync.m16n8k8` TF32, fp32 accumulate.  B planes are pre-rounded
+// to TF32 (PackTrain.*_r); A is rounded (cvt.rna) at fragment load.  8 warps = 4 (m) x 2 (n); warp (wm, wn) owns rows 32 wm..+31
+// and columns 128 wn..+127; acc[mt][nt][f] is the m16n8 C fragment: row 32 wm + 16 mt + g + 8 (f>>1), column 128 wn + 8 nt + 2 t + (f&1)
+// with g = lane/4, t = lane%4.  Weight ring rows are 264 floats apart so a fragment load touches 32 distinct banks.
+constexpr int WSTR = 264;
+__device__ __forceinline__ void gemm_tile_tf32(float (&acc)[2][16][4], const float* __restrict__ Bg, int R, int a_row0,
+                                               const float* __restrict__ As, float* __restrict__ Ws, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 128;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[i][j][f] = 0.f;
+    const int nch = R / KC;
+    auto issue = [&](int c) {
+        float* dst = Ws + (c % 3) * (KC * WSTR);
+        const float* src = Bg + (size_t)c * KC * 256;
+        for (int idx = tid; idx < KC * 64; idx += NT) {
+            const int row = idx >> 6, c4 = idx & 63;
+            cp_async16(dst + row * WSTR + c4 * 4, src + row * 256 + c4 * 4);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    if (nch > 1) issue(1);
+    for (int c = 0; c < nch; ++c) {
+        if (c + 1 < nch) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        if (c + 2 < nch) issue(c + 2);
+        const float* wb = Ws + (c % 3) * (KC * WSTR);
+        const int k0 = a_row0 + c * KC;
+        unsigned af[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int m = m0 + 16 * mt + g;
+            af[mt][0] = __float_as_uint(to_tf32(As[a_index(k0 + t, m)]));
+            af[mt][1] = __float_as_uint(to_tf32(As[a_index(k0 + t, m + 8)]));
+            af[mt][2] = __float_as_uint(to_tf32(As[a_index(k0 + t + 4, m)]));
+            af[mt][3] = __float_as_uint(to_tf32(As[a_index(k0 + t + 4, m + 8)]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+            unsigned bf[2];
+            bf[0] = __float_as_uint(wb[t * WSTR + n0 + 8 * nt + g]);
+            bf[1] = __float_as_uint(wb[(t + 4) * WSTR + n0 + 8 * nt + g]);
+            mma_tf32(acc[0][nt], af[0], bf);
+            mma_tf32(acc[1][nt], af[1], bf);
+        }
+    }
+    __syncthreads();
+}
+// visit the thread's C fragment as (row, even column, value pair)
+template <typename F>
+__device__ __forceinline__ void mma_each(float (&acc)[2][16][4], int tid, F f) {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 128;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                f(m0 + 16 * mt + g + 8 * hf, n0 + 8 * nt + 2 * t, acc[mt][nt][2 * hf], acc[mt][nt][2 * hf + 1]);
+}
+__device__ __forceinline__ float2 ld2(const float* __restrict__ plane, int row, int col) {
+    return *reinterpret_cast<const float2*>(plane + (size_t)row * 256 + col);
+}
+__device__ __forceinline__ void st2(float* __restrict__ plane, int row, int col, float a, float b) {
+    *reinterpret_cast<float2*>(plane + (size_t)row * 256 + col) = make_float2(a, b);
+}
+
+template <bool TF32>
 __global__ void __launch_bounds__(NT, 1)
 mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, const float* __restrict__ tp, const PackTrain T,
                const Stash st, float* __restrict__ scratch) {
@@ -113,6 +199,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
     const int nv = job.multires_view < 0 ? 3 : 3 + 6 * job.multires_view;
     const int spad = small_pad(job.multires_view);
     float acc[8][16];
+    float (&acc2)[2][16][4] = reinterpret_cast<float (&)[2][16][4]>(acc);      // the same registers as an mma C fragment
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TM;
@@ -373,23 +460,39 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
                 st_A4(S.A, ty, tx, j, acc);
                 st_frag4(WP(PL_D + 3), ty, tx, j, acc);
             }
-            for (int layer = 3; layer >= 1; --layer) {
-                gemm_tile<4>(acc, tp + T.rad_w[layer], W, 0, S.A, S.Ws, tid);   // dL/d ys[layer]
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 yv[8];
-                    ld_frag4(WP(PL_YS + layer - 1), ty, tx, j, yv);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = f4c(yv[i], c) > 0.f ? acc[i][4 * j + c] : 0.f;
-                    st_A4(S.A, ty, tx, j, acc);
-                    st_frag4(WP(PL_D + layer - 1), ty, tx, j, acc);
+            if constexpr (TF32) {
+                for (int layer = 3; layer >= 1; --layer) {
+                    gemm_tile_tf32(acc2, tp + T.rad_w_r[layer], W, 0, S.A, S.Ws, tid);          // dL/d ys[layer]
+                    const float* ysp = WP(PL_YS + layer - 1); float* dp = WP(PL_D + layer - 1);
+                    mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) {
+                        const float2 y = ld2(ysp, row, col);
+                        v0 = y.x > 0.f ? v0 : 0.f; v1 = y.y > 0.f ? v1 : 0.f;
+                        st2(dp, row, col, v0, v1);
+                        S.A[a_index(col, row)] = v0; S.A[a_index(col + 1, row)] = v1;
+                    });
                 }
+                gemm_tile_tf32(acc2, tp + T.rad_w_r[0], W, 0, S.A, S.Ws, tid);                  // dL/d feature
+                float* fbp = WP(PL_FB);
+                mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) { st2(fbp, row, col, v0, v1); });
+            } else {
+            for (int layer = 3; layer >= 1; --layer) {
+                    gemm_tile<4>(acc, tp + T.rad_w[layer], W, 0, S.A, S.Ws, tid);   // dL/d ys[layer]
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 yv[8];
+                        ld_frag4(WP(PL_YS + layer - 1), ty, tx, j, yv);
+    #pragma unroll
+                        for (int c = 0; c < 4; ++c)
+    #pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = f4c(yv[i], c) > 0.f ? acc[i][4 * j + c] : 0.f;
+                        st_A4(S.A, ty, tx, j, acc);
+                        st_frag4(WP(PL_D + layer - 1), ty, tx, j, acc);
+                    }
+                }
+                gemm_tile<4>(acc, tp + T.rad_w[0], W, 0, S.A, S.Ws, tid);           // dL/d feature
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) st_frag4(WP(PL_FB), ty, tx, j, acc);
             }
-            gemm_tile<4>(acc, tp + T.rad_w[0], W, 0, S.A, S.Ws, tid);           // dL/d feature
-#pragma unroll
-            for (int j = 0; j < 4; ++j) st_frag4(WP(PL_FB), ty, tx, j, acc);
             {
                 float acc1[8][4];
                 gemm_tile<1>(acc1, tp + T.rad_w0_small, W, 0, S.A, S.Ws, tid);   // dL/d (x | view | nabla): keep nabla
@@ -429,73 +532,120 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
             S.A[a_index(TAIL0 + 39, m)] = 0.f; vrow[39] = 0.f;
         }
         // ---- 8. second-order sweep, layers 0..7 (forward-like): g-bar_i = W_i v-bar_i ---------------------------------------
+        if constexpr (TF32) {
+            for (int layer = 0; layer < N_SDF_HID; ++layer) {
+                gemm_tile_tf32(acc2, tp + T.sdf_wt_r[layer], layer == 0 ? EMB_PAD : W, layer == 0 ? TAIL0 : 0, S.A, S.Ws, tid);
+                const float* spp = SP + layer * 256 * TM; float* qp = QP + layer * 256 * TM;
+                const float* gp_ = WP(PL_G + layer); float* vbp = WP(PL_VB + layer);
+                mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) {
+                    const float2 s2 = ld2(spp, row, col), g2 = ld2(gp_, row, col);
+                    st2(qp, row, col, 100.f * v0 * g2.x * (1.f - s2.x), 100.f * v1 * g2.y * (1.f - s2.y));
+                    v0 *= s2.x; v1 *= s2.y;
+                    if (layer == 3) {
+                        if (col >= SKIP_H) v0 = S.A[a_index(TAIL0 + (col - SKIP_H), row)];
+                        if (col + 1 >= SKIP_H) v1 = S.A[a_index(TAIL0 + (col + 1 - SKIP_H), row)];
+                    }
+                    st2(vbp, row, col, v0, v1);
+                    S.A[a_index(col, row)] = v0; S.A[a_index(col + 1, row)] = v1;
+                });
+            }
+        } else {
         for (int layer = 0; layer < N_SDF_HID; ++layer) {
-            if (layer == 0) gemm_tile<4>(acc, pk + L.sdf_wt[0], EMB_PAD, TAIL0, S.A, S.Ws, tid);
-            else            gemm_tile<4>(acc, pk + L.sdf_wt[layer], W, 0, S.A, S.Ws, tid);
-            float* qp = QP + layer * 256 * TM;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 sv[8], gv[8];
-                ld_frag4(SP + layer * 256 * TM, ty, tx, j, sv);
-                ld_frag4(WP(PL_G + layer), ty, tx, j, gv);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int k = 64 * j + 4 * tx + c;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float gb = acc[i][4 * j + c], s = f4c(sv[i], c), g = f4c(gv[i], c);
-                        const float q = 100.f * gb * g * (1.f - s);             // s-bar_i * softplus''(z_i)
-                        (c == 0 ? sv[i].x : c == 1 ? sv[i].y : c == 2 ? sv[i].z : sv[i].w) = q;
-                        acc[i][4 * j + c] = gb * s;                              // u-bar_i = v-bar_{i+1}
+                if (layer == 0) gemm_tile<4>(acc, pk + L.sdf_wt[0], EMB_PAD, TAIL0, S.A, S.Ws, tid);
+                else            gemm_tile<4>(acc, pk + L.sdf_wt[layer], W, 0, S.A, S.Ws, tid);
+                float* qp = QP + layer * 256 * TM;
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 sv[8], gv[8];
+                    ld_frag4(SP + layer * 256 * TM, ty, tx, j, sv);
+                    ld_frag4(WP(PL_G + layer), ty, tx, j, gv);
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = 64 * j + 4 * tx + c;
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float gb = acc[i][4 * j + c], s = f4c(sv[i], c), g = f4c(gv[i], c);
+                            const float q = 100.f * gb * g * (1.f - s);             // s-bar_i * softplus''(z_i)
+                            (c == 0 ? sv[i].x : c == 1 ? sv[i].y : c == 2 ? sv[i].z : sv[i].w) = q;
+                            acc[i][4 * j + c] = gb * s;                              // u-bar_i = v-bar_{i+1}
+                        }
+                        if (layer == 3 && k >= SKIP_H) {
+    #pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = S.A[a_index(TAIL0 + (k - SKIP_H), 8 * ty + i)];
+                        }
                     }
-                    if (layer == 3 && k >= SKIP_H) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = S.A[a_index(TAIL0 + (k - SKIP_H), 8 * ty + i)];
-                    }
+                    st_frag4v(qp, ty, tx, j, sv);
+                    st_A4(S.A, ty, tx, j, acc);
+                    st_frag4(WP(PL_VB + layer), ty, tx, j, acc);
                 }
-                st_frag4v(qp, ty, tx, j, sv);
-                st_A4(S.A, ty, tx, j, acc);
-                st_frag4(WP(PL_VB + layer), ty, tx, j, acc);
             }
         }
         // ---- 9. first-order backward through the trunk: z-bar_7 from the head, then layers 7..1 ----------------------------
-        if (job.has_rad) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 fv[8];
-                ld_frag4(WP(PL_FB), ty, tx, j, fv);
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = f4c(fv[i], c);
-                st_A4(S.A, ty, tx, j, acc);
+        if constexpr (TF32) {
+            if (job.has_rad) {
+                const float* fbp = WP(PL_FB);
+                mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) {
+                    const float2 f2 = ld2(fbp, row, col);
+                    S.A[a_index(col, row)] = f2.x; S.A[a_index(col + 1, row)] = f2.y;
+                });
+                gemm_tile_tf32(acc2, tp + T.w8_feat_r, W, 0, S.A, S.Ws, tid);                   // W8[1:,:]^T feat-bar
+            } else {
+                mma_each(acc2, tid, [&](int, int, float& v0, float& v1) { v0 = 0.f; v1 = 0.f; });
             }
-            gemm_tile<4>(acc, tp + T.w8_feat, W, 0, S.A, S.Ws, tid);             // W8[1:,:]^T feat-bar
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
-        }
-        for (int layer = 8; layer >= 1; --layer) {
-            if (layer < 8) gemm_tile<4>(acc, pk + L.sdf_w[layer], W, 0, S.A, S.Ws, tid);   // h-bar_{layer-1}
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 sv[8], qv[8];
-                ld_frag4(SP + (layer - 1) * 256 * TM, ty, tx, j, sv);
-                ld_frag4(QP + (layer - 1) * 256 * TM, ty, tx, j, qv);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float w8 = layer == 8 ? __ldg(pk + L.w8_sdf + 64 * j + 4 * tx + c) : 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float hb = acc[i][4 * j + c];
-                        if (layer == 8) hb += Q.GS[8 * ty + i] * w8;
-                        acc[i][4 * j + c] = hb * f4c(sv[i], c) + f4c(qv[i], c);
+            for (int layer = 8; layer >= 1; --layer) {
+                if (layer < 8) gemm_tile_tf32(acc2, tp + T.sdf_w_r[layer], W, 0, S.A, S.Ws, tid); // h-bar_{layer-1}
+                const float* spp = SP + (layer - 1) * 256 * TM; const float* qp = QP + (layer - 1) * 256 * TM;
+                float* zbp = WP(PL_ZB + layer - 1);
+                mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) {
+                    const float2 s2 = ld2(spp, row, col), q2 = ld2(qp, row, col);
+                    if (layer == 8) {
+                        const float gs = Q.GS[row];
+                        v0 += gs * __ldg(pk + L.w8_sdf + col); v1 += gs * __ldg(pk + L.w8_sdf + col + 1);
                     }
+                    v0 = v0 * s2.x + q2.x; v1 = v1 * s2.y + q2.y;
+                    st2(zbp, row, col, v0, v1);
+                    S.A[a_index(col, row)] = v0; S.A[a_index(col + 1, row)] = v1;
+                });
+            }
+        } else {
+        if (job.has_rad) {
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 fv[8];
+                    ld_frag4(WP(PL_FB), ty, tx, j, fv);
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c)
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = f4c(fv[i], c);
+                    st_A4(S.A, ty, tx, j, acc);
                 }
-                st_A4(S.A, ty, tx, j, acc);
-                st_frag4(WP(PL_ZB + layer - 1), ty, tx, j, acc);
+                gemm_tile<4>(acc, tp + T.w8_feat, W, 0, S.A, S.Ws, tid);             // W8[1:,:]^T feat-bar
+            } else {
+    #pragma unroll
+                for (int i = 0; i < 8; ++i)
+    #pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
+            }
+            for (int layer = 8; layer >= 1; --layer) {
+                if (layer < 8) gemm_tile<4>(acc, pk + L.sdf_w[layer], W, 0, S.A, S.Ws, tid);   // h-bar_{layer-1}
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 sv[8], qv[8];
+                    ld_frag4(SP + (layer - 1) * 256 * TM, ty, tx, j, sv);
+                    ld_frag4(QP + (layer - 1) * 256 * TM, ty, tx, j, qv);
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float w8 = layer == 8 ? __ldg(pk + L.w8_sdf + 64 * j + 4 * tx + c) : 0.f;
+    #pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float hb = acc[i][4 * j + c];
+                            if (layer == 8) hb += Q.GS[8 * ty + i] * w8;
+                            acc[i][4 * j + c] = hb * f4c(sv[i], c) + f4c(qv[i], c);
+                        }
+                    }
+                    st_A4(S.A, ty, tx, j, acc);
+                    st_frag4(WP(PL_ZB + layer - 1), ty, tx, j, acc);
+                }
             }
         }
         __syncthreads();
@@ -604,17 +754,6 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
 // Weight gradients are linear in the upstream gradient, so 10-bit operand mantissas cost ~3e-4 relative error per tensor
 // (measured, tests/test_gpu_train.py), inside the parity bound; the fp32 kernel above stays selectable (NA_WGRAD=fp32).
 constexpr int WLD = 136;
-__device__ __forceinline__ float to_tf32(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
 __global__ void __launch_bounds__(256)
 wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     __shared__ __align__(16) float Ls[2][WK][WLD];
@@ -963,16 +1102,19 @@ static TrainWs train_ws(void* base, long long n_rays, int P) {
 static int launch_mlp_bwd(const BwdJob& job, const float* pk, const PackF32& L, const float* tp, const PackTrain& T, const Stash& st,
                           float* scratch, cudaStream_t stream) {
     static thread_local bool attr_set = false;
+    static const bool fp32_bwd = [] { const char* e = getenv("NA_BWD"); return e && strcmp(e, "fp32") == 0; }();
     const size_t smem = sizeof(TrainSmem);
     if (!attr_set) {
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_set = true;
     }
     const long long total = (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;
     const long long tiles = (total + TM - 1) / TM;
     const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
-    mlp_bwd_kernel<<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, scratch);
+    if (fp32_bwd) mlp_bwd_kernel<false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, scratch);
+    else          mlp_bwd_kernel<true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, scratch);
     NA_CHECK_LAUNCH();
     return NA_OK;
 }

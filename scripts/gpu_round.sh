@@ -37,6 +37,7 @@ for s in $STEPS; do
     ncutrain) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mlp_bwd|wgrad" -s 2 -c 2 -f -o $OUT/prof_train python scripts/prof_train.py > $OUT/ncu_train.log 2>&1; echo "ncu train exit $?"; tail -3 $OUT/ncu_train.log ;;
     cliptests) timeout 900 python -m pytest tests/test_gpu_clip.py -m gpu -q -s -x > $OUT/pytest_clip.log 2>&1; echo "pytest clip exit $?"; tail -30 $OUT/pytest_clip.log ;;
     clipsan) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_clip.py -m gpu -q -s -x -k "forward_and_image_gradient and 3" > $OUT/clip_san.log 2>&1; echo "clip sanitize exit $?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" $OUT/clip_san.log | head -20 ;;
+    traintestsfp32) NA_BWD=fp32 NA_WGRAD=fp32 timeout 900 python -m pytest tests/test_gpu_train.py -m gpu -q -s > $OUT/pytest_train_fp32.log 2>&1; echo "pytest train fp32 exit $?"; grep -E "worst|passed|failed|ln_beta" $OUT/pytest_train_fp32.log | tail -12 ;;
     *) echo "unknown step $s" ;;
   esac
 done
