@@ -157,6 +157,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='render', choices=['render', 'train'],
                     help="'render' (default): BASELINE configs[1]; 'train': the fine-tune step, see bench_train.py")
+    ap.add_argument('--style', default='clip', choices=['clip', 'mse'], help='--workload train: style loss (see bench_train.py)')
     args = ap.parse_args()
     if args.workload == 'train':
         import bench_train

@@ -4,8 +4,11 @@ Reached through `python bench.py --workload train [...]`; `bench.py` without fla
 
 One "step" = one `Trainer.forward` + `optimizer.step()`:  pass 1 (no-grad render of all 129 600 rays), style loss, pass 2
 (108 patches of 1200 rays: forward render with detailed outputs + backward kernels), weight-norm unpack, Adam.
-The style loss is a synthetic image loss (weighted MSE to a constant target): the CLIP / VGG losses
-act on the rendered image only and are not part of this timing; the image gradient they produce has the same shape.
+Style loss (`--style`): 'clip' (default) = the three CLIP losses of nerfart_b200.criteria (directional + global contrastive +
+PatchNCE over 12 crops: 17 image-tower passes forward and 15 backward per step on csrc/clip_vit.cu) with SEEDED RANDOM tower
+weights and seeded stand-in text features -- openai/CLIP weights are not available offline, the arithmetic and its cost are the
+same; the VGG perceptual term is omitted (torchvision weights unavailable).  'mse' = weighted MSE to a
+constant target (render + backward only).
 value = n_rays * 192 / t  (full-MLP samples per second of wall-clock step time, same unit as the render bench).
 """
 import json
@@ -83,10 +86,22 @@ def main(args):
     target = torch.full((1, n_rays, 3), 0.25)
     wts = torch.linspace(0.5, 1.5, n_rays * 3, device=dev).reshape(1, 3, H, W)
     zero = lambda *a, **k: torch.zeros((), device=dev)
-    trainer = pv.Trainer(model, is_finetune=True, target_hw=[H, W],
-                         loss_dict={'clip': lambda gt, s, pred, t: ((pred - gt) ** 2 * wts).mean(), 'perceptual': None,
-                                    'contrastive': zero, 'patchnce': zero})
-    trainer.neg_texts = ['a'] * 10
+    style = getattr(args, 'style', 'clip')
+    if style == 'clip':
+        from nerfart_b200.criteria import make_loss_dict, TextFeatures
+        from nerfart_b200.criteria.clip_vit import ClipVisionB32
+
+        def fake_text(strings):                       # stand-in text tower: seeded features per prompt (cached by TextFeatures)
+            out = []
+            for s_ in strings:
+                gg = torch.Generator(device='cpu'); gg.manual_seed(sum(ord(c) * (i + 1) for i, c in enumerate(s_)) % (2 ** 31))
+                out.append(torch.randn(512, generator=gg))
+            return torch.stack(out).to(dev)
+        loss_dict = make_loss_dict(ClipVisionB32.random(0, dev), TextFeatures(fake_text, templates=['a photo of a {}.'] * 79), [H, W])
+    else:
+        loss_dict = {'clip': lambda gt, s, pred, t: ((pred - gt) ** 2 * wts).mean(), 'perceptual': None, 'contrastive': zero, 'patchnce': zero}
+    trainer = pv.Trainer(model, is_finetune=True, target_hw=[H, W], loss_dict=loss_dict)
+    trainer.neg_texts = [f'negative prompt {i}' for i in range(40)]
     targs = _A(training=_A(is_finetune=True), data=_A(downscale=2), model=_A(radiance=_A(use_view_dirs=True)),
                finetune=_A(use_eikonal=True, w_eikonal=0.1, w_clip=1.0, w_perceptual=2.0, w_contrastive=0.2, w_patchnce=0.1,
                            src_text='photo', target_text='painting'))
@@ -110,6 +125,16 @@ def main(args):
         return wrap
     eng.render_bwd = timed_call('render_bwd', orig_bwd)
     eng.volsdf_render = timed_call('patch_fwd', orig_fwd)
+    from nerfart_b200.models.frameworks import _finetune
+    phases['style'] = []
+    orig_style = _finetune.calc_style_loss
+
+    def style_timed(*a, **k):                          # forward of the style losses; their backward runs inside losses.backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = orig_style(*a, **k); e1.record()
+        phases['style'].append((e0, e1, True))
+        return r
+    _finetune.calc_style_loss = style_timed
 
     def step():
         ret = trainer(targs, None, {'intrinsics': K_pin.to(dev, non_blocking=True), 'c2w': c2w_pin.to(dev, non_blocking=True)},
@@ -152,6 +177,7 @@ def main(args):
     t_bwd = sum(a.elapsed_time(b) for a, b, _ in phases['render_bwd']) * 1e-3 / args.steps
     t_pfwd = sum(a.elapsed_time(b) for a, b, det in phases['patch_fwd'] if det) * 1e-3 / args.steps
     t_p1 = sum(a.elapsed_time(b) for a, b, det in phases['patch_fwd'] if not det) * 1e-3 / args.steps
+    t_style = sum(a.elapsed_time(b) for a, b, _ in phases['style']) * 1e-3 / args.steps
     if rank == 0:
         pk, kind = B.peaks()
         n_local = n_rays if world == 1 else None
@@ -164,21 +190,22 @@ def main(args):
         line = {'metric': 'MLP samples/sec (VolSDF 480x270x128 fine-tune step)', 'value': n_rays * P * args.steps / t, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': 'f32 (backward, CUDA cores); forward: ' + args.precision, 'data': 'synthetic',
+                'dtype': 'backward: tf32 mma.sync + f32 recompute (NA_BWD/NA_WGRAD); CLIP tower f32; forward: ' + args.precision, 'data': 'synthetic',
                 'config': {'workload': f'VolSDF fine-tune step {H}x{W} ({n_rays} rays), 128+64 samples/ray, pass 1 + pass 2 in 108 patches of '
-                                       '1200 rays, eikonal on, perturb on, synthetic image loss in place of CLIP/VGG, Adam step',
+                                       '1200 rays, eikonal on, perturb on, style=' + style + (' (3 CLIP losses, seeded random ViT-B/32 weights + stand-in text features, no VGG)' if style == 'clip' else ' (weighted MSE)') + ', Adam step',
                            'parallelism': f'patch round-robin x{world}' + (' + NCCL all-reduce of the packed gradient' if world > 1 else ''),
                            'l2': 'per-patch stash (9.9 GB) >> 126 MB L2; no explicit flush'},
                 'phases_ms': {'pass1_render': 1e3 * t_p1, 'pass2_patch_forward': 1e3 * t_pfwd, 'pass2_backward': 1e3 * t_bwd,
-                              'other (loss, unpack, Adam, host)': 1e3 * (t / args.steps - t_p1 - t_pfwd - t_bwd)},
+                              'style_loss_forward': 1e3 * t_style,
+                              'other (style backward, unpack, Adam, host)': 1e3 * (t / args.steps - t_p1 - t_pfwd - t_bwd - t_style)},
                 'e2e': {'value': n_rays * P * args.steps / t, 'unit': 'samples/s', 'ms_per_step': 1e3 * t / args.steps,
                         'h2d_bytes_per_step': 2 * 64 + n_rays * 12, 'd2h_bytes_per_step': 4,
                         'note': 'the step is timed through Trainer.forward with pinned-host camera / target image in and the loss out'},
                 'gpu_launches': int(launches), 'clocks': clk,
-                'roofline': {'bound': 'tensor', 'kernel': 'mlp_bwd_kernel + wgrad_kernel (pass-2 backward, fp32 CUDA cores)',
+                'roofline': {'bound': 'tensor', 'kernel': 'mlp_bwd_kernel + wgrad kernel (pass-2 backward)',
                              'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops'], 'traffic': None,
-                             'flop_per_sample': F_BWD, 'note': 'algorithmic backward FLOPs / time inside render_bwd; the kernels run on '
-                             'the fp32 FMA pipe (peak ~74 TFLOP/s), not yet on tcgen05', 'peak_kind': f'{kind} bf16 burst'},
+                             'flop_per_sample': F_BWD, 'note': 'algorithmic backward FLOPs / time inside render_bwd; recompute GEMMs on the fp32 FMA pipe, '
+                             'backward-data and weight-gradient GEMMs on legacy mma.sync TF32; not yet on tcgen05', 'peak_kind': f'{kind} bf16 burst'},
                 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -92,6 +92,26 @@ class ClipVisionB32:
             sd[b + 'mlp.c_proj.weight'], sd[b + 'mlp.c_proj.bias'] = s[a + 'mlp.fc2.weight'], s[a + 'mlp.fc2.bias']
         return cls(sd, device)
 
+    @classmethod
+    def random(cls, seed, device):
+        """Seeded random weights of the right shapes (benchmarks / smoke tests when no CLIP weights are available offline)."""
+        g = torch.Generator(device='cpu'); g.manual_seed(seed)
+        shapes = {'conv1.weight': (768, 3, 32, 32), 'class_embedding': (768,), 'positional_embedding': (50, 768), 'proj': (768, 512)}
+        per = {'attn.in_proj_weight': (2304, 768), 'attn.in_proj_bias': (2304,), 'attn.out_proj.weight': (768, 768),
+               'attn.out_proj.bias': (768,), 'mlp.c_fc.weight': (3072, 768), 'mlp.c_fc.bias': (3072,), 'mlp.c_proj.weight': (768, 3072),
+               'mlp.c_proj.bias': (768,)}
+        sd = {}
+        for k in cls.KEYS:
+            if k.endswith('.weight') and ('ln_' in k):
+                sd[k] = torch.ones(768)
+            elif k.endswith('.bias') and ('ln_' in k):
+                sd[k] = torch.zeros(768)
+            else:
+                shp = shapes.get(k) or per[k.split('.', 3)[3]]
+                fan_in = shp[-1] if len(shp) == 2 else (3072 if len(shp) == 4 else 768)
+                sd[k] = torch.randn(*shp, generator=g) * (fan_in ** -0.5 if len(shp) > 1 else 0.02)
+        return cls(sd, device)
+
     # -- the op ----------------------------------------------------------------------------------------------------
     def encode_image(self, images):
         """[B,3,224,224] fp32 (resized, CLIP-normalised) -> [B,512]; differentiable w.r.t. `images`."""
