@@ -214,21 +214,33 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     constexpr int N_PASS = KIND == K_BWD0 ? 1 : 4;                  // reverse GEMM 0: only 39 useful columns, all in pass 0
     // softplus' plane this epilogue multiplies by: feature head (g = 8) -> layer 7, reverse GEMM g = 9..15 -> layer 15 - g
     const uint2* dhp = c.dh + (size_t)((15 - c.g) * 64) * TM + r;
+    // softplus' codes of this thread's row: thread-private scratch (written by the same thread in the forward GEMM), so the
+    // loads can run one pass ahead -- pass 0's are issued before the wait for D, pass c+1's before pass c's arithmetic --
+    // which takes the L2 / DRAM latency (the MMA warp was starved 46 % of a full-mode tile, profiles/r1v) off the critical path
+    uint2 qn[4];
+    if (USES_DH) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) qn[j4] = dhp[(size_t)(c.cq * 4 + j4) * TM];
+    }
 #pragma unroll 1
     for (int c16 = 0; c16 < N_PASS; ++c16) {
         // thread = (row, column quarter cq): in pass c16 it owns columns 64*c16 + 16*cq .. +16, i.e. every pass completes one
         // 64-wide K-block of the next layer's A operand across the 16 epilogue warps
         const int col0 = c16 * 64 + c.cq * 16;
         uint2 q[4];
+        if (USES_DH) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) q[j4] = qn[j4];
+            if (c16 + 1 < N_PASS) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) qn[j4] = dhp[(size_t)(((col0 + 64) >> 2) + j4) * TM];
+            }
+        }
         if ((c16 & 1) == 0) {                                       // passes 0,1 read N-half 0 of D, passes 2,3 N-half 1
             const long long t0 = clock64();
             mbar_wait(c.d_bar + 8u * (unsigned)(c16 >> 1), c.d_phase);
             *c.t_wait += clock64() - t0;
             tc_fence_after();
-        }
-        if (USES_DH) {                                              // issued before the TMEM load: both latencies overlap
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) q[j4] = dhp[(size_t)((col0 >> 2) + j4) * TM];
         }
         float acc[16];
         {
