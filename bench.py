@@ -263,11 +263,11 @@ def main():
         e1.record(); torch.cuda.synchronize()
         t_k = e0.elapsed_time(e1) * 1e-3 / reps
         v = torch.nn.functional.normalize(torch.randn(m // 4, 3, device=dev, generator=g), dim=-1)
-        eng.full_eval(x[:m // 4], v)
+        eng.full_eval(x[:m // 4], v, want_feat=False)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(reps):
-            eng.full_eval(x[:m // 4], v)
+            eng.full_eval(x[:m // 4], v, want_feat=False)
         e1.record(); torch.cuda.synchronize()
         t_f = e0.elapsed_time(e1) * 1e-3 / reps
         ach = m * F_SDF / t_k / 1e12

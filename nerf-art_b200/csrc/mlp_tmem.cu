@@ -32,14 +32,29 @@ namespace tm {
 constexpr int TM = 128;
 constexpr int THREADS = 576;
 constexpr int EPI_THREADS = 512;
-constexpr int NS = 6;                            // weight stages
+#ifndef NA_TM_NS
+#define NA_TM_NS 5
+#endif
+constexpr int NS = NA_TM_NS;                     // weight stages (32 KB each); 5 leaves room for the encoding / small-weight stashes below
+constexpr bool STASH = NS <= 5;
 constexpr int STAGE_BYTES = 32768;               // 256 rows x 64 fp16
 constexpr float ACT_SCALE = 16.f;                // activations are stored x16 (keeps the lo term normal in fp16)
 constexpr int MAX_GEMM = 24;
 constexpr int N_PLANES = 21;                     // program: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
 
+// NA_TM_TRACE (diagnostic build): CTA 0 records clock64() stamps of its second tile into job.dbg[16..]:
+//   MMA lane:      slot (g*4+kb)*2 + {0: K-block of A ready, 1: its MMAs issued}
+//   epilogue lane: slot 192 + (g*4+pass)*3 + {0: D quarter ready, 1: tcgen05.ld done, 2: A stored}
+#ifdef NA_TM_TRACE
+#define NA_TRACE_M(tr, g, kb, w) do { if (tr) (tr)[((g) * 4 + (kb)) * 2 + (w)] = clock64(); } while (0)
+#define NA_TRACE_E(tr, g, ps, w) do { if (tr) (tr)[192 + ((g) * 4 + (ps)) * 3 + (w)] = clock64(); } while (0)
+#else
+#define NA_TRACE_M(tr, g, kb, w) do { } while (0)
+#define NA_TRACE_E(tr, g, ps, w) do { } while (0)
+#endif
+
 struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, pad; };
-struct Program { int n_gemm; Gemm g[MAX_GEMM]; };
+struct Program { int n_gemm; int nsplit; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -133,7 +148,7 @@ constexpr int N_BIAS_ROWS = 13;                  // 0..7 sdf fwd (x ACT_SCALE) |
 
 struct __align__(1024) Smem {
     unsigned char Wst[NS * STAGE_BYTES];
-    unsigned long long full_bar[NS], empty_bar[NS], d_ready[2], kb_ready[4];   // d_ready[h]: N-half h of D is complete; kb_ready[k]: K-block k of the next A operand is in TMEM
+    unsigned long long full_bar[NS], empty_bar[NS], d_ready[4], kb_ready[4];   // d_ready[q]: N-quarter q of D is complete; kb_ready[k]: K-block k of the next A operand is in TMEM
     unsigned tmem_base;
     __align__(16) float BIAS[N_BIAS_ROWS * 256];
     __align__(16) float W8[256];                       // row 0 of SDF layer 8 (the sdf head)
@@ -142,6 +157,10 @@ struct __align__(1024) Smem {
     float V[3 * TM];
     float PART[4 * 3 * TM];                            // per column-quarter partial sums of the narrow heads
     long long OIDX[TM];
+    // STASH: the tile's encoding (x ACT_SCALE; entry k of row r at k*TM + r), reused by the skip connection (layer 3) and the
+    // closed-form nabla instead of re-evaluating sincosf; and the 9 small-input rows of radiance layer 0 (VolSDF: x | view | nabla)
+    float EMBS[STASH ? EMB * TM : 1];
+    __align__(16) float RADW[STASH ? 9 * 256 : 4];
 };
 
 // per-CTA global scratch (full mode): 8 softplus' planes (16-bit codes), the geometry feature (fp32), misc rows
@@ -155,9 +174,9 @@ enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_R
 struct EpiCtx {
     Smem* S; uint2* dh; float4* featp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
     unsigned t_lane; int r, cq, g; float us; int sdim;
-    unsigned bias_s, w8_s, w4_s, kb_bar, d_bar;
+    unsigned bias_s, w8_s, w4_s, radw_s, kb_bar, d_bar;
     int signal, need_lo, lane;
-    unsigned d_phase; long long* t_wait;
+    unsigned d_phase; long long* t_wait; long long* trace;
 };
 
 // this warp's part of K-block kb of the next A operand is in TMEM (and its part of D columns [64kb, 64kb+64) is consumed)
@@ -188,19 +207,46 @@ __device__ __forceinline__ void store_a16(unsigned taddr, const float (&o)[16], 
     tmem_wait_st();
 }
 
-// softplus'(z) = sigmoid(100 z) as a 16-bit code: bit 15 = (z >= 0), low 15 bits = round(t * 32767), t = exp(-|100 z|);
-// decoded as z >= 0 ? 1/(1+t) : t/(1+t)   (absolute error <= 1.6e-5)
+// softplus'(z) = sigmoid(100 z) as a 16-bit code: bit 15 = (z >= 0), low 15 bits = round(t * 32767.49), t = exp(-|100 z|);
+// decoded as r = 1 / (1 + code/32768), z >= 0 ? r : 1 - r   (absolute error <= 2e-5).  The decode is two bit operations, one
+// MUFU.RCP and one add: the 15 bits are dropped straight into the mantissa of a float in [1, 2), which *is* 1 + t.
 __device__ __forceinline__ unsigned dh_code(float z16, float t) {
-    // round(t * 32767) through the 2^23 magic number (FMA pipe; F2I would go to the XU pipe the softplus already saturates)
-    return ((~__float_as_uint(z16) >> 16) & 0x8000u) | (__float_as_uint(fmaf(t, 32767.f, 8388608.f)) & 0x7fffu);
+    // round(t * 32767.49) through the 2^23 magic number (FMA pipe; F2I would go to the XU pipe the softplus already saturates)
+    return ((~__float_as_uint(z16) >> 16) & 0x8000u) | (__float_as_uint(fmaf(t, 32767.49f, 8388608.f)) & 0x7fffu);
 }
-__device__ __forceinline__ float dh_decode(unsigned code) {
-    const float t = (float)(code & 0x7fffu) * (1.f / 32767.f);
-    const float ru = rcp_approx(1.f + t);
-    return (code & 0x8000u) ? ru : t * ru;
+__device__ __forceinline__ float dh_decode_lo(unsigned w) {            // code in bits [0,16)
+    const float ru = rcp_approx(__uint_as_float(((w & 0x7fffu) << 8) | 0x3f800000u));
+    return (w & 0x8000u) ? ru : 1.f - ru;
+}
+__device__ __forceinline__ float dh_decode_hi(unsigned w) {            // code in bits [16,32)
+    const float ru = rcp_approx(__uint_as_float(((w >> 8) & 0x7fff00u) | 0x3f800000u));
+    return (w & 0x80000000u) ? ru : 1.f - ru;
 }
 __device__ __forceinline__ void dh_decode4(const uint2 q, float (&d)[4]) {
-    d[0] = dh_decode(q.x & 0xffffu); d[1] = dh_decode(q.x >> 16); d[2] = dh_decode(q.y & 0xffffu); d[3] = dh_decode(q.y >> 16);
+    d[0] = dh_decode_lo(q.x); d[1] = dh_decode_hi(q.x); d[2] = dh_decode_lo(q.y); d[3] = dh_decode_hi(q.y);
+}
+
+// encoding entries k in [K_LO, K_LO + 16) of [x, sin(2^f x), cos(2^f x)]_f (models/base.py:46-64), x ACT_SCALE; zero outside [0, 39)
+template <int K_LO>
+__device__ __forceinline__ void emb_range(const float (&xs)[3], float (&e)[16]) {
+    constexpr int k_lo = K_LO, k_hi = K_LO + 16;
+    float sn[18], cs[18];
+#pragma unroll
+    for (int pi = 0; pi < 18; ++pi) {
+        const int f = pi / 3, cc = pi % 3;
+        const int ks = 3 + 6 * f + cc, kc = ks + 3;
+        const bool need = (ks >= k_lo && ks < k_hi) || (kc >= k_lo && kc < k_hi);
+        sn[pi] = 0.f; cs[pi] = 0.f;
+        if (need) sincosf(__fmul_rn(xs[cc], (float)(1 << f)), &sn[pi], &cs[pi]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = k_lo + j;
+        float v = 0.f;
+        if (k >= 0 && k < 3) v = xs[k];
+        else if (k >= 3 && k < EMB) { const int f = (k - 3) / 6, rem = (k - 3) % 6; v = rem < 3 ? sn[f * 3 + rem] : cs[f * 3 + rem - 3]; }
+        e[j] = v * ACT_SCALE;
+    }
 }
 
 // one GEMM's epilogue for this thread's row and its 64 columns (4 passes of 16)
@@ -236,17 +282,19 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 for (int j4 = 0; j4 < 4; ++j4) qn[j4] = dhp[(size_t)(((col0 + 64) >> 2) + j4) * TM];
             }
         }
-        if ((c16 & 1) == 0) {                                       // passes 0,1 read N-half 0 of D, passes 2,3 N-half 1
+        {                                                            // pass c16 reads N-quarter c16 of D
             const long long t0 = clock64();
-            mbar_wait(c.d_bar + 8u * (unsigned)(c16 >> 1), c.d_phase);
+            mbar_wait(c.d_bar + 8u * (unsigned)c16, c.d_phase);
             *c.t_wait += clock64() - t0;
             tc_fence_after();
+            NA_TRACE_E(c.trace, c.g, c16, 0);
         }
         float acc[16];
         {
             unsigned v[16];
             tmem_ld16(t_d + col0, v);
             tmem_wait_ld();
+            NA_TRACE_E(c.trace, c.g, c16, 1);
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
         }
@@ -280,19 +328,22 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     c.dh[(size_t)(c.g * 64 + (col0 >> 2) + j4) * TM + r] = make_uint2(cd[0] | (cd[1] << 16), cd[2] | (cd[3] << 16));
                 }
             }
-            if (KIND == K_FWD3 && col0 + 15 >= SKIP_H) {
-                // skip connection columns: h = emb[k-217] (x16)
-                const float xs[3] = {S.X[r], S.X[TM + r], S.X[2 * TM + r]};
+            if (KIND == K_FWD3 && c16 == 3 && c.cq >= 1) {
+                // skip connection columns (k >= 217): h = emb[k - 217] (x16); this thread's 16 columns are encoding entries
+                // 16 cq - 25 .. + 16
+                const int e0 = 16 * c.cq - 25;
+                if (STASH) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int k = col0 + j;
-                    if (k >= SKIP_H) {
-                        const int ei = k - SKIP_H;
-                        float val;
-                        if (ei < 3) val = xs[ei];
-                        else { const int f = (ei - 3) / 6, rem = (ei - 3) % 6; float sn, cs; sincosf(__fmul_rn(xs[rem % 3], (float)(1 << f)), &sn, &cs); val = rem < 3 ? sn : cs; }
-                        o[j] = val * ACT_SCALE;
-                    }
+                    for (int j = 0; j < 16; ++j) if (e0 + j >= 0) o[j] = S.EMBS[(e0 + j) * TM + r];
+                } else {
+                    // evaluated with one sincosf per (frequency, coordinate) pair that falls in the range
+                    const float xs[3] = {S.X[r], S.X[TM + r], S.X[2 * TM + r]};
+                    float e[16];
+                    if (c.cq == 1) emb_range<-9>(xs, e);
+                    else if (c.cq == 2) emb_range<7>(xs, e);
+                    else emb_range<23>(xs, e);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (e0 + j >= 0) o[j] = e[j];
                 }
             }
             if (KIND == K_FWD7) {
@@ -348,7 +399,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     if (c.sdim == 9) {
 #pragma unroll
                         for (int j = 0; j < 9; ++j) {
-                            const float4 w = __ldg(wsm + j * 64);
+                            const float4 w = STASH ? lds128(c.radw_s + (unsigned)(j * 256 + col0 + 4 * j4) * 4u) : __ldg(wsm + j * 64);
                             z[0] = fmaf(small_in[j], w.x, z[0]); z[1] = fmaf(small_in[j], w.y, z[1]);
                             z[2] = fmaf(small_in[j], w.z, z[2]); z[3] = fmaf(small_in[j], w.w, z[3]);
                         }
@@ -377,6 +428,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         const bool store = !(KIND == K_BWD0 || KIND == K_RAD3 || (KIND == K_FWD7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL));
         if (store) store_a16(t_d + col0, o, c.need_lo);
+        NA_TRACE_E(c.trace, c.g, c16, 2);
         if (USES_DH && (c.lane & 15) == 0) {
             // the 16 lanes' codes of this pass share one line per column quad; they are dead now: keep them out of DRAM
 #pragma unroll
@@ -384,30 +436,8 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar, c16, c.lane);
     }
-    if (N_PASS < 3) { mbar_wait(c.d_bar + 8u, c.d_phase); tc_fence_after(); }      // keep the second barrier's phase in step
-}
-
-// encoding entries k in [16 CG, 16 CG + 16) of [x, sin(2^f x), cos(2^f x)]_f (models/base.py:46-64), x ACT_SCALE; zero beyond 39
-template <int CG>
-__device__ __forceinline__ void emb_chunk(const float (&xs)[3], float (&e)[16]) {
-    constexpr int k_lo = 16 * CG, k_hi = 16 * CG + 16;
-    float sn[18], cs[18];
-#pragma unroll
-    for (int pi = 0; pi < 18; ++pi) {
-        const int f = pi / 3, cc = pi % 3;
-        const int ks = 3 + 6 * f + cc, kc = ks + 3;
-        const bool need = (ks >= k_lo && ks < k_hi) || (kc >= k_lo && kc < k_hi);
-        sn[pi] = 0.f; cs[pi] = 0.f;
-        if (need) sincosf(__fmul_rn(xs[cc], (float)(1 << f)), &sn[pi], &cs[pi]);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int k = k_lo + j;
-        float v = 0.f;
-        if (k < 3) v = xs[k];
-        else if (k < EMB) { const int f = (k - 3) / 6, rem = (k - 3) % 6; v = rem < 3 ? sn[f * 3 + rem] : cs[f * 3 + rem - 3]; }
-        e[j] = v * ACT_SCALE;
-    }
+    for (int k = N_PASS; k < 4; ++k) mbar_wait(c.d_bar + 8u * (unsigned)k, c.d_phase);      // keep the other barriers' phases in step
+    if (N_PASS < 4) tc_fence_after();
 }
 
 template <bool FULL>
@@ -424,7 +454,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
-        mbar_init(smem_u32(&S.d_ready[0]), 1); mbar_init(smem_u32(&S.d_ready[1]), 1);
+        for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.d_ready[k]), 1);
         for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.kb_ready[k]), EPI_THREADS / 32);   // one arrive per epilogue warp
         fence_barrier_init();
     }
@@ -440,6 +470,8 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
     }
     for (int i = tid; i < 256; i += THREADS) S.W8[i] = pk[L.w8_sdf + i];
     for (int i = tid; i < 768; i += THREADS) S.W4[i] = pk[L.rad_w4 + i];
+    if (STASH && FULL && job.rad && small_dim(job.multires_view) == 9)
+        for (int i = tid; i < 9 * 256; i += THREADS) S.RADW[i] = pk[L.rad_wt[0] + (size_t)256 * 256 + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -471,75 +503,73 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         const unsigned wst = smem_u32(S.Wst);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int g = 0; g < prog.n_gemm; ++g) {
+#ifdef NA_TM_TRACE
+                long long* const tr = (job.dbg && blockIdx.x == 0 && tile == (long long)gridDim.x && lane == 0) ? job.dbg + 16 : nullptr;
+#endif
                 const int n_kb = prog.g[g].n_kb, prods = prog.g[g].prods;
                 const unsigned idesc = prog.g[g].n64 ? IDESC_N64 : IDESC_N256;
                 const unsigned t_in = tmem_d + (unsigned)(g & 1) * 256u, t_out = tmem_d + (unsigned)((g + 1) & 1) * 256u;
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    { const long long t0 = clock64(); mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase); t_a += clock64() - t0; }
-                    tc_fence_after();
                     const unsigned slot0 = it % NS, ph0 = (it / NS) & 1;
                     const unsigned slot1 = (it + 1) % NS, ph1 = ((it + 1) / NS) & 1;
                     const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
-                    if (kb + 1 < n_kb || prog.g[g].n64) {
-                        // 256-wide MMAs, stage by stage
-                        { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot0]), ph0); t_full += clock64() - t0; }
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const unsigned long long bd = umma_desc(wst + slot0 * STAGE_BYTES);
+                    // the weights first (the ring runs K-blocks ahead, so these return at once), then the A operand: the MMAs go out
+                    // right behind the epilogue's signal
+                    { const long long t0 = clock64();
+                      mbar_wait(smem_u32(&S.full_bar[slot0]), ph0);
+                      if (prods == 3) mbar_wait(smem_u32(&S.full_bar[slot1]), ph1);
+                      t_full += clock64() - t0; }
+                    { const long long t0 = clock64(); mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase); t_a += clock64() - t0; }
+                    tc_fence_after();
+                    NA_TRACE_M(tr, g, kb, 0);
+                    if (elect_one()) {
+                        const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES), bd1 = umma_desc(wst + slot1 * STAGE_BYTES);
+                        if (kb + 1 < n_kb || prog.g[g].n64) {
+                            // 256-wide MMAs
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd + 2 * ks, idesc, (kb | ks) != 0);          // hi * hi
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd0 + 2 * ks, idesc, (kb | ks) != 0);              // hi * hi
                             if (prods == 3) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks + 8u, bd + 2 * ks, idesc, 1);              // lo * hi
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks + 8u, bd0 + 2 * ks, idesc, 1);                  // lo * hi
                             }
                             umma_commit(smem_u32(&S.empty_bar[slot0]));
-                        }
-                        __syncwarp();
-                        ++it;
-                        if (prods == 3) {
-                            { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot1]), ph1); t_full += clock64() - t0; }
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const unsigned long long bd = umma_desc(wst + slot1 * STAGE_BYTES);
+                            if (prods == 3) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd + 2 * ks, idesc, 1);                   // hi * lo
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd1 + 2 * ks, idesc, 1);                       // hi * lo
                                 umma_commit(smem_u32(&S.empty_bar[slot1]));
                             }
-                            __syncwarp();
-                            ++it;
-                        }
-                    } else {
-                        // last K-block: N-half 0 first (its own commit), so that the epilogue's first two passes overlap N-half 1
-                        { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot0]), ph0); t_full += clock64() - t0; }
-                        if (prods == 3) { const long long t0 = clock64(); mbar_wait(smem_u32(&S.full_bar[slot1]), ph1); t_full += clock64() - t0; }
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES), bd1 = umma_desc(wst + slot1 * STAGE_BYTES);
+                        } else {
+                            // last K-block: issued in N-parts (quarters, or halves with nsplit == 2), each with its own commit, so that
+                            // the epilogue's first passes overlap the MMAs of the remaining parts
+                            const int nsp = prog.nsplit;
+                            const unsigned ncol = 256u / (unsigned)nsp, idn = nsp == 4 ? IDESC_N64 : IDESC_N128;
+                            for (int np = 0; np < nsp; ++np) {
+                                const unsigned t_dn = t_out + ncol * np;
+                                const unsigned long long boff = (unsigned long long)(np * (int)(ncol * 128u / 16u));     // ncol rows x 128 B
+                                const unsigned long long b0 = bd0 + boff, b1 = bd1 + boff;
 #pragma unroll
-                            for (int nh = 0; nh < 2; ++nh) {
-                                const unsigned t_dn = t_out + 128u * nh;
-                                const unsigned long long b0 = bd0 + (unsigned long long)(nh * (STAGE_BYTES / 2 / 16)), b1 = bd1 + (unsigned long long)(nh * (STAGE_BYTES / 2 / 16));
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b0 + 2 * ks, IDESC_N128, (kb | ks) != 0);  // hi * hi
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b0 + 2 * ks, idn, (kb | ks) != 0);             // hi * hi
                                 if (prods == 3) {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks + 8u, b0 + 2 * ks, IDESC_N128, 1);      // lo * hi
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks + 8u, b0 + 2 * ks, idn, 1);                 // lo * hi
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b1 + 2 * ks, IDESC_N128, 1);           // hi * lo
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b1 + 2 * ks, idn, 1);                      // hi * lo
                                 }
-                                umma_commit(smem_u32(&S.d_ready[nh]));
+                                if (nsp == 4) umma_commit(smem_u32(&S.d_ready[np]));
+                                else { umma_commit(smem_u32(&S.d_ready[2 * np])); umma_commit(smem_u32(&S.d_ready[2 * np + 1])); }
                             }
                             umma_commit(smem_u32(&S.empty_bar[slot0]));
                             if (prods == 3) umma_commit(smem_u32(&S.empty_bar[slot1]));
                         }
-                        __syncwarp();
-                        it += prods == 3 ? 2 : 1;
                     }
+                    __syncwarp();
+                    it += prods == 3 ? 2 : 1;
+                    NA_TRACE_M(tr, g, kb, 1);
                 }
                 for (int kb = n_kb; kb < 4; ++kb) mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase);     // keep the phases in step
                 a_phase ^= 1;
                 if (prog.g[g].n64) {
-                    if (elect_one()) { umma_commit(smem_u32(&S.d_ready[0])); umma_commit(smem_u32(&S.d_ready[1])); }
+                    if (elect_one()) { for (int k = 0; k < 4; ++k) umma_commit(smem_u32(&S.d_ready[k])); }
                     __syncwarp();
                 }
             }
@@ -554,14 +584,17 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.misc = reinterpret_cast<float*>(sp + DH_BYTES + FEAT_BYTES);
         c.pk = pk; c.L = &L; c.job = &job; c.t_lane = tmem_d + ((unsigned)(32 * q) << 16); c.r = r; c.cq = cq;
         c.sdim = small_dim(job.multires_view);
-        c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4);
+        c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4); c.radw_s = smem_u32(S.RADW);
         c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
         c.d_phase = 0;
         long long t_d = 0, t_e0 = clock64();
-        c.t_wait = &t_d;
+        c.t_wait = &t_d; c.trace = nullptr;
         const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#ifdef NA_TM_TRACE
+            c.trace = (job.dbg && blockIdx.x == 0 && tile == (long long)gridDim.x && tid == 64) ? job.dbg + 16 : nullptr;
+#endif
             // ---- tile inputs: point, encoding (x ACT_SCALE, hi/lo) into K-block 0 of region 0 ---------------------
             {
                 const long long w = tile * TM + r;
@@ -592,10 +625,14 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 }
                 const float xs[3] = {x0, x1, x2};
                 float e[16];
-                if (cq == 0) emb_chunk<0>(xs, e);
-                else if (cq == 1) emb_chunk<1>(xs, e);
-                else if (cq == 2) emb_chunk<2>(xs, e);
-                else emb_chunk<3>(xs, e);
+                if (cq == 0) emb_range<0>(xs, e);
+                else if (cq == 1) emb_range<16>(xs, e);
+                else if (cq == 2) emb_range<32>(xs, e);
+                else emb_range<48>(xs, e);
+                if (STASH) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (16 * cq + j < EMB) S.EMBS[(16 * cq + j) * TM + r] = e[j];
+                }
                 store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
             }
             for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
@@ -621,10 +658,28 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     } else if (g == 16) {
                         epi_bar_sync();                                   // embedding-branch gradients (written at g == 12 by other threads)
                         epi_gemm<K_BWD0, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
-                        epi_bar_sync();                                   // all 39 d sdf/d emb entries complete
                     } else if (g == 17) {
+                        // small radiance inputs [x | embed(view) | nabla] (x16), kept in registers: every thread rebuilds its row's
+                        const float xs[3] = {S.X[r], S.X[TM + r], S.X[2 * TM + r]}, vs[3] = {S.V[r], S.V[TM + r], S.V[2 * TM + r]};
+                        const float nb[3] = {S.PART[r], S.PART[TM + r], S.PART[2 * TM + r]};
 #pragma unroll
-                        for (int j = 0; j < 36; ++j) small_in[j] = j < c.sdim ? c.misc[(40 + j) * TM + r] * ACT_SCALE : 0.f;
+                        for (int j = 0; j < 36; ++j) small_in[j] = 0.f;
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) { small_in[cc] = xs[cc] * ACT_SCALE; small_in[3 + cc] = vs[cc] * ACT_SCALE; }
+                        if (c.sdim == 9) {
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) small_in[6 + cc] = nb[cc] * ACT_SCALE;
+                        } else {
+#pragma unroll
+                            for (int f = 0; f < 4; ++f)
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) {
+                                    float sn, cs; sincosf(__fmul_rn(vs[cc], (float)(1 << f)), &sn, &cs);
+                                    small_in[6 + 6 * f + cc] = sn * ACT_SCALE; small_in[9 + 6 * f + cc] = cs * ACT_SCALE;
+                                }
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) small_in[30 + cc] = nb[cc] * ACT_SCALE;
+                        }
                         epi_gemm<K_RAD0, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 20) {
                         epi_gemm<K_RAD3, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
@@ -649,40 +704,9 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     }
                 }
                 if (FULL && g == 16) {
-                    if (cq == 0) {
-                        // nabla and the fp32 small radiance inputs
-                        const float xs[3] = {S.X[r], S.X[TM + r], S.X[2 * TM + r]};
-                        float nb[3];
-#pragma unroll
-                        for (int cc = 0; cc < 3; ++cc) {
-                            float n = c.misc[cc * TM + r];
-#pragma unroll
-                            for (int f = 0; f < 6; ++f) {
-                                const float fr = (float)(1 << f);
-                                float sn, cs; sincosf(__fmul_rn(xs[cc], fr), &sn, &cs);
-                                n += fr * (c.misc[(3 + 6 * f + cc) * TM + r] * cs - c.misc[(6 + 6 * f + cc) * TM + r] * sn);
-                            }
-                            nb[cc] = n;
-                        }
-                        const long long oo = S.OIDX[r];
-                        if (oo >= 0 && job.nab) { job.nab[oo * 3] = nb[0]; job.nab[oo * 3 + 1] = nb[1]; job.nab[oo * 3 + 2] = nb[2]; }
-                        if (has_rad) {
-                            float* sm = c.misc + 40 * TM + r;
-                            int qn = 0;
-                            for (int cc = 0; cc < 3; ++cc) sm[(qn++) * TM] = xs[cc];
-                            const float vs[3] = {S.V[r], S.V[TM + r], S.V[2 * TM + r]};
-                            for (int cc = 0; cc < 3; ++cc) sm[(qn++) * TM] = vs[cc];
-                            for (int f = 0; f < job.multires_view; ++f) {
-                                float sn[3], cs[3];
-                                for (int cc = 0; cc < 3; ++cc) sincosf(__fmul_rn(vs[cc], (float)(1 << f)), &sn[cc], &cs[cc]);
-                                for (int cc = 0; cc < 3; ++cc) sm[(qn++) * TM] = sn[cc];
-                                for (int cc = 0; cc < 3; ++cc) sm[(qn++) * TM] = cs[cc];
-                            }
-                            for (int cc = 0; cc < 3; ++cc) sm[(qn++) * TM] = nb[cc];
-                        }
-                    }
                     if (has_rad) {
-                        // A <- geometry feature (x16) for radiance layer 0, written over the consumed D of GEMM 16
+                        // A <- geometry feature (x16) for radiance layer 0, written over this thread's own (consumed) columns of D of
+                        // GEMM 16; signalled at once, so radiance GEMM 0 runs under the nabla arithmetic below
                         float4 fn[4];
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) fn[j4] = c.featp[(size_t)(cq * 4 + j4) * TM + r];
@@ -704,8 +728,29 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 #pragma unroll
                                 for (int j4 = 0; j4 < 4; ++j4) discard_l2(c.featp + (size_t)((col0 >> 2) + j4) * TM + r);
                             }
+                            signal_kb(c.kb_bar, c16, lane);
                         }
-                        epi_bar_sync();                       // small inputs written by cq == 0 threads are read by all four next
+                    }
+                    epi_bar_sync();                                       // all 39 d sdf/d emb entries complete
+                    if (cq < 3) {
+                        // nabla component cq in closed form: one column quarter per coordinate
+                        const int cc = cq;
+                        const float xc = S.X[cc * TM + r];
+                        float n = c.misc[cc * TM + r];
+#pragma unroll
+                        for (int f = 0; f < 6; ++f) {
+                            const float fr = (float)(1 << f);
+                            float sn, cs;
+                            if (STASH) { sn = S.EMBS[(3 + 6 * f + cc) * TM + r] * (1.f / ACT_SCALE); cs = S.EMBS[(6 + 6 * f + cc) * TM + r] * (1.f / ACT_SCALE); }
+                            else sincosf(__fmul_rn(xc, fr), &sn, &cs);
+                            n += fr * (c.misc[(3 + 6 * f + cc) * TM + r] * cs - c.misc[(6 + 6 * f + cc) * TM + r] * sn);
+                        }
+                        S.PART[cc * TM + r] = n;
+                    }
+                    epi_bar_sync();                                       // PART[0..2] = nabla of every row
+                    if (cq == 0) {
+                        const long long oo = S.OIDX[r];
+                        if (oo >= 0 && job.nab) { job.nab[oo * 3] = S.PART[r]; job.nab[oo * 3 + 1] = S.PART[TM + r]; job.nab[oo * 3 + 2] = S.PART[2 * TM + r]; }
                     }
                 }
                 if (FULL && g == 20) {
@@ -722,9 +767,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         }
                     }
                 }
-                if (g + 1 < prog.n_gemm) {
-                    if (FULL && g == 16) for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);    // A was written by the tail above
-                } else {
+                if (g + 1 >= prog.n_gemm) {
                     tc_fence_before();
                     epi_bar_sync();                           // X / OIDX / PART and TMEM region 0 are rewritten by the next tile's input stage
                 }
@@ -825,6 +868,8 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     if (total <= 0) return NA_OK;
     const ImageLayout T = image_layout();
     Program prog; prog.n_gemm = 0;
+    static const char* nsplit_env = getenv("NA_TM_NSPLIT");                   // diagnostics: "2" = N-halves (the r1n scheme), default quarters
+    prog.nsplit = (nsplit_env && nsplit_env[0] == '2') ? 2 : 4;
     const int last = !job.want_full ? (job.feat ? 8 : 7) : (job.rad ? 20 : 16);
     for (int g = 0; g <= last; ++g) {
         Gemm t; t.w_off = T.w_off[g]; t.stage_bytes = (unsigned)T.N[g] * 128u; t.n_kb = (unsigned char)T.n_kb[g];

@@ -102,7 +102,7 @@ class NetEngine:
                                 ptr(sdf), ptr(feat), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_sdf_eval')
         return sdf.reshape(shape), (feat.reshape(*shape, 256) if want_feat else None)
 
-    def full_eval(self, x, view_dirs, want_radiance=True, apply_bg=None):
+    def full_eval(self, x, view_dirs, want_radiance=True, apply_bg=None, want_feat=True):
         L = _lib.lib()
         shape = x.shape[:-1]
         xf = x.detach().reshape(-1, 3).float().contiguous()
@@ -112,7 +112,7 @@ class NetEngine:
         rad = torch.empty(m, 3, device=dev, dtype=torch.float32) if want_radiance else None
         sdf = torch.empty(m, device=dev, dtype=torch.float32)
         nab = torch.empty(m, 3, device=dev, dtype=torch.float32)
-        feat = torch.empty(m, 256, device=dev, dtype=torch.float32)
+        feat = torch.empty(m, 256, device=dev, dtype=torch.float32) if want_feat else None
         self.pack()
         ws = self.workspace(L.na_eval_workspace_bytes(m))
         desc = self.desc
@@ -121,7 +121,7 @@ class NetEngine:
         with torch.cuda.device(dev):
             check(L.na_full_eval(C.byref(desc), ptr(self.packed), ptr(xf), ptr(vf), m, PRECISIONS[self.precision],
                                  ptr(rad), ptr(sdf), ptr(nab), ptr(feat), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_full_eval')
-        return (rad.reshape(*shape, 3) if want_radiance else None), sdf.reshape(shape), nab.reshape(*shape, 3), feat.reshape(*shape, 256)
+        return (rad.reshape(*shape, 3) if want_radiance else None), sdf.reshape(shape), nab.reshape(*shape, 3), (feat.reshape(*shape, 256) if want_feat else None)
 
     # ------------------------------------------------------------------------------------------
     def volsdf_render(self, rays_o, rays_d, alpha_beta, *, near, far, N_samples, N_importance, max_upsample_steps,

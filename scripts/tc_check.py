@@ -38,17 +38,19 @@ x = torch.rand(n, 3, device=dev, generator=g) * 4 - 2
 v = torch.nn.functional.normalize(torch.randn(n // 4, 3, device=dev, generator=g), dim=-1)
 F_SDF = 2 * (39 * 256 + 256 * 256 * 2 + 256 * 217 + 256 * 256 * 4 + 256); F_FULL = 2 * (524544 + 459008 + 265216)
 import ctypes as C
-dbg = torch.zeros(8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(512, dtype=torch.int64, device=dev)
+trace_dir = os.environ.get('NA_TRACE_DIR')
 for prec in ('fp32',) + TC_MODES:
     m.engine().precision = prec
     eng = m.engine()
     nerfart_b200.lib().na_debug_set_buffer(C.c_void_p(dbg.data_ptr()) if prec != 'fp32' else None)
-    for fn, cnt, fl, name in ((lambda: eng.sdf_eval(x, apply_bg=True), n, F_SDF, 'sdf-only'), (lambda: eng.full_eval(x[:n // 4], v), n // 4, F_FULL, 'full')):
-        fn(); torch.cuda.synchronize()
+    for fn, cnt, fl, name in ((lambda: eng.sdf_eval(x, apply_bg=True), n, F_SDF, 'sdf-only'), (lambda: eng.full_eval(x[:n // 4], v, want_feat=False), n // 4, F_FULL, 'full')):
+        fn(); torch.cuda.synchronize(); dbg.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); fn(); e1.record(); torch.cuda.synchronize()
         t = e0.elapsed_time(e1) * 1e-3 / 2
         print(f'{prec:9s} {name:9s} {cnt/t/1e6:9.2f} Msamples/s  {cnt*fl/t/1e12:8.2f} TFLOP/s (algorithmic)  {t*1e3:8.2f} ms')
         if prec != 'fp32':
+            if trace_dir: np.save(os.path.join(trace_dir, f'trace_{prec}_{name}.npy'), dbg.cpu().numpy())
             d = dbg.cpu().tolist(); ntile = (cnt + 127) // 128 / 148
             print(f'      CTA0 cycles/tile: mma-thread total {d[0]/ntile:9.0f}  wait a_ready {d[1]/ntile:9.0f}  wait weights {d[2]/ntile:9.0f} | epilogue total {d[3]/ntile:9.0f}  wait d_ready {d[4]/ntile:9.0f}')
