@@ -277,7 +277,21 @@ typedef struct NaClipWeights {
     NaClipLayer layers[12];                  /* visual.transformer.resblocks.{i}                               */
     const float *ln_post_w, *ln_post_b;
     const float* proj;                       /* visual.proj [768,512]                                          */
+    const void* packed;                      /* na_clip_pack_weights output (required for NA_CLIP_TF32), else NULL */
+    int32_t precision;                       /* NA_CLIP_FP32 | NA_CLIP_TF32                                    */
+    int32_t reserved;
 } NaClipWeights;
+/* arithmetic of the tower's linear layers (conv1-as-GEMM, in_proj, out_proj, c_fc, c_proj, proj; forward and backward-data):
+ * NA_CLIP_FP32 = fp32 CUDA cores; NA_CLIP_TF32 = tcgen05 kind::tf32 with fp32 accumulation in TMEM (csrc/tgemm.cu).  The
+ * reference runs this model in fp16 on the GPU (clip.load keeps fp16 weights), so both are at least its precision.
+ * LayerNorm, softmax attention over the 50 tokens and QuickGELU stay fp32 in both modes.                                  */
+#define NA_CLIP_FP32 0
+#define NA_CLIP_TF32 1
+
+/* TF32 weight images for NA_CLIP_TF32: every linear weight in both orientations (y = x W^T and dx = dy W), rounded to TF32,
+ * pre-tiled as the shared-memory image of the tensor-core operand.  The weights are frozen, so this runs once per tower.  */
+size_t na_clip_packed_bytes(void);
+int na_clip_pack_weights(const NaClipWeights* weights, void* packed, void* stream);
 
 size_t na_clip_workspace_bytes(int32_t batch);
 /* images [B,3,224,224] (already resized + CLIP-normalised) -> feats [B,512].  The workspace keeps the activations of this

@@ -24,7 +24,12 @@ class _Layer(C.Structure):
 class NaClipWeights(C.Structure):
     _fields_ = [('conv1', C.c_void_p), ('class_embedding', C.c_void_p), ('positional_embedding', C.c_void_p),
                 ('ln_pre_w', C.c_void_p), ('ln_pre_b', C.c_void_p), ('layers', _Layer * 12),
-                ('ln_post_w', C.c_void_p), ('ln_post_b', C.c_void_p), ('proj', C.c_void_p)]
+                ('ln_post_w', C.c_void_p), ('ln_post_b', C.c_void_p), ('proj', C.c_void_p),
+                ('packed', C.c_void_p), ('precision', C.c_int32), ('reserved', C.c_int32)]
+
+
+NA_CLIP_FP32, NA_CLIP_TF32 = 0, 1
+CLIP_PRECISIONS = {'fp32': NA_CLIP_FP32, 'tf32': NA_CLIP_TF32}
 
 
 def _bind():
@@ -34,6 +39,9 @@ def _bind():
         L.na_clip_workspace_bytes.argtypes = [C.c_int32]
         L.na_clip_vitb32_encode_fwd.argtypes = [C.POINTER(NaClipWeights), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.na_clip_vitb32_encode_bwd.argtypes = [C.POINTER(NaClipWeights), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_clip_packed_bytes.restype = C.c_size_t
+        L.na_clip_packed_bytes.argtypes = []
+        L.na_clip_pack_weights.argtypes = [C.POINTER(NaClipWeights), C.c_void_p, C.c_void_p]
         L._clip_bound = True
     return L
 
@@ -46,8 +54,14 @@ class ClipVisionB32:
                 'ln_1.weight', 'ln_1.bias', 'attn.in_proj_weight', 'attn.in_proj_bias', 'attn.out_proj.weight', 'attn.out_proj.bias',
                 'ln_2.weight', 'ln_2.bias', 'mlp.c_fc.weight', 'mlp.c_fc.bias', 'mlp.c_proj.weight', 'mlp.c_proj.bias')]
 
-    def __init__(self, state_dict, device):
+    def __init__(self, state_dict, device, precision=None):
+        """precision: 'tf32' (default; tcgen05 kind::tf32 linear layers, csrc/tgemm.cu) or 'fp32' (CUDA cores); env NA_CLIP overrides
+        the default.  The reference runs this tower in fp16 (clip.load on CUDA), so either is at least its precision."""
+        import os
         self.device = torch.device(device)
+        self.precision = precision or os.environ.get('NA_CLIP', 'tf32')
+        if self.precision not in CLIP_PRECISIONS:
+            raise RuntimeError(f'unknown CLIP precision {self.precision!r} (expected one of {sorted(CLIP_PRECISIONS)})')
         if self.device.type != 'cuda':
             raise RuntimeError('nerfart_b200: the CLIP image tower runs on CUDA only (no CPU path exists)')
         self.w = {k: state_dict[k].detach().to(self.device, torch.float32).contiguous() for k in self.KEYS}
@@ -62,17 +76,26 @@ class ClipVisionB32:
             Lw.ln_1_w, Lw.ln_1_b, Lw.in_proj_w, Lw.in_proj_b = g(p + 'ln_1.weight'), g(p + 'ln_1.bias'), g(p + 'attn.in_proj_weight'), g(p + 'attn.in_proj_bias')
             Lw.out_proj_w, Lw.out_proj_b, Lw.ln_2_w, Lw.ln_2_b = g(p + 'attn.out_proj.weight'), g(p + 'attn.out_proj.bias'), g(p + 'ln_2.weight'), g(p + 'ln_2.bias')
             Lw.c_fc_w, Lw.c_fc_b, Lw.c_proj_w, Lw.c_proj_b = g(p + 'mlp.c_fc.weight'), g(p + 'mlp.c_fc.bias'), g(p + 'mlp.c_proj.weight'), g(p + 'mlp.c_proj.bias')
+        W.packed, W.precision, W.reserved = None, CLIP_PRECISIONS[self.precision], 0
         self.cw = W
+        self.packed = None
+        if self.precision == 'tf32':
+            # TF32 operand images of the (frozen) weights, both orientations: built once
+            L = _bind()
+            self.packed = torch.empty(int(L.na_clip_packed_bytes()), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                check(L.na_clip_pack_weights(C.byref(W), ptr(self.packed), stream_ptr(self.device)), 'na_clip_pack_weights')
+            W.packed = self.packed.data_ptr()
 
     # -- constructors ---------------------------------------------------------------------------------------------
     @classmethod
-    def from_openai(cls, clip_model, device):
+    def from_openai(cls, clip_model, device, precision=None):
         """`clip_model` = the object `clip.load("ViT-B/32")` returns (clip_loss.py:165)."""
         sd = {k[len('visual.'):]: v for k, v in clip_model.state_dict().items() if k.startswith('visual.')}
-        return cls(sd, device)
+        return cls(sd, device, precision)
 
     @classmethod
-    def from_hf(cls, hf_model, device):
+    def from_hf(cls, hf_model, device, precision=None):
         """transformers.CLIPVisionModelWithProjection (the offline stand-in oracle) -> openai layout."""
         s = hf_model.state_dict()
         v = 'vision_model.'
@@ -90,10 +113,10 @@ class ClipVisionB32:
             sd[b + 'attn.out_proj.weight'], sd[b + 'attn.out_proj.bias'] = s[a + 'self_attn.out_proj.weight'], s[a + 'self_attn.out_proj.bias']
             sd[b + 'mlp.c_fc.weight'], sd[b + 'mlp.c_fc.bias'] = s[a + 'mlp.fc1.weight'], s[a + 'mlp.fc1.bias']
             sd[b + 'mlp.c_proj.weight'], sd[b + 'mlp.c_proj.bias'] = s[a + 'mlp.fc2.weight'], s[a + 'mlp.fc2.bias']
-        return cls(sd, device)
+        return cls(sd, device, precision)
 
     @classmethod
-    def random(cls, seed, device):
+    def random(cls, seed, device, precision=None):
         """Seeded random weights of the right shapes (benchmarks / smoke tests when no CLIP weights are available offline)."""
         g = torch.Generator(device='cpu'); g.manual_seed(seed)
         shapes = {'conv1.weight': (768, 3, 32, 32), 'class_embedding': (768,), 'positional_embedding': (50, 768), 'proj': (768, 512)}
@@ -110,7 +133,7 @@ class ClipVisionB32:
                 shp = shapes.get(k) or per[k.split('.', 3)[3]]
                 fan_in = shp[-1] if len(shp) == 2 else (3072 if len(shp) == 4 else 768)
                 sd[k] = torch.randn(*shp, generator=g) * (fan_in ** -0.5 if len(shp) > 1 else 0.02)
-        return cls(sd, device)
+        return cls(sd, device, precision)
 
     # -- the op ----------------------------------------------------------------------------------------------------
     def encode_image(self, images):

@@ -280,15 +280,39 @@ static Ws layout(int B) {
     return w;
 }
 
-static int gemm(bool nt, const float* A, const float* Bm, float* C, int M, int N, int K, const float* bias, float* raw, int act,
-                const float* R, cudaStream_t s) {
-    if (N % 64 || K % 16) return NA_ERR_UNSUPPORTED;
-    dim3 grid(N / 64, (M + 63) / 64);
-    if (nt) sgemm_kernel<true><<<grid, 256, 0, s>>>(A, Bm, C, M, N, K, bias, raw, act, R);
-    else    sgemm_kernel<false><<<grid, 256, 0, s>>>(A, Bm, C, M, N, K, bias, raw, act, R);
-    NA_CHECK_LAUNCH();
-    return NA_OK;
+}  // namespace clipv
+int tgemm(const float* A, const unsigned char* img, float* C, int M, int N, int K, const float* bias, float* raw, int act,
+          const float* R, cudaStream_t stream);                                            // csrc/tgemm.cu
+int tgemm_pack(const float* src, int rows, int cols, int transpose, unsigned char* img, cudaStream_t stream);
+namespace clipv {
+
+// TF32 weight images of one [R][C] matrix (byte offsets into the packed buffer): `nt` serves y = x W^T (operand rows = R,
+// contraction = C), `tn` serves dx = dy W (operand rows = C, contraction = R)
+struct Img { size_t nt, tn; };
+struct Packed { Img conv1, proj, in[LAYERS], out[LAYERS], fc[LAYERS], pr[LAYERS]; size_t total; };
+static Packed packed_layout() {
+    Packed P; size_t o = 0;
+    auto take = [&](size_t r, size_t c) { Img im; im.nt = o; o += r * c * 4; im.tn = o; o += r * c * 4; return im; };
+    P.conv1 = take(D, PATCH_K); P.proj = take(D, OUT);
+    for (int l = 0; l < LAYERS; ++l) { P.in[l] = take(3 * D, D); P.out[l] = take(D, D); P.fc[l] = take(FF, D); P.pr[l] = take(D, FF); }
+    P.total = o;
+    return P;
 }
+
+// one linear layer: the tcgen05 TF32 kernel when `packed` is set (NA_CLIP_TF32), else the fp32 CUDA-core kernel
+struct Gemm {
+    const unsigned char* packed; cudaStream_t s;
+    int operator()(bool nt, const float* A, const float* Bm, const Img& im, float* C, int M, int N, int K, const float* bias, float* raw,
+                   int act, const float* R) const {
+        if (N % 64 || K % 16) return NA_ERR_UNSUPPORTED;
+        if (packed) return tgemm(A, packed + (nt ? im.nt : im.tn), C, M, N, K, bias, raw, act, R, s);
+        dim3 grid(N / 64, (M + 63) / 64);
+        if (nt) sgemm_kernel<true><<<grid, 256, 0, s>>>(A, Bm, C, M, N, K, bias, raw, act, R);
+        else    sgemm_kernel<false><<<grid, 256, 0, s>>>(A, Bm, C, M, N, K, bias, raw, act, R);
+        NA_CHECK_LAUNCH();
+        return NA_OK;
+    }
+};
 static int ln_fwd(const float* x, size_t stride, const float* w, const float* b, float* y, float* stats, int rows, cudaStream_t s) {
     ln_fwd_kernel<<<(rows + 3) / 4, 128, 0, s>>>(x, stride, w, b, y, stats, rows);
     NA_CHECK_LAUNCH();
@@ -307,6 +331,29 @@ static int ln_bwd(const float* dy, const float* x, size_t stride, const float* w
 using namespace na;
 using namespace na::clipv;
 
+extern "C" size_t na_clip_packed_bytes(void) { return packed_layout().total; }
+
+extern "C" int na_clip_pack_weights(const NaClipWeights* Wt, void* packed_, void* stream_) {
+    if (!Wt || !packed_) return NA_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream_;
+    unsigned char* pk = (unsigned char*)packed_;
+    const Packed P = packed_layout();
+    auto both = [&](const float* src, int rows, int cols, const Img& im) {
+        NA_TRY(tgemm_pack(src, rows, cols, 0, pk + im.nt, s));
+        return tgemm_pack(src, rows, cols, 1, pk + im.tn, s);
+    };
+    NA_TRY(both(Wt->conv1, D, PATCH_K, P.conv1));
+    NA_TRY(both(Wt->proj, D, OUT, P.proj));
+    for (int l = 0; l < LAYERS; ++l) {
+        const NaClipLayer& Lw = Wt->layers[l];
+        NA_TRY(both(Lw.in_proj_w, 3 * D, D, P.in[l]));
+        NA_TRY(both(Lw.out_proj_w, D, D, P.out[l]));
+        NA_TRY(both(Lw.c_fc_w, FF, D, P.fc[l]));
+        NA_TRY(both(Lw.c_proj_w, D, FF, P.pr[l]));
+    }
+    return NA_OK;
+}
+
 extern "C" size_t na_clip_workspace_bytes(int32_t batch) { return batch > 0 ? layout(batch).total * sizeof(float) : 0; }
 
 extern "C" int na_clip_vitb32_encode_fwd(const NaClipWeights* Wt, const float* images, int32_t B, float* feats, void* ws_, size_t ws_bytes,
@@ -317,26 +364,29 @@ extern "C" int na_clip_vitb32_encode_fwd(const NaClipWeights* Wt, const float* i
     cudaStream_t s = (cudaStream_t)stream_;
     float* ws = (float*)ws_;
     const int T = B * TOK;
+    const Packed P = packed_layout();
+    const Gemm gemm{Wt->precision == NA_CLIP_TF32 ? (const unsigned char*)Wt->packed : nullptr, s};
+    if (Wt->precision == NA_CLIP_TF32 && !Wt->packed) return NA_ERR_BAD_ARG;
     const size_t npix = (size_t)B * 3 * IMG * IMG;
     im2col_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(images, ws + w.patches, B, 0, nullptr);
     NA_CHECK_LAUNCH();
-    NA_TRY(gemm(true, ws + w.patches, Wt->conv1, ws + w.emb, B * NPATCH, D, PATCH_K, nullptr, nullptr, 0, nullptr, s));
+    NA_TRY(gemm(true, ws + w.patches, Wt->conv1, P.conv1, ws + w.emb, B * NPATCH, D, PATCH_K, nullptr, nullptr, 0, nullptr));
     tokens_kernel<<<(unsigned)(((size_t)T * D + 255) / 256), 256, 0, s>>>(ws + w.emb, Wt->class_embedding, Wt->positional_embedding, ws + w.x0, B);
     NA_CHECK_LAUNCH();
     NA_TRY(ln_fwd(ws + w.x0, D, Wt->ln_pre_w, Wt->ln_pre_b, ws + w.x[0], ws + w.stats_pre, T, s));
     for (int l = 0; l < LAYERS; ++l) {
         const NaClipLayer& Lw = Wt->layers[l];
         NA_TRY(ln_fwd(ws + w.x[l], D, Lw.ln_1_w, Lw.ln_1_b, ws + w.ybuf, ws + w.stats1[l], T, s));
-        NA_TRY(gemm(true, ws + w.ybuf, Lw.in_proj_w, ws + w.qkv[l], T, 3 * D, D, Lw.in_proj_b, nullptr, 0, nullptr, s));
+        NA_TRY(gemm(true, ws + w.ybuf, Lw.in_proj_w, P.in[l], ws + w.qkv[l], T, 3 * D, D, Lw.in_proj_b, nullptr, 0, nullptr));
         attn_fwd_kernel<<<B * HEADS, 128, 0, s>>>(ws + w.qkv[l], ws + w.ctx, ws + w.P[l]);
         NA_CHECK_LAUNCH();
-        NA_TRY(gemm(true, ws + w.ctx, Lw.out_proj_w, ws + w.xmid[l], T, D, D, Lw.out_proj_b, nullptr, 0, ws + w.x[l], s));
+        NA_TRY(gemm(true, ws + w.ctx, Lw.out_proj_w, P.out[l], ws + w.xmid[l], T, D, D, Lw.out_proj_b, nullptr, 0, ws + w.x[l]));
         NA_TRY(ln_fwd(ws + w.xmid[l], D, Lw.ln_2_w, Lw.ln_2_b, ws + w.ybuf, ws + w.stats2[l], T, s));
-        NA_TRY(gemm(true, ws + w.ybuf, Lw.c_fc_w, ws + w.abuf, T, FF, D, Lw.c_fc_b, ws + w.h[l], 1, nullptr, s));
-        NA_TRY(gemm(true, ws + w.abuf, Lw.c_proj_w, ws + w.x[l + 1], T, D, FF, Lw.c_proj_b, nullptr, 0, ws + w.xmid[l], s));
+        NA_TRY(gemm(true, ws + w.ybuf, Lw.c_fc_w, P.fc[l], ws + w.abuf, T, FF, D, Lw.c_fc_b, ws + w.h[l], 1, nullptr));
+        NA_TRY(gemm(true, ws + w.abuf, Lw.c_proj_w, P.pr[l], ws + w.x[l + 1], T, D, FF, Lw.c_proj_b, nullptr, 0, ws + w.xmid[l]));
     }
     NA_TRY(ln_fwd(ws + w.x[LAYERS], (size_t)TOK * D, Wt->ln_post_w, Wt->ln_post_b, ws + w.ypost, ws + w.stats_post, B, s));
-    return gemm(false, ws + w.ypost, Wt->proj, feats, B, OUT, D, nullptr, nullptr, 0, nullptr, s);
+    return gemm(false, ws + w.ypost, Wt->proj, P.proj, feats, B, OUT, D, nullptr, nullptr, 0, nullptr);
 }
 
 extern "C" int na_clip_vitb32_encode_bwd(const NaClipWeights* Wt, const float* grad_feats, int32_t B, float* grad_images, void* ws_,
@@ -352,31 +402,34 @@ extern "C" int na_clip_vitb32_encode_bwd(const NaClipWeights* Wt, const float* g
         NA_TRY(check_cuda(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM)));
         attr_set = true;
     }
+    const Packed P = packed_layout();
+    const Gemm gemm{Wt->precision == NA_CLIP_TF32 ? (const unsigned char*)Wt->packed : nullptr, s};
+    if (Wt->precision == NA_CLIP_TF32 && !Wt->packed) return NA_ERR_BAD_ARG;
     float* dx = ws + w.d_c;                       // gradient w.r.t. the residual stream, [T][768]
     float* dy = ws + w.ybuf;                      // scratch [T][768]
     // feats = ln_post(x[:,0,:]) @ proj  ->  d ypost = grad_feats @ proj^T  (proj is [768][512] = "B[N=768][K=512]" in NT form)
-    NA_TRY(gemm(true, grad_feats, Wt->proj, ws + w.ypost, B, D, OUT, nullptr, nullptr, 0, nullptr, s));
+    NA_TRY(gemm(true, grad_feats, Wt->proj, P.proj, ws + w.ypost, B, D, OUT, nullptr, nullptr, 0, nullptr));
     NA_TRY(check_cuda(cudaMemsetAsync(dx, 0, (size_t)T * D * sizeof(float), s)));
     NA_TRY(ln_bwd(ws + w.ypost, ws + w.x[LAYERS], (size_t)TOK * D, Wt->ln_post_w, ws + w.stats_post, nullptr, dx, (size_t)TOK * D, B, s));
     for (int l = LAYERS - 1; l >= 0; --l) {
         const NaClipLayer& Lw = Wt->layers[l];
         // x_{l+1} = xmid + c_proj(qgelu(c_fc(ln_2(xmid))))
-        NA_TRY(gemm(false, dx, Lw.c_proj_w, ws + w.d_a, T, FF, D, nullptr, nullptr, 0, nullptr, s));             // d a = dx @ Wproj
+        NA_TRY(gemm(false, dx, Lw.c_proj_w, P.pr[l], ws + w.d_a, T, FF, D, nullptr, nullptr, 0, nullptr));             // d a = dx @ Wproj
         qgelu_bwd_kernel<<<(unsigned)(((size_t)T * FF + 255) / 256), 256, 0, s>>>(ws + w.h[l], ws + w.d_a, (size_t)T * FF);
         NA_CHECK_LAUNCH();
-        NA_TRY(gemm(false, ws + w.d_a, Lw.c_fc_w, dy, T, D, FF, nullptr, nullptr, 0, nullptr, s));               // d ln_2 out
+        NA_TRY(gemm(false, ws + w.d_a, Lw.c_fc_w, P.fc[l], dy, T, D, FF, nullptr, nullptr, 0, nullptr));               // d ln_2 out
         NA_TRY(ln_bwd(dy, ws + w.xmid[l], D, Lw.ln_2_w, ws + w.stats2[l], dx, dx, D, T, s));                     // dx := d xmid
         // xmid = x_l + out_proj(attn(in_proj(ln_1(x_l))))
-        NA_TRY(gemm(false, dx, Lw.out_proj_w, ws + w.ctx, T, D, D, nullptr, nullptr, 0, nullptr, s));            // d ctx
+        NA_TRY(gemm(false, dx, Lw.out_proj_w, P.out[l], ws + w.ctx, T, D, D, nullptr, nullptr, 0, nullptr));            // d ctx
         attn_bwd_kernel<<<B * HEADS, 128, ATTN_BWD_SMEM, s>>>(ws + w.qkv[l], ws + w.P[l], ws + w.ctx, ws + w.d_b);
         NA_CHECK_LAUNCH();
-        NA_TRY(gemm(false, ws + w.d_b, Lw.in_proj_w, dy, T, D, 3 * D, nullptr, nullptr, 0, nullptr, s));         // d ln_1 out
+        NA_TRY(gemm(false, ws + w.d_b, Lw.in_proj_w, P.in[l], dy, T, D, 3 * D, nullptr, nullptr, 0, nullptr));         // d ln_1 out
         NA_TRY(ln_bwd(dy, ws + w.x[l], D, Lw.ln_1_w, ws + w.stats1[l], dx, dx, D, T, s));                        // dx := d x_l
     }
     NA_TRY(ln_bwd(dx, ws + w.x0, D, Wt->ln_pre_w, ws + w.stats_pre, nullptr, dy, D, T, s));                       // d x0
     tokens_bwd_kernel<<<(unsigned)(((size_t)B * NPATCH * D + 255) / 256), 256, 0, s>>>(dy, ws + w.emb, B);
     NA_CHECK_LAUNCH();
-    NA_TRY(gemm(false, ws + w.emb, Wt->conv1, ws + w.patches, B * NPATCH, PATCH_K, D, nullptr, nullptr, 0, nullptr, s));   // d patches
+    NA_TRY(gemm(false, ws + w.emb, Wt->conv1, P.conv1, ws + w.patches, B * NPATCH, PATCH_K, D, nullptr, nullptr, 0, nullptr));   // d patches
     const size_t npix = (size_t)B * 3 * IMG * IMG;
     im2col_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(nullptr, ws + w.patches, B, 1, grad_images);
     NA_CHECK_LAUNCH();

@@ -33,7 +33,13 @@ def towers():
     hf = hf.to(DEV).float().eval()
     for p in hf.parameters():
         p.requires_grad_(False)
-    return hf, ClipVisionB32.from_hf(hf, DEV)
+    return hf, ClipVisionB32.from_hf(hf, DEV, precision='fp32')
+
+
+@pytest.fixture(scope='module')
+def tower_tf32(towers):
+    from nerfart_b200.criteria.clip_vit import ClipVisionB32
+    return ClipVisionB32.from_hf(towers[0], DEV, precision='tf32')
 
 
 def rel(a, b):
@@ -55,6 +61,31 @@ def test_encode_image_forward_and_image_gradient(towers, B):
     e_f, e_g = rel(out, ref), rel(x2.grad, x1.grad)
     print(f'B={B}: features rel err {e_f:.2e} (max |f| {float(ref.abs().max()):.3f}), image-gradient rel err {e_g:.2e}')
     assert e_f < 2e-4 and e_g < 2e-4
+
+
+@pytest.mark.parametrize('B', [1, 2, 3, 14])
+def test_tf32_tensor_core_tower_forward_and_image_gradient(towers, tower_tf32, B):
+    """The default arithmetic: every linear layer on tcgen05 kind::tf32 (csrc/tgemm.cu; 11-bit operands, fp32 accumulation in
+    TMEM; the reference runs the tower in fp16).  Tolerances are those of 10-bit-mantissa operands through 12 blocks, against
+    the fp32 stand-in: 1e-2 of the largest feature, 3e-2 of the largest image-gradient entry, cosine > 0.9999."""
+    import nerfart_b200
+    hf, _ = towers
+    g = torch.Generator(device='cpu'); g.manual_seed(100 + B)
+    x = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
+    gf = torch.randn(B, 512, generator=g).to(DEV)
+    x1 = x.clone().requires_grad_(True)
+    ref = hf(pixel_values=x1).image_embeds
+    (ref * gf).sum().backward()
+    x2 = x.clone().requires_grad_(True)
+    n0 = nerfart_b200.launch_count()
+    out = tower_tf32.encode_image(x2)
+    (out * gf).sum().backward()
+    assert nerfart_b200.launch_count() > n0
+    e_f, e_g = rel(out, ref), rel(x2.grad, x1.grad)
+    cos_f = float(F.cosine_similarity(out.flatten(), ref.flatten(), dim=0))
+    cos_g = float(F.cosine_similarity(x2.grad.flatten(), x1.grad.flatten(), dim=0))
+    print(f'tf32 B={B}: features rel err {e_f:.2e} cos {cos_f:.6f}, image-gradient rel err {e_g:.2e} cos {cos_g:.6f}')
+    assert e_f < 1e-2 and e_g < 3e-2 and cos_f > 0.9999 and cos_g > 0.9995
 
 
 def test_two_encodes_before_backward_keep_their_own_activations(towers):
