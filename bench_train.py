@@ -190,11 +190,11 @@ def main(args):
         line = {'metric': 'MLP samples/sec (VolSDF 480x270x128 fine-tune step)', 'value': n_rays * P * args.steps / t, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': 'backward: tf32 mma.sync + f32 recompute (NA_BWD/NA_WGRAD); CLIP tower f32; forward: ' + args.precision, 'data': 'synthetic',
+                'dtype': ('backward: activations from the tcgen05 forward kernel (no recompute), ' if args.precision != 'fp32' else 'backward: f32 recompute, ') + 'backward-data / weight-gradient GEMMs tf32 mma.sync (NA_BWD/NA_WGRAD); CLIP tower linear layers tcgen05 tf32; forward: ' + args.precision, 'data': 'synthetic',
                 'config': {'workload': f'VolSDF fine-tune step {H}x{W} ({n_rays} rays), 128+64 samples/ray, pass 1 + pass 2 in 108 patches of '
                                        '1200 rays, eikonal on, perturb on, style=' + style + (' (3 CLIP losses, seeded random ViT-B/32 weights + stand-in text features, no VGG)' if style == 'clip' else ' (weighted MSE)') + ', Adam step',
                            'parallelism': f'patch round-robin x{world}' + (' + NCCL all-reduce of the packed gradient' if world > 1 else ''),
-                           'l2': 'per-patch stash (9.9 GB) >> 126 MB L2; no explicit flush'},
+                           'l2': 'per-patch stash (11.8 GB) >> 126 MB L2; no explicit flush'},
                 'phases_ms': {'pass1_render': 1e3 * t_p1, 'pass2_patch_forward': 1e3 * t_pfwd, 'pass2_backward': 1e3 * t_bwd,
                               'style_loss_forward': 1e3 * t_style,
                               'other (style backward, unpack, Adam, host)': 1e3 * (t / args.steps - t_p1 - t_pfwd - t_bwd - t_style)},
@@ -204,8 +204,8 @@ def main(args):
                 'gpu_launches': int(launches), 'clocks': clk,
                 'roofline': {'bound': 'tensor', 'kernel': 'mlp_bwd_kernel + wgrad kernel (pass-2 backward)',
                              'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops'], 'traffic': None,
-                             'flop_per_sample': F_BWD, 'note': 'algorithmic backward FLOPs / time inside render_bwd; recompute GEMMs on the fp32 FMA pipe, '
-                             'backward-data and weight-gradient GEMMs on legacy mma.sync TF32; not yet on tcgen05', 'peak_kind': f'{kind} bf16 burst'},
+                             'flop_per_sample': F_BWD, 'note': 'algorithmic backward FLOPs / time inside render_bwd; the forward half of the backward (21 GEMMs) runs on tcgen05 '
+                             '(stash-out launch of the TMEM kernel), backward-data and weight-gradient GEMMs on legacy mma.sync TF32', 'peak_kind': f'{kind} bf16 burst'},
                 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -227,7 +227,9 @@ typedef struct NaTrainCfg {
     float   speed_factor;         /* ln_beta / ln_s speed factor (volsdf.py:337-339, neus.py:116-117)                   */
     int32_t train_surface;        /* 0: implicit_surface is frozen (fix_module): no SDF-net weight gradients            */
     int32_t train_radiance;       /* 0: radiance_net is frozen (NeuS fine-tune, neus.py:28)                             */
-    int32_t reserved;
+    int32_t precision;            /* NA_PRECISION_*: FP32 = the backward kernel recomputes the forward pass of the patch in fp32
+                                     on CUDA cores; tensor-core modes = the tcgen05 forward kernel re-evaluates the patch once and
+                                     leaves the activations the backward needs in the workspace (no recompute)              */
 } NaTrainCfg;
 
 typedef struct NaRawGrads {       /* where na_unpack_grads writes; same layer order as NaRawParams; NULL = skip layer   */

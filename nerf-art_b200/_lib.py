@@ -68,7 +68,7 @@ class NaSurfaceOut(C.Structure):
 
 class NaTrainCfg(C.Structure):
     _fields_ = [('points_per_ray', C.c_int32), ('w_eikonal', C.c_float), ('eikonal_count', C.c_int32), ('white_bkgd', C.c_int32),
-                ('speed_factor', C.c_float), ('train_surface', C.c_int32), ('train_radiance', C.c_int32), ('reserved', C.c_int32)]
+                ('speed_factor', C.c_float), ('train_surface', C.c_int32), ('train_radiance', C.c_int32), ('precision', C.c_int32)]
 
 
 class NaRawGrads(C.Structure):

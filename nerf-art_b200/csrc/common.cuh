@@ -117,6 +117,17 @@ struct EvalJob {
     int   want_full;                                 // 0: SDF only; 1: + nablas (+ radiance if rad != nullptr)
     int   multires_view;
     long long* dbg;                                  // optional cycle counters (na_debug_set_buffer), else nullptr
+    // activation stash for the backward pass (csrc/train.cu; tensor-core modes, want_full == 1): sample-major fp32 planes
+    // [plane][st_mpad][256] indexed by the launch's flat sample number; nullptr = not written
+    float* st_wide;  size_t st_mpad;
+    float* st_small;                                 // [st_mpad][40]: the small radiance inputs x | embed(view) | nabla
 };
+
+// planes of EvalJob::st_wide a forward launch fills (the backward kernels of csrc/train.cu add theirs; see the enum there)
+constexpr int ST_IN = 0;        // 0..7   h_i = output of SDF layer i (layer 3: [h_3 | emb])
+constexpr int ST_G = 16;        // 16..23 g_i = reverse-sweep value u_i * softplus'(z_i)
+constexpr int ST_FEAT = 32;     // geometry feature
+constexpr int ST_YS = 34;       // 34..37 outputs of radiance layers 0..3
+constexpr int ST_S = 42;        // 42..49 softplus'(z_i)
 
 }  // namespace na

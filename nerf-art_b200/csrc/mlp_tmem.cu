@@ -176,6 +176,8 @@ struct EpiCtx {
     unsigned t_lane; int r, cq, g; float us; int sdim;
     unsigned bias_s, w8_s, w4_s, radw_s, kb_bar, d_bar;
     int signal, need_lo, lane;
+    float* st_row;                  // ST: st_wide + (flat sample) * 256 of this thread's row, nullptr for padding rows
+    size_t st_plane;                // ST: floats per plane
     unsigned d_phase; long long* t_wait; long long* trace;
 };
 
@@ -249,8 +251,16 @@ __device__ __forceinline__ void emb_range(const float (&xs)[3], float (&e)[16]) 
     }
 }
 
+// ST: 16 consecutive columns of this thread's row -> stash plane `plane` (values are stored x `scale`)
+__device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, const float (&o)[16], float scale) {
+    if (!c.st_row) return;
+    float4* dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + col0);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(o[4 * j4] * scale, o[4 * j4 + 1] * scale, o[4 * j4 + 2] * scale, o[4 * j4 + 3] * scale);
+}
+
 // one GEMM's epilogue for this thread's row and its 64 columns (4 passes of 16)
-template <int KIND, bool FULL>
+template <int KIND, bool FULL, bool ST>
 __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, float& sdf_part, float (&rgb_part)[3], const float (&small_in)[36]) {
     Smem& S = *c.S;
     const int r = c.r;
@@ -346,6 +356,17 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     for (int j = 0; j < 16; ++j) if (e0 + j >= 0) o[j] = e[j];
                 }
             }
+            if (ST) {
+                stash16(c, ST_IN + c.g, col0, o, 1.f / ACT_SCALE);
+                float sv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float ru = rcp_approx(1.f + t[j]);
+                    sv[j] = z16[j] >= 0.f ? ru : 1.f - ru;
+                    if (KIND == K_FWD3 && col0 + j >= SKIP_H) sv[j] = 0.f;
+                }
+                stash16(c, ST_S + c.g, col0, sv, 1.f);
+            }
             if (KIND == K_FWD7) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -361,6 +382,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 const float4 f4 = make_float4(fmaf(acc[4 * j4], us, b4.x), fmaf(acc[4 * j4 + 1], us, b4.y),
                                               fmaf(acc[4 * j4 + 2], us, b4.z), fmaf(acc[4 * j4 + 3], us, b4.w));
                 if (FULL) c.featp[(size_t)((col0 >> 2) + j4) * TM + r] = f4;
+                if (ST && c.st_row) reinterpret_cast<float4*>(c.st_row + (size_t)ST_FEAT * c.st_plane + col0)[j4] = f4;
                 if (c.job->feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(c.job->feat + S.OIDX[r] * 256 + col0) + j4) = f4;
                 if (FULL) {
                     // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
@@ -371,6 +393,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + 2] = w4.z * d4[2] * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4[3] * ACT_SCALE;
                 }
             }
+            if (ST && FULL) stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE);
         } else if (KIND == K_BWD || KIND == K_BWD4) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -383,6 +406,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
                 }
             }
+            if (ST) stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE);
         } else if (KIND == K_BWD0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[k * TM + r] += acc[j] * us; }
@@ -415,6 +439,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[4 * j4 + i] = fmaxf(z[i], 0.f);
             }
+            if (ST) stash16(c, ST_YS + c.g - 17, col0, o, 1.f / ACT_SCALE);
             if (KIND == K_RAD3) {
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc)
@@ -440,7 +465,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     if (N_PASS < 4) tc_fence_after();
 }
 
-template <bool FULL>
+template <bool FULL, bool ST>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
                 const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch) {
@@ -588,7 +613,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
         c.d_phase = 0;
         long long t_d = 0, t_e0 = clock64();
-        c.t_wait = &t_d; c.trace = nullptr;
+        c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
         const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -618,6 +643,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         oidx = ray * job.o_stride + job.o_off + j;
                     }
                 }
+                c.st_row = (ST && w < total) ? job.st_wide + (size_t)w * 256 : nullptr;
                 if (cq == 0) {
                     S.OIDX[r] = oidx;
                     S.X[r] = x0; S.X[TM + r] = x1; S.X[2 * TM + r] = x2;
@@ -646,18 +672,18 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 const unsigned t_dd = c.t_lane + (unsigned)((g + 1) & 1) * 256u;       // D of this GEMM == A of the next
                 // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
                 if (g < 8) {
-                    if (g == 3) epi_gemm<K_FWD3, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
-                    else if (g == 7) epi_gemm<K_FWD7, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
-                    else epi_gemm<K_FWD, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                    if (g == 3) epi_gemm<K_FWD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    else if (g == 7) epi_gemm<K_FWD7, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    else epi_gemm<K_FWD, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                 } else if (g == 8) {
-                    epi_gemm<K_FEAT, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                    epi_gemm<K_FEAT, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                 } else if (FULL) {
                     if (g <= 15) {
-                        if (g == 12) epi_gemm<K_BWD4, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
-                        else epi_gemm<K_BWD, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                        if (g == 12) epi_gemm<K_BWD4, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        else epi_gemm<K_BWD, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 16) {
                         epi_bar_sync();                                   // embedding-branch gradients (written at g == 12 by other threads)
-                        epi_gemm<K_BWD0, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                        epi_gemm<K_BWD0, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 17) {
                         // small radiance inputs [x | embed(view) | nabla] (x16), kept in registers: every thread rebuilds its row's
                         const float xs[3] = {S.X[r], S.X[TM + r], S.X[2 * TM + r]}, vs[3] = {S.V[r], S.V[TM + r], S.V[2 * TM + r]};
@@ -680,11 +706,18 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) small_in[30 + cc] = nb[cc] * ACT_SCALE;
                         }
-                        epi_gemm<K_RAD0, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                        if (ST && cq == 0 && c.st_row && job.st_small) {
+                            float* srow = job.st_small + (size_t)((c.st_row - job.st_wide) >> 8) * 40;
+#pragma unroll
+                            for (int j = 0; j < 36; ++j) srow[j] = small_in[j] * (1.f / ACT_SCALE);
+#pragma unroll
+                            for (int j = 36; j < 40; ++j) srow[j] = 0.f;
+                        }
+                        epi_gemm<K_RAD0, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 20) {
-                        epi_gemm<K_RAD3, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                        epi_gemm<K_RAD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else {
-                        epi_gemm<K_RAD, FULL>(c, t_dd, sdf_part, rgb_part, small_in);
+                        epi_gemm<K_RAD, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     }
                 }
                 c.d_phase ^= 1;
@@ -860,8 +893,9 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     static const char* prods_env = getenv("NA_TM_PRODS");
     const size_t smem = sizeof(Smem) + 1024;
     if (!attr_set) {
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_set = true;
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
@@ -882,8 +916,10 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
     if (scratch_bytes < mlp_tmem_scratch_bytes(grid)) return NA_ERR_WORKSPACE;
     const float* usc = (const float*)(image + T.unscale_off);
-    if (job.want_full) mlp_tmem_kernel<true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
-    else               mlp_tmem_kernel<false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    if (job.st_wide && !job.want_full) return NA_ERR_BAD_ARG;
+    if (job.st_wide)        mlp_tmem_kernel<true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    else if (job.want_full) mlp_tmem_kernel<true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    else                    mlp_tmem_kernel<false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
     NA_CHECK_LAUNCH();
     return NA_OK;
 }

@@ -31,8 +31,10 @@ enum {
     PL_FB = 33,     // dL/d feature
     PL_YS = 34,     // ys_1..4: outputs of radiance layers 0..3                                                    planes 34..37
     PL_D = 38,      // delta_0..3: dL/d(pre-activation) of radiance layers 0..3                                    planes 38..41
-    N_WIDE = 42
+    PL_S = 42,      // softplus'(z_0..7), written by the tcgen05 forward launch of the patch (loaded mode)          planes 42..49
+    N_WIDE = 50
 };
+static_assert(PL_IN == ST_IN && PL_G == ST_G && PL_FEAT == ST_FEAT && PL_YS == ST_YS && PL_S == ST_S, "stash plane numbering (common.cuh)");
 constexpr int NLD = 40;     // row stride of the narrow planes EMB, VB0, SMALL
 enum { NP_EMB = 0, NP_VB0 = 1, NP_SMALL = 2 };
 struct Stash {
@@ -54,6 +56,8 @@ struct BwdJob {
     int apply_bg; float bound_r;
     int has_rad;                                    // 0: NeuS pass A (sdf + nabla only)
     int multires_view;
+    // loaded mode: raw sdf [n_rows*P] and radiance [n_rows*P,3] of the forward launch that filled the IN / S / G / FEAT / YS planes
+    const float* f_sdf; const float* f_rad;
 };
 
 struct __align__(16) TrainSmem {
@@ -184,7 +188,7 @@ __device__ __forceinline__ void st2(float* __restrict__ plane, int row, int col,
     *reinterpret_cast<float2*>(plane + (size_t)row * 256 + col) = make_float2(a, b);
 }
 
-template <bool TF32>
+template <bool TF32, bool LOADED>
 __global__ void __launch_bounds__(NT, 1)
 mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, const float* __restrict__ tp, const PackTrain T,
                const Stash st, float* __restrict__ scratch) {
@@ -204,6 +208,8 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TM;
         auto WP = [&](int p) { return st.w(p) + row0 * 256; };
+        // softplus' of SDF layer i as a [TM][256] tile: the forward launch's stash plane (loaded mode) or this CTA's scratch
+        auto SPL = [&](int layer) -> float* { return LOADED ? WP(PL_S + layer) : SP + layer * 256 * TM; };
         // ---- 0. points, upstream gradients, positional encoding ---------------------------------------------------
         if (tid < TM) {
             const int m = tid;
@@ -244,6 +250,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
             }
             S.A[a_index(TAIL0 + 39, m)] = 0.f; emb_row[39] = 0.f;
         }
+        if constexpr (!LOADED) {
         // ---- 1. SDF forward, layers 0..7: h_i -> A and IN_{i+1}; softplus' -> SP_i -------------------------------------
         for (int layer = 0; layer < N_SDF_HID; ++layer) {
             if (layer == 0) gemm_tile<4>(acc, pk + L.sdf_wt[0], EMB_PAD, TAIL0, S.A, S.Ws, tid);
@@ -278,13 +285,18 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
                 st_frag4(inp, ty, tx, j, acc);
             }
         }
+                }
         __syncthreads();
         // ---- 2. sdf head, sphere-background mask of the upstream gradient (volsdf.py:349-357) ---------------------------
-        narrow_layer<1>(S.A, pk + L.w8_sdf, S.RED, tid);
-        __syncthreads();
+        if constexpr (!LOADED) {
+            narrow_layer<1>(S.A, pk + L.w8_sdf, S.RED, tid);
+            __syncthreads();
+        }
         if (tid < TM) {
             const int m = tid;
-            const float sdf = S.RED[m] + S.RED[3 * TM + m] + __ldg(pk + L.b8_sdf);
+            float sdf;
+            if constexpr (LOADED) { const long long w = tile * TM + m; sdf = w < total ? job.f_sdf[w] : 0.f; }
+            else sdf = S.RED[m] + S.RED[3 * TM + m] + __ldg(pk + L.b8_sdf);
             float gs = Q.GSDF[m];
             if (job.apply_bg) {
                 const float x0 = S.X[m], x1 = S.X[TM + m], x2 = S.X[2 * TM + m];
@@ -294,6 +306,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
             Q.GS[m] = gs;
             *reinterpret_cast<float4*>(st.t(1) + (row0 + m) * 4) = make_float4(gs, 0.f, 0.f, 0.f);
         }
+        if constexpr (!LOADED) {
         // ---- 3. geometry feature -> FEAT plane -------------------------------------------------------------------------
         if (job.has_rad) {
             gemm_tile<4>(acc, pk + L.w8t_feat, W, 0, S.A, S.Ws, tid);
@@ -358,6 +371,8 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
             }
         }
         __syncthreads();
+        }
+        if constexpr (!LOADED) {
         // ---- 5. nabla; radiance forward ---------------------------------------------------------------------------------
         if (tid < TM) {
             const int m = tid;
@@ -400,7 +415,34 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
                 while (q < NLD) { if (q < spad) S.A[a_index(TAIL0 + q, m)] = 0.f; srow[q] = 0.f; ++q; }
             }
         }
+        }
         if (job.has_rad) {
+            if constexpr (LOADED) {
+                // ys_4 (radiance layer 3 output, for the ReLU mask of delta_3) -> A; delta_4 from the forward launch's rgb
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 yv[8];
+                    ld_frag4(WP(PL_YS + 3), ty, tx, j, yv);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i][4 * j + c] = f4c(yv[i], c);
+                    st_A4(S.A, ty, tx, j, acc);
+                }
+                if (tid < TM) {
+                    const int m = tid;
+                    const long long w = tile * TM + m;
+                    float d4[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float rgb = w < total ? job.f_rad[w * 3 + c] : 0.f;
+                        d4[c] = Q.GRAD[c * TM + m] * rgb * (1.f - rgb);
+                        Q.D4[c * TM + m] = d4[c];
+                    }
+                    *reinterpret_cast<float4*>(st.t(0) + (row0 + m) * 4) = make_float4(d4[0], d4[1], d4[2], 0.f);
+                }
+                __syncthreads();
+            } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float4 fv[8];
@@ -441,6 +483,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
                 *reinterpret_cast<float4*>(st.t(0) + (row0 + m) * 4) = make_float4(d4[0], d4[1], d4[2], 0.f);
             }
             __syncthreads();
+            }
             // ---- 6. radiance backward: delta_3 from the output layer, then layers 3..1, then the layer-0 inputs ---------
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -535,7 +578,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
         if constexpr (TF32) {
             for (int layer = 0; layer < N_SDF_HID; ++layer) {
                 gemm_tile_tf32(acc2, tp + T.sdf_wt_r[layer], layer == 0 ? EMB_PAD : W, layer == 0 ? TAIL0 : 0, S.A, S.Ws, tid);
-                const float* spp = SP + layer * 256 * TM; float* qp = QP + layer * 256 * TM;
+                const float* spp = SPL(layer); float* qp = QP + layer * 256 * TM;
                 const float* gp_ = WP(PL_G + layer); float* vbp = WP(PL_VB + layer);
                 mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) {
                     const float2 s2 = ld2(spp, row, col), g2 = ld2(gp_, row, col);
@@ -557,7 +600,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
     #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 sv[8], gv[8];
-                    ld_frag4(SP + layer * 256 * TM, ty, tx, j, sv);
+                    ld_frag4(SPL(layer), ty, tx, j, sv);
                     ld_frag4(WP(PL_G + layer), ty, tx, j, gv);
     #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -594,7 +637,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
             }
             for (int layer = 8; layer >= 1; --layer) {
                 if (layer < 8) gemm_tile_tf32(acc2, tp + T.sdf_w_r[layer], W, 0, S.A, S.Ws, tid); // h-bar_{layer-1}
-                const float* spp = SP + (layer - 1) * 256 * TM; const float* qp = QP + (layer - 1) * 256 * TM;
+                const float* spp = SPL(layer - 1); const float* qp = QP + (layer - 1) * 256 * TM;
                 float* zbp = WP(PL_ZB + layer - 1);
                 mma_each(acc2, tid, [&](int row, int col, float& v0, float& v1) {
                     const float2 s2 = ld2(spp, row, col), q2 = ld2(qp, row, col);
@@ -631,7 +674,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
     #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 sv[8], qv[8];
-                    ld_frag4(SP + (layer - 1) * 256 * TM, ty, tx, j, sv);
+                    ld_frag4(SPL(layer - 1), ty, tx, j, sv);
                     ld_frag4(QP + (layer - 1) * 256 * TM, ty, tx, j, qv);
     #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -1084,8 +1127,11 @@ __global__ void normalize_dirs_train_kernel(const float* __restrict__ d, float* 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 struct TrainWs {
     float* dirs; float* g_sdf; float* g_nab; float* g_rad; float* stash; float* scratch;
+    float* f_sdf; float* f_rad; float* fwd_scratch; size_t fwd_scratch_bytes;       // loaded mode: outputs / scratch of the forward launch
     size_t total;
 };
+size_t mlp_scratch_bytes();                                                         // csrc/api.cu
+int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream);
 static TrainWs train_ws(void* base, long long n_rays, int P) {
     const size_t M = (size_t)n_rays * P, mpad = (M + TM - 1) / TM * TM;
     unsigned char* p = (unsigned char*)base; size_t o = 0;
@@ -1095,26 +1141,53 @@ static TrainWs train_ws(void* base, long long n_rays, int P) {
     w.g_sdf = take(M * 4); w.g_nab = take(M * 12); w.g_rad = take(M * 12);
     w.stash = take(stash_floats(mpad) * 4);
     w.scratch = take((size_t)num_sms() * 16 * 256 * TM * 4);
+    w.f_sdf = take(M * 4); w.f_rad = take(M * 12);
+    w.fwd_scratch_bytes = mlp_scratch_bytes(); w.fwd_scratch = take(w.fwd_scratch_bytes);
     w.total = o;
     return w;
 }
 
-static int launch_mlp_bwd(const BwdJob& job, const float* pk, const PackF32& L, const float* tp, const PackTrain& T, const Stash& st,
-                          float* scratch, cudaStream_t stream) {
+// NA_BWD=fp32: all-fp32 backward GEMMs.  cfg.precision == NA_PRECISION_FP32 (or NA_BWD_RECOMPUTE=1): the backward kernel recomputes
+// the forward pass of every tile on the fp32 FMA pipe (the first version); tensor-core modes: the tcgen05 forward kernel (csrc/mlp_tmem.cu, stash-out mode) re-evaluates the
+// patch once and leaves h_i, softplus'(z_i), g_i, the feature and the radiance activations in the stash planes the backward and
+// weight-gradient kernels read ("loaded mode").
+static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision, const float* pk, const PackF32& L, const float* tp,
+                          const PackTrain& T, const Stash& st, const TrainWs& w, cudaStream_t stream) {
     static thread_local bool attr_set = false;
     static const bool fp32_bwd = [] { const char* e = getenv("NA_BWD"); return e && strcmp(e, "fp32") == 0; }();
+    static const bool force_recompute = [] { const char* e = getenv("NA_BWD_RECOMPUTE"); return e && e[0] == '1'; }();
+    const bool recompute = force_recompute || precision == NA_PRECISION_FP32;
+    const int fwd_precision = precision == NA_PRECISION_TC_MIXED ? NA_PRECISION_TC : precision;    // softplus' needs the 3-product forward
     const size_t smem = sizeof(TrainSmem);
     if (!attr_set) {
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_set = true;
     }
+    BwdJob job = job_;
     const long long total = (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;
     const long long tiles = (total + TM - 1) / TM;
     const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
-    if (fp32_bwd) mlp_bwd_kernel<false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, scratch);
-    else          mlp_bwd_kernel<true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, scratch);
+    if (!recompute) {
+        EvalJob e = {};
+        e.rays_o = job.rays_o; e.rays_d = job.rays_d; e.n_rows = job.n_rows; e.P = job.P;
+        e.t = job.t; e.t_stride = job.t_stride; e.t_off = 0; e.midpoints = job.midpoints;
+        e.o_stride = job.P; e.o_off = 0;
+        e.sdf = w.f_sdf; e.rad = job.has_rad ? w.f_rad : nullptr;
+        e.apply_bg = 0;                                   // raw network sdf: the background mask below compares it with R - |x| itself
+        e.bound_r = job.bound_r; e.want_full = 1; e.multires_view = job.multires_view;
+        e.st_wide = st.wide; e.st_mpad = st.mpad; e.st_small = st.n(NP_SMALL);
+        NA_TRY(launch_mlp(e, packed, fwd_precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream));
+        job.f_sdf = w.f_sdf; job.f_rad = w.f_rad;
+        if (fp32_bwd) mlp_bwd_kernel<false, true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
+        else          mlp_bwd_kernel<true, true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
+    } else {
+        if (fp32_bwd) mlp_bwd_kernel<false, false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
+        else          mlp_bwd_kernel<true, false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
+    }
     NA_CHECK_LAUNCH();
     return NA_OK;
 }
@@ -1208,25 +1281,25 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     NA_CHECK_LAUNCH();
     const size_t M = (size_t)n * P, mpad = (M + TM - 1) / TM * TM;
     Stash st; st.mpad = mpad; st.wide = w.stash; st.narrow = w.stash + (size_t)N_WIDE * mpad * 256; st.tiny = st.narrow + 3 * mpad * NLD;
-    BwdJob job;
+    BwdJob job = {};
     job.rays_o = rays_o; job.rays_d = w.dirs; job.n_rows = (int)n; job.t = d_all; job.t_stride = P;
     job.multires_view = desc->multires_view; job.bound_r = desc->bounding_radius;
     const bool has_eik = cfg->w_eikonal != 0.f;
     if (!neus) {
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = w.g_rad;
         job.apply_bg = 1; job.has_rad = 1;
-        NA_TRY(launch_mlp_bwd(job, pk, L, tp, T, st, w.scratch, stream));
+        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
         NA_TRY(launch_wgrad(st, (long long)M, 1, cfg->train_surface, cfg->train_radiance, gp, stream));
     } else {
         // pass A: the P points of d_all (sdf -> alpha, nabla -> eikonal); pass B: the P-1 midpoints (radiance), neus.py:320-324
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = nullptr;
         job.apply_bg = 0; job.has_rad = 0;
         if (cfg->train_surface) {
-            NA_TRY(launch_mlp_bwd(job, pk, L, tp, T, st, w.scratch, stream));
+            NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
             NA_TRY(launch_wgrad(st, (long long)M, 0, 1, 0, gp, stream));
         }
         job.P = P - 1; job.midpoints = 1; job.g_sdf = nullptr; job.g_nab = nullptr; job.g_rad = w.g_rad; job.has_rad = 1;
-        NA_TRY(launch_mlp_bwd(job, pk, L, tp, T, st, w.scratch, stream));
+        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
         NA_TRY(launch_wgrad(st, (long long)n * (P - 1), 1, cfg->train_surface, cfg->train_radiance, gp, stream));
     }
     return NA_OK;

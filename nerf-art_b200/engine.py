@@ -211,7 +211,7 @@ class NetEngine:
         d_all = fwd['d_all'] if neus else fwd['d_vals']
         P = d_all.shape[-1]
         cfg = NaTrainCfg(int(P), float(w_eikonal), int(eikonal_count), int(bool(white_bkgd)), float(speed_factor),
-                         int(bool(train_surface)), int(bool(train_radiance)), 0)
+                         int(bool(train_surface)), int(bool(train_radiance)), PRECISIONS[self.precision])
         nbytes = L.na_train_workspace_bytes(C.byref(self.desc), n, P)
         if getattr(self, '_tws', None) is None or self._tws.device != dev or self._tws.numel() < nbytes:
             self._tws = None

@@ -26,6 +26,28 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 REL_TOL = 1e-2
 L2_TOL = 5e-3
+# tensor-core modes ("loaded" backward: the activations come from the tcgen05 forward kernel, whose pre-activations carry the
+# 1.5e-5 error of split-fp16 operands + truncating fp32 accumulation).  softplus' = sigmoid(100 z) amplifies it 25x and the
+# second-order (eikonal) term 100 g-bar g (1 - s) another 100x, so the eikonal-on cases land at 0.5-2.3 % (Linf) / 0.4-0.8 %
+# (L2) on the most sensitive tensors (measured on B200: SDF layer 7 bias, radiance layer 0 bias); without the eikonal term and
+# for NeuS the tensor-core mode is as close as fp32 (5e-4 / 1e-3).  fp32 mode keeps the all-fp32 recompute and the tight bound.
+TOL = {'fp32': (REL_TOL, L2_TOL), 'tc': (3e-2, 1.2e-2)}
+
+
+def worst_errors(grads, g):
+    """(worst Linf / max|ref|, worst relative L2, its tensor) over the tensors the golden file holds in full"""
+    worst = (0.0, 0.0, '')
+    for k, v in grads.items():
+        if 'grad.' + k not in g:
+            continue
+        ref = g['grad.' + k]; a = np.asarray(v).reshape(ref.shape)
+        li = float(np.abs(a - ref).max() / (np.abs(ref).max() + 1e-30))
+        l2 = float(np.linalg.norm((a - ref).ravel()) / (np.linalg.norm(ref.ravel()) + 1e-30))
+        if l2 > worst[1]:
+            worst = (max(li, worst[0]), l2, k)
+        else:
+            worst = (max(li, worst[0]), worst[1], worst[2])
+    return worst
 
 
 def t(a):
@@ -84,29 +106,33 @@ def product_grads(m, framework, ro, rd, fwd, G, w_eik, white, train_radiance=Tru
     return grads, scal_out.cpu().numpy()
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
 @pytest.mark.parametrize('name', ['train_volsdf_b0.1', 'train_volsdf_b0.01_white', 'train_volsdf_noeik'])
-def test_volsdf_backward_matches_reference_autograd(name):
+def test_volsdf_backward_matches_reference_autograd(name, precision):
     g = golden(name)
     m = make_volsdf(float(g['beta_init']), float(g['bump']), device=DEV)
-    m.engine().precision = 'fp32'
+    m.engine().precision = precision
     ro, rd = t(g['rays_o']), t(g['rays_d'])
     fwd = volsdf_fwd_at(m, ro, rd, t(g['d_vals']))
     grads, scal = product_grads(m, 'volsdf', ro, rd, fwd, t(g['G']), float(g['w_eikonal']), bool(g['white_bkgd']))
     grads['ln_beta'] = np.array([scal[0]], np.float32)
-    assert compare_grads(grads, g, REL_TOL, L2_TOL) == 9 * 3 + 5 * 3 + 1
+    print(name, precision, 'worst (Linf, L2, tensor) vs reference autograd:', worst_errors(grads, g))
+    assert compare_grads(grads, g, *TOL[precision]) == 9 * 3 + 5 * 3 + 1
     assert abs(scal[1] - float(g['eikonal_loss'])) <= 1e-5 + 1e-4 * float(g['eikonal_loss'])
     print(name, 'ln_beta grad', scal[0], float(g['grad.ln_beta'][0]), 'eik', scal[1], float(g['eikonal_loss']))
 
 
-def test_neus_backward_matches_reference_autograd():
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_neus_backward_matches_reference_autograd(precision):
     g = golden('train_neus')
     m = make_neus(float(g['variance_init']), float(g['bump']), device=DEV)
-    m.engine().precision = 'fp32'
+    m.engine().precision = precision
     ro, rd = t(g['rays_o']), t(g['rays_d'])
     fwd = neus_fwd_at(m, ro, rd, t(g['d_all']))
     grads, scal = product_grads(m, 'neus', ro, rd, fwd, t(g['G']), float(g['w_eikonal']), False, train_radiance=False)
     grads['ln_s'] = np.array([scal[0]], np.float32)
-    assert compare_grads(grads, g, REL_TOL, L2_TOL) == 9 * 3 + 1
+    print('neus', precision, 'worst (Linf, L2, tensor) vs reference autograd:', worst_errors(grads, g))
+    assert compare_grads(grads, g, *TOL[precision]) == 9 * 3 + 1
     assert abs(scal[1] - float(g['eikonal_loss'])) <= 1e-5 + 1e-4 * float(g['eikonal_loss'])
 
 
@@ -137,9 +163,9 @@ def test_volsdf_backward_vs_oracle_many_tiles(precision):
     og, oeik, orgb = ot.volsdf_backward(net, ro.cpu().numpy(), rd.cpu().numpy(), fwd['d_vals'].cpu().numpy(), G.cpu().numpy(), 0.1, False)
     worst = max(rel_err(grads[k], np.asarray(og[k]).reshape(grads[k].shape)) for k in grads)
     worst2 = max(l2_err(grads[k], np.asarray(og[k]).reshape(grads[k].shape)) for k in grads)
-    assert worst2 < L2_TOL, worst2
     print(precision, 'worst relative gradient error vs oracle (Linf, L2)', worst, worst2, 'ln_beta', scal[0], float(og['ln_beta'][0]), 'eik', scal[1], oeik)
-    assert worst < REL_TOL
+    assert worst2 < TOL[precision][1], worst2
+    assert worst < TOL[precision][0]
     assert abs(scal[0] - float(og['ln_beta'][0])) <= 2e-3 * abs(float(og['ln_beta'][0])) + 1e-6
     assert abs(scal[1] - oeik) <= 1e-4 * oeik + 1e-6
     assert np.abs(fwd['rgb'].cpu().numpy() - orgb).max() < (1e-4 if precision == 'fp32' else 1e-3)
