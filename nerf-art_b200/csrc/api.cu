@@ -32,7 +32,8 @@ int launch_mlp_tc(const EvalJob& job, const unsigned char* packed_base, size_t f
 size_t mlp_tc_scratch_bytes(int grid);
 extern long long* g_tc_dbg;
 size_t mlp_tmem_image_bytes();
-int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, const float* d_absmax, unsigned char* image, cudaStream_t stream);
+int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, const float* d_absmax, size_t train_off, const PackTrain& TP,
+              unsigned char* image, cudaStream_t stream);
 int launch_mlp_tmem(const EvalJob& job, const float* pk_f32, const unsigned char* image, const PackF32& L, int mixed,
                     unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t mlp_tmem_scratch_bytes(int grid);
@@ -216,6 +217,7 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
     // second image (TMEM-resident kernel: 256-row stages) from the same planes / per-plane scales (tables left by tc_pack)
     unsigned char* meta = (unsigned char*)packed_ + T.meta_off;
     return tmem_pack(packed, (const size_t*)meta, (const int*)(meta + 256), (const float*)(meta + 1280),
+                     train_pack_off(desc->multires_view) / sizeof(float), pack_layout_train(),
                      (unsigned char*)packed_ + tmem_image_off(desc->multires_view), stream);
 }
 

@@ -121,6 +121,12 @@ struct EvalJob {
     // [plane][st_mpad][256] indexed by the launch's flat sample number; nullptr = not written
     float* st_wide;  size_t st_mpad;
     float* st_small;                                 // [st_mpad][40]: the small radiance inputs x | embed(view) | nabla
+    // backward in the same launch (csrc/mlp_tmem.cu, BW program; needs the stash): upstream gradients per sample (nullable = 0),
+    // the remaining stash planes, and the sphere-background mask of d L / d sdf (volsdf.py:349-357)
+    int bw;  int bw_bg_mask;
+    const float* bw_gsdf;  const float* bw_gnab;  const float* bw_grad;
+    float* st_emb;  float* st_vb0;                   // [st_mpad][40]: encoding, v-bar_0
+    float* st_t0;  float* st_t1;                     // [st_mpad][4]: delta of the radiance output layer; masked d L / d sdf
 };
 
 // planes of EvalJob::st_wide a forward launch fills (the backward kernels of csrc/train.cu add theirs; see the enum there)
@@ -129,5 +135,10 @@ constexpr int ST_G = 16;        // 16..23 g_i = reverse-sweep value u_i * softpl
 constexpr int ST_FEAT = 32;     // geometry feature
 constexpr int ST_YS = 34;       // 34..37 outputs of radiance layers 0..3
 constexpr int ST_S = 42;        // 42..49 softplus'(z_i)
+// ... and the planes the backward program adds (same numbering as the enum in csrc/train.cu)
+constexpr int ST_ZB = 8;        // 8..15  z-bar_i
+constexpr int ST_VB = 24;       // 24..31 v-bar_{i+1}
+constexpr int ST_FB = 33;       // d L / d feature
+constexpr int ST_D = 38;        // 38..41 delta_0..3 of the radiance hidden layers
 
 }  // namespace na

@@ -39,8 +39,12 @@ constexpr int NS = NA_TM_NS;                     // weight stages (32 KB each); 
 constexpr bool STASH = NS <= 5;
 constexpr int STAGE_BYTES = 32768;               // 256 rows x 64 fp16
 constexpr float ACT_SCALE = 16.f;                // activations are stored x16 (keeps the lo term normal in fp16)
-constexpr int MAX_GEMM = 24;
-constexpr int N_PLANES = 21;                     // program: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
+constexpr int MAX_GEMM = 44;
+constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 feat | 9..15 reverse 7..1 | 16 reverse 0 | 17..20 radiance |
+                                                 //                21..24 radiance backward (layers 3,2,1, 0-feature columns) | 25 head backward
+// forward program = images 0..20 in order.  BW program (forward + backward of a training patch, 41 GEMMs) appends:
+//   21..23 delta_{2,1,0} = (delta_{3,2,1} R_{3,2,1}) * relu'   | 24 feat-bar = delta_0 R_0[:, feature]   | 25 h-bar_7 = feat-bar W8[1:]
+//   26..33 second-order sweep g-bar_i = v-bar_i W_i^T (images 0..7) | 34..40 trunk h-bar_{i-1} = z-bar_i W_i, i = 7..1 (images 9..15)
 
 // NA_TM_TRACE (diagnostic build): CTA 0 records clock64() stamps of its second tile into job.dbg[16..]:
 //   MMA lane:      slot (g*4+kb)*2 + {0: K-block of A ready, 1: its MMAs issued}
@@ -53,7 +57,8 @@ constexpr int N_PLANES = 21;                     // program: 0..7 fwd | 8 feat |
 #define NA_TRACE_E(tr, g, ps, w) do { } while (0)
 #endif
 
-struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, pad; };
+enum BwOp { OP_FWD = 0, OP_DR, OP_FB, OP_HB, OP_SO, OP_TR };      // OP_FWD: forward program, dispatched on the program index
+struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, img, op, lyr, pad0, pad1; };   // img: weight image (unscale index)
 struct Program { int n_gemm; int nsplit; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
 
 // ------------------------------------------------------------------------------------------------
@@ -160,6 +165,8 @@ struct __align__(1024) Smem {
     // STASH: the tile's encoding (x ACT_SCALE; entry k of row r at k*TM + r), reused by the skip connection (layer 3) and the
     // closed-form nabla instead of re-evaluating sincosf; and the 9 small-input rows of radiance layer 0 (VolSDF: x | view | nabla)
     float EMBS[STASH ? EMB * TM : 1];
+    float BWV[8 * TM];                                 // BW: per row 0..2 d L/d nabla (eikonal) x rs | 3..5 d L/d radiance x rs, then delta_4 x rs | 6 masked d L/d sdf x rs
+    unsigned long long MASK[EPI_THREADS];              // BW: ReLU masks of radiance layer 3
     __align__(16) float RADW[STASH ? 9 * 256 : 4];
 };
 
@@ -169,7 +176,8 @@ constexpr size_t FEAT_BYTES = (size_t)64 * TM * 16;           // float4 at k4*12
 constexpr size_t MISC_BYTES = (size_t)80 * TM * 4;            // float at j*128 + r : d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
 constexpr size_t SCRATCH_BYTES = DH_BYTES + FEAT_BYTES + MISC_BYTES;
 
-enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_RAD, K_RAD3 };
+enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_RAD, K_RAD3,
+               K_DR, K_DR0, K_FB, K_HB, K_SO, K_SO3, K_SO7, K_TR };      // BW program only
 
 struct EpiCtx {
     Smem* S; uint2* dh; float4* featp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
@@ -178,6 +186,11 @@ struct EpiCtx {
     int signal, need_lo, lane;
     float* st_row;                  // ST: st_wide + (flat sample) * 256 of this thread's row, nullptr for padding rows
     size_t st_plane;                // ST: floats per plane
+    // BW: per-row power-of-two scale of the upstream gradient (the backward is linear in it and rows are independent, so every
+    // backward quantity of the row is carried x rs in the fp16 operands and stored x irs) and the row's total d L / d nabla (x rs)
+    float rs, irs, nbar[3];
+    int lyr, has_rad;               // BW: layer index of the running backward GEMM; the program has the radiance part
+    unsigned long long* mask;       // BW: this thread's slot for the ReLU mask of radiance layer 3 (64 columns)
     unsigned d_phase; long long* t_wait; long long* trace;
 };
 
@@ -257,6 +270,28 @@ __device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, co
     float4* dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + col0);
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(o[4 * j4] * scale, o[4 * j4 + 1] * scale, o[4 * j4 + 2] * scale, o[4 * j4 + 3] * scale);
+}
+
+// BW: entry k of v-bar_0 = (d emb / d x)^T-contracted total d L / d nabla of row r (x rs): x_c -> n_c, sin(f x_c) -> f cos(f x_c) n_c,
+// cos(f x_c) -> -f sin(f x_c) n_c; sin / cos come from the tile's encoding stash (x ACT_SCALE)
+__device__ __forceinline__ float vbar0_entry(const Smem& S, int k, int r, const float (&nbar)[3]) {
+    if (k < 0 || k >= EMB) return 0.f;
+    if (k < 3) return k == 0 ? nbar[0] : (k == 1 ? nbar[1] : nbar[2]);
+    const int f = (k - 3) / 6, rem = (k - 3) % 6, cc = rem % 3;
+    const float nb = cc == 0 ? nbar[0] : (cc == 1 ? nbar[1] : nbar[2]), fr = (float)(1 << f);
+    return rem < 3 ?  nb * fr * S.EMBS[(k + 3) * TM + r] * (1.f / ACT_SCALE)
+                   : -nb * fr * S.EMBS[(k - 3) * TM + r] * (1.f / ACT_SCALE);
+}
+// BW: 16 consecutive columns of this thread's row from stash plane `plane` (zeros on padding rows)
+__device__ __forceinline__ void load16(const EpiCtx& c, int plane, int col0, float (&v)[16]) {
+    if (c.st_row) {
+        const float4* p = reinterpret_cast<const float4*>(c.st_row + (size_t)plane * c.st_plane + col0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) { const float4 q = p[j4]; v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
 }
 
 // one GEMM's epilogue for this thread's row and its 64 columns (4 passes of 16)
@@ -410,6 +445,87 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         } else if (KIND == K_BWD0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[k * TM + r] += acc[j] * us; }
+        } else if (KIND >= K_DR) {
+            // ---- backward program (BW): every value is carried x rs in the operands; stash planes receive x irs ----------------
+            if (KIND == K_DR || KIND == K_DR0) {
+                // delta_lyr = (delta_{lyr+1} R_{lyr+1}) * [ys_{lyr+1} > 0]   (radiance hidden layers, lyr = 2, 1, 0)
+                float y[16];
+                load16(c, ST_YS + c.lyr, col0, y);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = y[j] > 0.f ? acc[j] * us16 : 0.f;
+                stash16(c, ST_D + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
+                if (KIND == K_DR0) {
+                    // d L / d nabla through radiance layer 0: delta_0 . W0[:, nabla columns]  (partial over this thread's columns)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int srow = c.sdim - 3 + cc;
+                            const float4 w = (STASH && c.sdim == 9) ? lds128(c.radw_s + (unsigned)(srow * 256 + col0 + 4 * j4) * 4u)
+                                                                    : __ldg(reinterpret_cast<const float4*>(c.pk + c.L->rad_wt[0] + (size_t)(256 + srow) * 256 + col0) + j4);
+                            rgb_part[cc] = fmaf(o[4 * j4], w.x, rgb_part[cc]); rgb_part[cc] = fmaf(o[4 * j4 + 1], w.y, rgb_part[cc]);
+                            rgb_part[cc] = fmaf(o[4 * j4 + 2], w.z, rgb_part[cc]); rgb_part[cc] = fmaf(o[4 * j4 + 3], w.w, rgb_part[cc]);
+                        }
+                }
+            } else if (KIND == K_FB) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = acc[j] * us16;                       // d L / d feature
+                stash16(c, ST_FB, col0, o, c.irs * (1.f / ACT_SCALE));
+            } else if (KIND == K_HB) {
+                // feature part of h-bar_7, parked (x rs) in the z-bar_7 plane until the second-order sweep reaches layer 7
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = acc[j] * us;
+                stash16(c, ST_ZB + 7, col0, o, 1.f);
+            } else if (KIND == K_SO || KIND == K_SO3 || KIND == K_SO7) {
+                // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
+                float sv[16], gv[16], q[16];
+                load16(c, ST_S + c.lyr, col0, sv);
+                load16(c, ST_G + c.lyr, col0, gv);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float gb = acc[j] * us;
+                    q[j] = 100.f * gb * gv[j] * (1.f - sv[j]);
+                    o[j] = gb * sv[j];
+                }
+                if (KIND == K_SO3 && col0 + 15 >= SKIP_H) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (col0 + j >= SKIP_H) o[j] = vbar0_entry(S, col0 + j - SKIP_H, r, c.nbar);      // skip connection
+                }
+                stash16(c, ST_VB + c.lyr, col0, o, c.irs);
+                if (KIND == K_SO7) {
+                    // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]
+                    float hb[16];
+                    if (c.has_rad) load16(c, ST_ZB + 7, col0, hb);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) hb[j] = 0.f;
+                    }
+                    const float gs = S.BWV[6 * TM + r];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
+                        hb[4 * j4] = fmaf(gs, w4.x, hb[4 * j4]); hb[4 * j4 + 1] = fmaf(gs, w4.y, hb[4 * j4 + 1]);
+                        hb[4 * j4 + 2] = fmaf(gs, w4.z, hb[4 * j4 + 2]); hb[4 * j4 + 3] = fmaf(gs, w4.w, hb[4 * j4 + 3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = fmaf(hb[j], sv[j], q[j]);
+                    stash16(c, ST_ZB + 7, col0, o, c.irs);
+                } else {
+                    stash16(c, ST_ZB + c.lyr, col0, q, 1.f);                             // parked (x rs) until the trunk reaches this layer
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
+            } else {
+                // trunk, K_TR: z-bar_lyr = h-bar_lyr s_lyr + q_lyr
+                float sv[16], qv[16];
+                load16(c, ST_S + c.lyr, col0, sv);
+                load16(c, ST_ZB + c.lyr, col0, qv);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j] * us, sv[j], qv[j]);
+                stash16(c, ST_ZB + c.lyr, col0, o, c.irs);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
+            }
         } else {
             // radiance hidden layers: relu(16 z)
 #pragma unroll
@@ -440,6 +556,12 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 for (int i = 0; i < 4; ++i) o[4 * j4 + i] = fmaxf(z[i], 0.f);
             }
             if (ST) stash16(c, ST_YS + c.g - 17, col0, o, 1.f / ACT_SCALE);
+            if (ST && KIND == K_RAD3 && c.mask) {
+                unsigned long long m16 = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) m16 |= (unsigned long long)(o[j] > 0.f) << j;
+                *c.mask = (c16 == 0 ? 0ull : *c.mask) | (m16 << (16 * c16));
+            }
             if (KIND == K_RAD3) {
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc)
@@ -451,7 +573,8 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     }
             }
         }
-        const bool store = !(KIND == K_BWD0 || KIND == K_RAD3 || (KIND == K_FWD7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL));
+        const bool store = !(KIND == K_BWD0 || KIND == K_RAD3 || KIND == K_HB || (KIND == K_FWD7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL) ||
+                             (KIND >= K_DR && !c.signal));
         if (store) store_a16(t_d + col0, o, c.need_lo);
         NA_TRACE_E(c.trace, c.g, c16, 2);
         if (USES_DH && (c.lane & 15) == 0) {
@@ -465,7 +588,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     if (N_PASS < 4) tc_fence_after();
 }
 
-template <bool FULL, bool ST>
+template <bool FULL, bool ST, bool BW>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
                 const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch) {
@@ -614,6 +737,8 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.d_phase = 0;
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
+        c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = job.rad != nullptr;
+        c.mask = BW ? &S.MASK[tid - 64] : nullptr;
         const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -643,7 +768,8 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         oidx = ray * job.o_stride + job.o_off + j;
                     }
                 }
-                c.st_row = (ST && w < total) ? job.st_wide + (size_t)w * 256 : nullptr;
+                // padding rows of the last tile are written too (zero upstream gradient): the weight-gradient kernels read whole tiles
+                c.st_row = (ST && (size_t)w < job.st_mpad) ? job.st_wide + (size_t)w * 256 : nullptr;
                 if (cq == 0) {
                     S.OIDX[r] = oidx;
                     S.X[r] = x0; S.X[TM + r] = x1; S.X[2 * TM + r] = x2;
@@ -659,19 +785,78 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 #pragma unroll
                     for (int j = 0; j < 16; ++j) if (16 * cq + j < EMB) S.EMBS[(16 * cq + j) * TM + r] = e[j];
                 }
+                if (BW) {
+                    // upstream gradients of the row and its power-of-two scale rs: max(|.|) * rs in [1, 2)
+                    float gs = 0.f, gn[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f};
+                    if (w < total) {
+                        if (job.bw_gsdf) gs = job.bw_gsdf[w];
+                        if (job.bw_gnab) { gn[0] = job.bw_gnab[w * 3]; gn[1] = job.bw_gnab[w * 3 + 1]; gn[2] = job.bw_gnab[w * 3 + 2]; }
+                        if (job.bw_grad) { gr[0] = job.bw_grad[w * 3]; gr[1] = job.bw_grad[w * 3 + 1]; gr[2] = job.bw_grad[w * 3 + 2]; }
+                    }
+                    const float mx = fmaxf(fmaxf(fabsf(gs), fmaxf(fabsf(gn[0]), fmaxf(fabsf(gn[1]), fabsf(gn[2])))),
+                                           0.25f * fmaxf(fabsf(gr[0]), fmaxf(fabsf(gr[1]), fabsf(gr[2]))));
+                    int ex = 0;
+                    if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &ex);                       // mx = m * 2^ex, m in [0.5, 1)
+                    ex = max(-100, min(100, ex));
+                    c.rs = ldexpf(1.f, 1 - ex); c.irs = ldexpf(1.f, ex - 1);
+                    if (cq == 0) {
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) { S.BWV[cc * TM + r] = gn[cc] * c.rs; S.BWV[(3 + cc) * TM + r] = gr[cc] * c.rs; }
+                        S.BWV[6 * TM + r] = gs;                                          // masked and scaled at the sdf head (g == 7)
+                    }
+                    if (c.st_row && job.st_emb) {
+                        float* erow = job.st_emb + (size_t)w * 40;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (16 * cq + j < 40) erow[16 * cq + j] = e[j] * (1.f / ACT_SCALE);
+                    }
+                }
                 store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
             }
             for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
 
             float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
             float small_in[36];
+            // BW: A <- v-bar_0 (K-block 0 of the second-order sweep's first GEMM), over this thread's own (consumed) columns of the
+            // previous D; also the narrow v-bar_0 stash plane
+            auto write_vbar0 = [&](unsigned t_region) {
+                float e[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) e[j] = vbar0_entry(S, 16 * cq + j, r, c.nbar);
+                if (c.st_row && job.st_vb0) {
+                    float* vrow = job.st_vb0 + (size_t)((c.st_row - job.st_wide) >> 8) * 40;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (16 * cq + j < 40) vrow[16 * cq + j] = e[j] * c.irs;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) e[j] *= ACT_SCALE;
+                store_a16(t_region + (unsigned)(16 * cq), e, 0);
+                for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
+            };
             for (int g = 0; g < prog.n_gemm; ++g) {
-                c.g = g; c.us = unscale[g];                      // us = 2^-(weight shift) / ACT_SCALE
+                const int op = BW ? (int)prog.g[g].op : (int)OP_FWD;
+                c.g = g; c.us = unscale[prog.g[g].img];          // us = 2^-(weight shift) / ACT_SCALE
+                c.lyr = prog.g[g].lyr;
                 c.signal = g + 1 < prog.n_gemm;
                 c.need_lo = c.signal ? (prog.g[g + 1].prods == 3) : 0;
+                if (BW && (op == OP_HB || (op == OP_FWD && g == 20))) c.signal = 0;     // the next A operand is written by the tail below
                 const unsigned t_dd = c.t_lane + (unsigned)((g + 1) & 1) * 256u;       // D of this GEMM == A of the next
                 // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
-                if (g < 8) {
+                if (BW && op != OP_FWD) {
+                    if (op == OP_DR) {
+                        if (c.lyr == 0) epi_gemm<K_DR0, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        else epi_gemm<K_DR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    } else if (op == OP_FB) {
+                        epi_gemm<K_FB, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    } else if (op == OP_HB) {
+                        epi_gemm<K_HB, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    } else if (op == OP_SO) {
+                        if (c.lyr == 3) epi_gemm<K_SO3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        else if (c.lyr == 7) epi_gemm<K_SO7, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        else epi_gemm<K_SO, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    } else {
+                        epi_gemm<K_TR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    }
+                } else if (g < 8) {
                     if (g == 3) epi_gemm<K_FWD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     else if (g == 7) epi_gemm<K_FWD7, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     else epi_gemm<K_FWD, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
@@ -734,6 +919,18 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                             sdf = fminf(sdf, job.bound_r - nrm);
                         }
                         if (S.OIDX[r] >= 0 && job.sdf) job.sdf[S.OIDX[r]] = sdf;
+                        if (BW) {
+                            // sphere-background override (volsdf.py:349-357): where R - |x| < sdf the network's sdf is not the output
+                            float gs = S.BWV[6 * TM + r];
+                            if (job.bw_bg_mask) {
+                                const float x0 = S.X[r], x1 = S.X[TM + r], x2 = S.X[2 * TM + r];
+                                const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+                                if (job.bound_r - nrm < sdf) gs = 0.f;
+                            }
+                            S.BWV[6 * TM + r] = gs * c.rs;
+                            if (c.st_row && job.st_t1)
+                                *reinterpret_cast<float4*>(job.st_t1 + (size_t)((c.st_row - job.st_wide) >> 8) * 4) = make_float4(gs, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
                 if (FULL && g == 16) {
@@ -785,8 +982,24 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         const long long oo = S.OIDX[r];
                         if (oo >= 0 && job.nab) { job.nab[oo * 3] = S.PART[r]; job.nab[oo * 3 + 1] = S.PART[TM + r]; job.nab[oo * 3 + 2] = S.PART[2 * TM + r]; }
                     }
+                    if (BW && !has_rad && g + 1 < prog.n_gemm) {
+                        // no radiance part (NeuS pass A): the second-order sweep starts here with the eikonal gradient alone
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) c.nbar[cc] = S.BWV[cc * TM + r];
+                        write_vbar0(t_dd);
+                    }
                 }
-                if (FULL && g == 20) {
+                if (BW && op == OP_DR && c.lyr == 0) {
+                    // d L / d nabla through the radiance net: sum the four column quarters, add the eikonal part
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) { S.PART[(cq * 3 + cc) * TM + r] = rgb_part[cc] * (1.f / ACT_SCALE); rgb_part[cc] = 0.f; }
+                    epi_bar_sync();
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        c.nbar[cc] = S.PART[cc * TM + r] + S.PART[(3 + cc) * TM + r] + S.PART[(6 + cc) * TM + r] + S.PART[(9 + cc) * TM + r] + S.BWV[cc * TM + r];
+                }
+                if (BW && op == OP_HB) write_vbar0(t_dd);
+                if (FULL && g == 20 && op == OP_FWD) {
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) { S.PART[(cq * 3 + cc) * TM + r] = rgb_part[cc]; rgb_part[cc] = 0.f; }
                     epi_bar_sync();
@@ -796,7 +1009,35 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                             // radiance layer 3 stored relu x16: undo in the head
                             const float z = (S.PART[cc * TM + r] + S.PART[(3 + cc) * TM + r] + S.PART[(6 + cc) * TM + r] + S.PART[(9 + cc) * TM + r])
                                             * (1.f / ACT_SCALE) + __ldg(pk + L.rad_b4 + cc);
-                            job.rad[S.OIDX[r] * 3 + cc] = __fdiv_rn(1.f, 1.f + expf(-z));
+                            const float rgb = __fdiv_rn(1.f, 1.f + expf(-z));
+                            job.rad[S.OIDX[r] * 3 + cc] = rgb;
+                            if (BW) S.BWV[(3 + cc) * TM + r] *= rgb * (1.f - rgb);          // delta_4 (x rs) = d L/d radiance * sigmoid'
+                        }
+                        if (BW && c.st_row && job.st_t0)
+                            *reinterpret_cast<float4*>(job.st_t0 + (size_t)((c.st_row - job.st_wide) >> 8) * 4) =
+                                make_float4(S.BWV[3 * TM + r] * c.irs, S.BWV[4 * TM + r] * c.irs, S.BWV[5 * TM + r] * c.irs, 0.f);
+                    }
+                    if (BW && g + 1 < prog.n_gemm) {
+                        epi_bar_sync();                                   // delta_4 of every row
+                        // A <- delta_3 = (delta_4 W4) * [ys_4 > 0], over this thread's own (consumed) columns of D of GEMM 20
+                        const float d4[3] = {S.BWV[3 * TM + r], S.BWV[4 * TM + r], S.BWV[5 * TM + r]};
+                        const unsigned long long m64 = S.MASK[tid - 64];
+#pragma unroll 1
+                        for (int c16 = 0; c16 < 4; ++c16) {
+                            const int col0 = c16 * 64 + cq * 16;
+                            float o[16];
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w0 = lds128(c.w4_s + (unsigned)(col0 + 4 * j4) * 4u), w1 = lds128(c.w4_s + (unsigned)(256 + col0 + 4 * j4) * 4u),
+                                             w2 = lds128(c.w4_s + (unsigned)(512 + col0 + 4 * j4) * 4u);
+                                o[4 * j4] = d4[0] * w0.x + d4[1] * w1.x + d4[2] * w2.x; o[4 * j4 + 1] = d4[0] * w0.y + d4[1] * w1.y + d4[2] * w2.y;
+                                o[4 * j4 + 2] = d4[0] * w0.z + d4[1] * w1.z + d4[2] * w2.z; o[4 * j4 + 3] = d4[0] * w0.w + d4[1] * w1.w + d4[2] * w2.w;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = ((m64 >> (16 * c16 + j)) & 1ull) ? o[j] * ACT_SCALE : 0.f;
+                            stash16(c, ST_D + 3, col0, o, c.irs * (1.f / ACT_SCALE));
+                            store_a16(t_dd + col0, o, c.need_lo);
+                            signal_kb(c.kb_bar, c16, lane);
                         }
                     }
                 }
@@ -858,23 +1099,47 @@ static ImageLayout image_layout() {
     T.image_bytes = o;
     T.unscale_off = (o + 1023) & ~(size_t)1023;
     T.meta_off = T.unscale_off + 256;
-    T.total = T.meta_off + 1024;
+    T.total = T.meta_off + 2048;
     return T;
+}
+
+__global__ void absmax_kernel(const float* __restrict__ pk, const size_t* __restrict__ offs, const int* __restrict__ rows, float* __restrict__ out) {
+    const int g = blockIdx.x;
+    const float* p = pk + offs[g];
+    const int n = rows[g] * 256;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+    __shared__ float red[256];
+    red[threadIdx.x] = m; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    if (threadIdx.x == 0) out[g] = red[0];
 }
 
 }  // namespace tm
 
 size_t mlp_tmem_image_bytes() { return tm::image_layout().total; }
 
-// `image` = this kernel's region of the packed buffer; d_offs / d_rows / d_absmax are the per-plane tables tc_pack() left on the device
-int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, const float* d_absmax, unsigned char* image, cudaStream_t stream) {
+// `image` = this kernel's region of the packed buffer; d_offs / d_rows / d_absmax are the tables of the 21 forward planes tc_pack()
+// left on the device; the 5 backward planes (images 21..25) live in the train pack (`train_off` floats from pk_f32)
+int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, const float* d_absmax, size_t train_off, const PackTrain& TP,
+              unsigned char* image, cudaStream_t stream) {
     using namespace tm;
     const ImageLayout T = image_layout();
     int meta[N_PLANES * 4];
     for (int g = 0; g < N_PLANES; ++g) { meta[g * 4] = T.n_kb[g]; meta[g * 4 + 1] = T.N[g]; meta[g * 4 + 2] = (int)(T.w_off[g] / 16); meta[g * 4 + 3] = 0; }
-    int* d_meta = (int*)(image + T.meta_off);
+    unsigned char* mbase = image + T.meta_off;
+    int* d_meta = (int*)mbase; size_t* offs = (size_t*)(mbase + 512); int* rows = (int*)(mbase + 768); float* absmax = (float*)(mbase + 1024);
     NA_TRY(check_cuda(cudaMemcpyAsync(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, stream)));
-    pack_kernel<<<dim3(32, N_PLANES), 256, 0, stream>>>(pk_f32, d_offs, d_rows, d_meta, d_absmax, image, (float*)(image + T.unscale_off));
+    NA_TRY(check_cuda(cudaMemcpyAsync(offs, d_offs, 21 * sizeof(size_t), cudaMemcpyDeviceToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(rows, d_rows, 21 * sizeof(int), cudaMemcpyDeviceToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(absmax, d_absmax, 21 * sizeof(float), cudaMemcpyDeviceToDevice, stream)));
+    const size_t offs_bw[5] = {train_off + TP.rad_w[3], train_off + TP.rad_w[2], train_off + TP.rad_w[1], train_off + TP.rad_w[0], train_off + TP.w8_feat};
+    const int rows_bw[5] = {256, 256, 256, 256, 256};
+    NA_TRY(check_cuda(cudaMemcpyAsync(offs + 21, offs_bw, sizeof(offs_bw), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(check_cuda(cudaMemcpyAsync(rows + 21, rows_bw, sizeof(rows_bw), cudaMemcpyHostToDevice, stream)));
+    absmax_kernel<<<5, 256, 0, stream>>>(pk_f32, offs + 21, rows + 21, absmax + 21);
+    NA_CHECK_LAUNCH();
+    pack_kernel<<<dim3(32, N_PLANES), 256, 0, stream>>>(pk_f32, offs, rows, d_meta, absmax, image, (float*)(image + T.unscale_off));
     NA_CHECK_LAUNCH();
     return NA_OK;
 }
@@ -893,9 +1158,10 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     static const char* prods_env = getenv("NA_TM_PRODS");
     const size_t smem = sizeof(Smem) + 1024;
     if (!attr_set) {
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_set = true;
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
@@ -909,17 +1175,33 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
         Gemm t; t.w_off = T.w_off[g]; t.stage_bytes = (unsigned)T.N[g] * 128u; t.n_kb = (unsigned char)T.n_kb[g];
         t.prods = (unsigned char)((mixed && g >= 8) ? 1 : 3);
         if (prods_env && (int)strlen(prods_env) > g) t.prods = prods_env[g] == '1' ? 1 : 3;
-        t.n64 = T.N[g] == 64; t.pad = 0;
+        t.n64 = T.N[g] == 64; t.img = (unsigned char)g; t.op = OP_FWD; t.lyr = 0; t.pad0 = t.pad1 = 0;
         prog.g[prog.n_gemm++] = t;
+    }
+    if (job.bw) {
+        // backward program of a training patch (needs the stash): single-product operands, rows scaled per sample
+        if (!job.st_wide || !job.want_full || !STASH) return NA_ERR_BAD_ARG;
+        auto add = [&](int img, int op, int lyr) {
+            Gemm t; t.w_off = T.w_off[img]; t.stage_bytes = (unsigned)T.N[img] * 128u; t.n_kb = (unsigned char)T.n_kb[img];
+            t.prods = 1; t.n64 = 0; t.img = (unsigned char)img; t.op = (unsigned char)op; t.lyr = (unsigned char)lyr; t.pad0 = t.pad1 = 0;
+            prog.g[prog.n_gemm++] = t;
+        };
+        if (job.rad) {
+            add(21, OP_DR, 2); add(22, OP_DR, 1); add(23, OP_DR, 0);     // delta_2, delta_1, delta_0
+            add(24, OP_FB, 0); add(25, OP_HB, 0);                         // feat-bar; feature part of h-bar_7
+        }
+        for (int l = 0; l < 8; ++l) add(l, OP_SO, l);                     // second-order sweep
+        for (int l = 6; l >= 0; --l) add(15 - l, OP_TR, l);               // trunk: z-bar_l from z-bar_{l+1} W_{l+1}
     }
     long long tiles = (total + TM - 1) / TM;
     int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
     if (scratch_bytes < mlp_tmem_scratch_bytes(grid)) return NA_ERR_WORKSPACE;
     const float* usc = (const float*)(image + T.unscale_off);
     if (job.st_wide && !job.want_full) return NA_ERR_BAD_ARG;
-    if (job.st_wide)        mlp_tmem_kernel<true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
-    else if (job.want_full) mlp_tmem_kernel<true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
-    else                    mlp_tmem_kernel<false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    if (job.bw)             mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    else if (job.st_wide)   mlp_tmem_kernel<true, true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    else if (job.want_full) mlp_tmem_kernel<true, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    else                    mlp_tmem_kernel<false, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
     NA_CHECK_LAUNCH();
     return NA_OK;
 }

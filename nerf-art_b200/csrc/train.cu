@@ -34,7 +34,8 @@ enum {
     PL_S = 42,      // softplus'(z_0..7), written by the tcgen05 forward launch of the patch (loaded mode)          planes 42..49
     N_WIDE = 50
 };
-static_assert(PL_IN == ST_IN && PL_G == ST_G && PL_FEAT == ST_FEAT && PL_YS == ST_YS && PL_S == ST_S, "stash plane numbering (common.cuh)");
+static_assert(PL_IN == ST_IN && PL_G == ST_G && PL_FEAT == ST_FEAT && PL_YS == ST_YS && PL_S == ST_S && PL_ZB == ST_ZB && PL_VB == ST_VB &&
+              PL_FB == ST_FB && PL_D == ST_D, "stash plane numbering (common.cuh)");
 constexpr int NLD = 40;     // row stride of the narrow planes EMB, VB0, SMALL
 enum { NP_EMB = 0, NP_VB0 = 1, NP_SMALL = 2 };
 struct Stash {
@@ -1180,6 +1181,15 @@ static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision,
         e.apply_bg = 0;                                   // raw network sdf: the background mask below compares it with R - |x| itself
         e.bound_r = job.bound_r; e.want_full = 1; e.multires_view = job.multires_view;
         e.st_wide = st.wide; e.st_mpad = st.mpad; e.st_small = st.n(NP_SMALL);
+        // default: the 20 backward GEMMs run in the same tcgen05 launch (BW program of csrc/mlp_tmem.cu) and mlp_bwd_kernel is not used;
+        // NA_BWD_TMEM=0 keeps the forward-only stash launch + the SIMT / mma.sync backward kernel ("loaded mode")
+        const bool bw_tmem = [] { const char* e = getenv("NA_BWD_TMEM"); return !(e && e[0] == '0'); }();
+        if (bw_tmem && !fp32_bwd) {
+            e.bw = 1; e.bw_bg_mask = job.apply_bg;
+            e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
+            e.st_emb = st.n(NP_EMB); e.st_vb0 = st.n(NP_VB0); e.st_t0 = st.t(0); e.st_t1 = st.t(1);
+            return launch_mlp(e, packed, fwd_precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream);
+        }
         NA_TRY(launch_mlp(e, packed, fwd_precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream));
         job.f_sdf = w.f_sdf; job.f_rad = w.f_rad;
         if (fp32_bwd) mlp_bwd_kernel<false, true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
@@ -1294,10 +1304,12 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
         // pass A: the P points of d_all (sdf -> alpha, nabla -> eikonal); pass B: the P-1 midpoints (radiance), neus.py:320-324
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = nullptr;
         job.apply_bg = 0; job.has_rad = 0;
-        if (cfg->train_surface) {
+        const char* dbg_pass = getenv("NA_BWD_DEBUG_PASS");                 // diagnostics: "A" / "B" runs only that pass
+        if (cfg->train_surface && !(dbg_pass && dbg_pass[0] == 'B')) {
             NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
             NA_TRY(launch_wgrad(st, (long long)M, 0, 1, 0, gp, stream));
         }
+        if (dbg_pass && dbg_pass[0] == 'A') return NA_OK;
         job.P = P - 1; job.midpoints = 1; job.g_sdf = nullptr; job.g_nab = nullptr; job.g_rad = w.g_rad; job.has_rad = 1;
         NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
         NA_TRY(launch_wgrad(st, (long long)n * (P - 1), 1, cfg->train_surface, cfg->train_radiance, gp, stream));

@@ -16,6 +16,6 @@ x = torch.rand(n, 3, device=dev, generator=g) * 4 - 2
 v = torch.nn.functional.normalize(torch.randn(n // 4, 3, device=dev, generator=g), dim=-1)
 with torch.no_grad():
     m.engine().sdf_eval(x, apply_bg=True)
-    m.engine().full_eval(x[:n // 4], v)
+    m.engine().full_eval(x[:n // 4], v, want_feat=False)
 torch.cuda.synchronize()
 print('done')
