@@ -34,7 +34,7 @@ P = N_SAMPLES + N_IMPORTANCE
 F_SDF = 2 * (39 * 256 + 256 * 256 * 2 + 256 * 217 + 256 * 256 * 4 + 256)
 F_FULL = 2 * (524544 + 459008 + 265216)
 # measured DRAM bytes per sample (SDF-only, full) of the MLP kernel by precision mode -- profiles/r1n_tmem_v2.md
-TRAFFIC_B_PER_SAMPLE = {'tc': (14587392 / 1048576, (350204416 + 1091515000) / 262144)}
+TRAFFIC_B_PER_SAMPLE = {'tc': (14568448 / 1048576, (134657024 + 492769280) / 262144)}
 RENDER_KW = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=False, white_bkgd=False,
                  max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, epsilon=0.1, max_bisection_steps=10,
                  require_nablas=True, calc_normal=True, detailed_output=False)
@@ -277,7 +277,7 @@ def main():
         traffic = TRAFFIC_B_PER_SAMPLE.get(os.environ.get('NA_PRECISION', 'tc'))
         roof = {'bound': 'tensor', 'kernel': 'mlp kernel, SDF-only mode', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': ach / peak, 'traffic': None if traffic is None else traffic[0] * m,
-                'traffic_src': 'profiles/r1n_tmem_v2.md (ncu --set full, bytes/sample x samples_per_launch)', 'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
+                'traffic_src': 'profiles/r2e_tmem_v3.md (ncu --set full, bytes/sample x samples_per_launch)', 'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
                 'flop_per_sample': F_SDF, 'samples_per_launch': m, 'launch_ms': t_k * 1e3,
                 'full_mode': {'traffic': None if traffic is None else traffic[1] * (m // 4), 'achieved': (m // 4) * F_FULL / t_f / 1e12, 'flop_per_sample': F_FULL, 'launch_ms': t_f * 1e3,
                               'frac': (m // 4) * F_FULL / t_f / 1e12 / peak},

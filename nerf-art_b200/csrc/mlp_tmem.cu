@@ -166,7 +166,6 @@ struct __align__(1024) Smem {
     // closed-form nabla instead of re-evaluating sincosf; and the 9 small-input rows of radiance layer 0 (VolSDF: x | view | nabla)
     float EMBS[STASH ? EMB * TM : 1];
     float BWV[8 * TM];                                 // BW: per row 0..2 d L/d nabla (eikonal) x rs | 3..5 d L/d radiance x rs, then delta_4 x rs | 6 masked d L/d sdf x rs
-    unsigned long long MASK[EPI_THREADS];              // BW: ReLU masks of radiance layer 3
     __align__(16) float RADW[STASH ? 9 * 256 : 4];
 };
 
@@ -174,7 +173,12 @@ struct __align__(1024) Smem {
 constexpr size_t DH_BYTES = (size_t)8 * 64 * TM * 8;          // plane p, column quad k4, row r -> uint2 at (p*64 + k4)*128 + r
 constexpr size_t FEAT_BYTES = (size_t)64 * TM * 16;           // float4 at k4*128 + r
 constexpr size_t MISC_BYTES = (size_t)80 * TM * 4;            // float at j*128 + r : d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
-constexpr size_t SCRATCH_BYTES = DH_BYTES + FEAT_BYTES + MISC_BYTES;
+// BW program only (same quad layout as the feature plane: float4 at (plane*64 + k4)*128 + r): q_0..6 = 100 g-bar g (1 - s) parked for
+// the trunk, plane 7 = feature part of h-bar_7; a private copy of g_0..7; the ReLU masks of the four radiance hidden layers
+constexpr size_t QP_BYTES = (size_t)8 * 64 * TM * 16;
+constexpr size_t GP_BYTES = (size_t)8 * 64 * TM * 16;
+constexpr size_t MK_BYTES = (size_t)4 * EPI_THREADS * 8;
+constexpr size_t SCRATCH_BYTES = DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES + MK_BYTES;
 
 enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_RAD, K_RAD3,
                K_DR, K_DR0, K_FB, K_HB, K_SO, K_SO3, K_SO7, K_TR };      // BW program only
@@ -190,7 +194,9 @@ struct EpiCtx {
     // backward quantity of the row is carried x rs in the fp16 operands and stored x irs) and the row's total d L / d nabla (x rs)
     float rs, irs, nbar[3];
     int lyr, has_rad;               // BW: layer index of the running backward GEMM; the program has the radiance part
-    unsigned long long* mask;       // BW: this thread's slot for the ReLU mask of radiance layer 3 (64 columns)
+    unsigned long long* mk;         // BW: this thread's ReLU-mask slots: mk[l * EPI_THREADS], l = radiance hidden layer (64 columns each)
+    float4* qp; float4* gp;         // BW: per-CTA scratch planes (quad layout)
+    int bw;
     unsigned d_phase; long long* t_wait; long long* trace;
 };
 
@@ -294,6 +300,28 @@ __device__ __forceinline__ void load16(const EpiCtx& c, int plane, int col0, flo
     }
 }
 
+// BW: 16 consecutive columns of row r in a per-CTA quad-layout scratch plane (coalesced: a warp instruction covers 32 rows x 16 B)
+__device__ __forceinline__ void qstore16(float4* base, int plane, int col0, int r, const float (&v)[16], float scale) {
+    float4* p = base + (size_t)(plane * 64 + (col0 >> 2)) * TM + r;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) p[(size_t)j4 * TM] = make_float4(v[4 * j4] * scale, v[4 * j4 + 1] * scale, v[4 * j4 + 2] * scale, v[4 * j4 + 3] * scale);
+}
+__device__ __forceinline__ void qload16(const float4* base, int plane, int col0, int r, float (&v)[16]) {
+    const float4* p = base + (size_t)(plane * 64 + (col0 >> 2)) * TM + r;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) { const float4 q = p[(size_t)j4 * TM]; v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w; }
+}
+// BW: softplus'(z_lyr) of 16 columns from the 16-bit codes the forward epilogue left in the per-CTA scratch
+__device__ __forceinline__ void sload16(const EpiCtx& c, int lyr, int col0, float (&v)[16]) {
+    const uint2* p = c.dh + (size_t)(lyr * 64 + (col0 >> 2)) * TM + c.r;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+        float d4[4];
+        dh_decode4(p[(size_t)j4 * TM], d4);
+        v[4 * j4] = d4[0]; v[4 * j4 + 1] = d4[1]; v[4 * j4 + 2] = d4[2]; v[4 * j4 + 3] = d4[3];
+    }
+}
+
 // one GEMM's epilogue for this thread's row and its 64 columns (4 passes of 16)
 template <int KIND, bool FULL, bool ST>
 __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, float& sdf_part, float (&rgb_part)[3], const float (&small_in)[36]) {
@@ -393,14 +421,16 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             }
             if (ST) {
                 stash16(c, ST_IN + c.g, col0, o, 1.f / ACT_SCALE);
-                float sv[16];
+                if (!c.bw) {                 // the BW program reads softplus' from the codes in the per-CTA scratch instead
+                    float sv[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float ru = rcp_approx(1.f + t[j]);
-                    sv[j] = z16[j] >= 0.f ? ru : 1.f - ru;
-                    if (KIND == K_FWD3 && col0 + j >= SKIP_H) sv[j] = 0.f;
+                    for (int j = 0; j < 16; ++j) {
+                        const float ru = rcp_approx(1.f + t[j]);
+                        sv[j] = z16[j] >= 0.f ? ru : 1.f - ru;
+                        if (KIND == K_FWD3 && col0 + j >= SKIP_H) sv[j] = 0.f;
+                    }
+                    stash16(c, ST_S + c.g, col0, sv, 1.f);
                 }
-                stash16(c, ST_S + c.g, col0, sv, 1.f);
             }
             if (KIND == K_FWD7) {
 #pragma unroll
@@ -428,7 +458,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + 2] = w4.z * d4[2] * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4[3] * ACT_SCALE;
                 }
             }
-            if (ST && FULL) stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE);
+            if (ST && FULL) { stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE); if (c.bw) qstore16(c.gp, 7, col0, r, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD || KIND == K_BWD4) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -441,7 +471,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
                 }
             }
-            if (ST) stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE);
+            if (ST) { stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE); if (c.bw) qstore16(c.gp, 15 - c.g, col0, r, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[k * TM + r] += acc[j] * us; }
@@ -449,10 +479,9 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             // ---- backward program (BW): every value is carried x rs in the operands; stash planes receive x irs ----------------
             if (KIND == K_DR || KIND == K_DR0) {
                 // delta_lyr = (delta_{lyr+1} R_{lyr+1}) * [ys_{lyr+1} > 0]   (radiance hidden layers, lyr = 2, 1, 0)
-                float y[16];
-                load16(c, ST_YS + c.lyr, col0, y);
+                const unsigned long long m64 = c.mk[(size_t)c.lyr * EPI_THREADS] >> (16 * c16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = y[j] > 0.f ? acc[j] * us16 : 0.f;
+                for (int j = 0; j < 16; ++j) o[j] = ((m64 >> j) & 1ull) ? acc[j] * us16 : 0.f;
                 stash16(c, ST_D + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
                 if (KIND == K_DR0) {
                     // d L / d nabla through radiance layer 0: delta_0 . W0[:, nabla columns]  (partial over this thread's columns)
@@ -472,15 +501,15 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 for (int j = 0; j < 16; ++j) o[j] = acc[j] * us16;                       // d L / d feature
                 stash16(c, ST_FB, col0, o, c.irs * (1.f / ACT_SCALE));
             } else if (KIND == K_HB) {
-                // feature part of h-bar_7, parked (x rs) in the z-bar_7 plane until the second-order sweep reaches layer 7
+                // feature part of h-bar_7, parked (x rs) in scratch plane 7 until the second-order sweep reaches layer 7
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = acc[j] * us;
-                stash16(c, ST_ZB + 7, col0, o, 1.f);
+                qstore16(c.qp, 7, col0, r, o, 1.f);
             } else if (KIND == K_SO || KIND == K_SO3 || KIND == K_SO7) {
                 // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
                 float sv[16], gv[16], q[16];
-                load16(c, ST_S + c.lyr, col0, sv);
-                load16(c, ST_G + c.lyr, col0, gv);
+                sload16(c, c.lyr, col0, sv);
+                qload16(c.gp, c.lyr, col0, r, gv);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float gb = acc[j] * us;
@@ -495,7 +524,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 if (KIND == K_SO7) {
                     // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]
                     float hb[16];
-                    if (c.has_rad) load16(c, ST_ZB + 7, col0, hb);
+                    if (c.has_rad) qload16(c.qp, 7, col0, r, hb);
                     else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) hb[j] = 0.f;
@@ -511,15 +540,15 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     for (int j = 0; j < 16; ++j) o[j] = fmaf(hb[j], sv[j], q[j]);
                     stash16(c, ST_ZB + 7, col0, o, c.irs);
                 } else {
-                    stash16(c, ST_ZB + c.lyr, col0, q, 1.f);                             // parked (x rs) until the trunk reaches this layer
+                    qstore16(c.qp, c.lyr, col0, r, q, 1.f);                              // parked (x rs) until the trunk reaches this layer
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
             } else {
                 // trunk, K_TR: z-bar_lyr = h-bar_lyr s_lyr + q_lyr
                 float sv[16], qv[16];
-                load16(c, ST_S + c.lyr, col0, sv);
-                load16(c, ST_ZB + c.lyr, col0, qv);
+                sload16(c, c.lyr, col0, sv);
+                qload16(c.qp, c.lyr, col0, r, qv);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j] * us, sv[j], qv[j]);
                 stash16(c, ST_ZB + c.lyr, col0, o, c.irs);
@@ -556,11 +585,12 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 for (int i = 0; i < 4; ++i) o[4 * j4 + i] = fmaxf(z[i], 0.f);
             }
             if (ST) stash16(c, ST_YS + c.g - 17, col0, o, 1.f / ACT_SCALE);
-            if (ST && KIND == K_RAD3 && c.mask) {
+            if (ST && c.bw) {
                 unsigned long long m16 = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) m16 |= (unsigned long long)(o[j] > 0.f) << j;
-                *c.mask = (c16 == 0 ? 0ull : *c.mask) | (m16 << (16 * c16));
+                unsigned long long* slot = c.mk + (size_t)(c.g - 17) * EPI_THREADS;
+                *slot = (c16 == 0 ? 0ull : *slot) | (m16 << (16 * c16));
             }
             if (KIND == K_RAD3) {
 #pragma unroll
@@ -577,7 +607,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                              (KIND >= K_DR && !c.signal));
         if (store) store_a16(t_d + col0, o, c.need_lo);
         NA_TRACE_E(c.trace, c.g, c16, 2);
-        if (USES_DH && (c.lane & 15) == 0) {
+        if (USES_DH && (c.lane & 15) == 0 && !(ST && c.bw)) {
             // the 16 lanes' codes of this pass share one line per column quad; they are dead now: keep them out of DRAM
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) discard_l2(dhp + (size_t)((col0 >> 2) + j4) * TM);
@@ -738,7 +768,10 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
         c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = job.rad != nullptr;
-        c.mask = BW ? &S.MASK[tid - 64] : nullptr;
+        c.bw = BW ? 1 : 0;
+        c.qp = reinterpret_cast<float4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES);
+        c.gp = reinterpret_cast<float4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES);
+        c.mk = reinterpret_cast<unsigned long long*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES) + (tid - 64);
         const bool has_rad = job.rad != nullptr;
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1021,7 +1054,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         epi_bar_sync();                                   // delta_4 of every row
                         // A <- delta_3 = (delta_4 W4) * [ys_4 > 0], over this thread's own (consumed) columns of D of GEMM 20
                         const float d4[3] = {S.BWV[3 * TM + r], S.BWV[4 * TM + r], S.BWV[5 * TM + r]};
-                        const unsigned long long m64 = S.MASK[tid - 64];
+                        const unsigned long long m64 = c.mk[(size_t)3 * EPI_THREADS];
 #pragma unroll 1
                         for (int c16 = 0; c16 < 4; ++c16) {
                             const int col0 = c16 * 64 + cq * 16;
