@@ -120,6 +120,7 @@ struct EvalJob {
     // activation stash for the backward pass (csrc/train.cu; tensor-core modes, want_full == 1): sample-major fp32 planes
     // [plane][st_mpad][256] indexed by the launch's flat sample number; nullptr = not written
     float* st_wide;  size_t st_mpad;
+    int st_quad;                                     // 1: wide planes in the quad layout (stash_quad_index below) instead of [m][256]
     float* st_small;                                 // [st_mpad][40]: the small radiance inputs x | embed(view) | nabla
     // backward in the same launch (csrc/mlp_tmem.cu, BW program; needs the stash): upstream gradients per sample (nullable = 0),
     // the remaining stash planes, and the sphere-background mask of d L / d sdf (volsdf.py:349-357)
@@ -128,6 +129,12 @@ struct EvalJob {
     float* st_emb;  float* st_vb0;                   // [st_mpad][40]: encoding, v-bar_0
     float* st_t0;  float* st_t1;                     // [st_mpad][4]: delta of the radiance output layer; masked d L / d sdf
 };
+
+// quad layout of a wide stash plane: tile of 128 samples x column quad, float4 at ((m / 128) * 64 + col / 4) * 128 + m % 128 -- the
+// tcgen05 epilogues (thread = sample row) then store 32 rows x 16 B contiguously per warp instruction
+__host__ __device__ inline size_t stash_quad_index(long long m, int col) {
+    return ((size_t)(m >> 7) * 64 + (size_t)(col >> 2)) * 512 + (size_t)(m & 127) * 4 + (size_t)(col & 3);
+}
 
 // planes of EvalJob::st_wide a forward launch fills (the backward kernels of csrc/train.cu add theirs; see the enum there)
 constexpr int ST_IN = 0;        // 0..7   h_i = output of SDF layer i (layer 3: [h_3 | emb])

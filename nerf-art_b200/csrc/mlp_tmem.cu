@@ -173,10 +173,11 @@ struct __align__(1024) Smem {
 constexpr size_t DH_BYTES = (size_t)8 * 64 * TM * 8;          // plane p, column quad k4, row r -> uint2 at (p*64 + k4)*128 + r
 constexpr size_t FEAT_BYTES = (size_t)64 * TM * 16;           // float4 at k4*128 + r
 constexpr size_t MISC_BYTES = (size_t)80 * TM * 4;            // float at j*128 + r : d sdf/d emb (39) @0 | small radiance inputs (<=33) @40
-// BW program only (same quad layout as the feature plane: float4 at (plane*64 + k4)*128 + r): q_0..6 = 100 g-bar g (1 - s) parked for
-// the trunk, plane 7 = feature part of h-bar_7; a private copy of g_0..7; the ReLU masks of the four radiance hidden layers
-constexpr size_t QP_BYTES = (size_t)8 * 64 * TM * 16;
-constexpr size_t GP_BYTES = (size_t)8 * 64 * TM * 16;
+// BW program only: q_0..6 = 100 g-bar g (1 - s) parked for the trunk and, as plane 7, the feature part of h-bar_7, as fp16 (both are
+// x rs, i.e. O(1), and are added into fp16 operands anyway): uint4 = 8 columns at (plane*32 + k/8)*128 + r; the ReLU masks of the four
+// radiance hidden layers
+constexpr size_t QP_BYTES = (size_t)8 * 32 * TM * 16;
+constexpr size_t GP_BYTES = 0;
 constexpr size_t MK_BYTES = (size_t)4 * EPI_THREADS * 8;
 constexpr size_t SCRATCH_BYTES = DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES + MK_BYTES;
 
@@ -188,14 +189,17 @@ struct EpiCtx {
     unsigned t_lane; int r, cq, g; float us; int sdim;
     unsigned bias_s, w8_s, w4_s, radw_s, kb_bar, d_bar;
     int signal, need_lo, lane;
-    float* st_row;                  // ST: st_wide + (flat sample) * 256 of this thread's row, nullptr for padding rows
+    float* st_row;                  // ST: this thread's row in plane 0 of the stash (row-major: st_wide + m * 256; quad layout: the row's
+                                    // slot in column quad 0 of its tile), nullptr beyond the allocation
     size_t st_plane;                // ST: floats per plane
+    long long st_m;                 // ST: flat sample index of the row
+    int st_quad;
     // BW: per-row power-of-two scale of the upstream gradient (the backward is linear in it and rows are independent, so every
     // backward quantity of the row is carried x rs in the fp16 operands and stored x irs) and the row's total d L / d nabla (x rs)
     float rs, irs, nbar[3];
     int lyr, has_rad;               // BW: layer index of the running backward GEMM; the program has the radiance part
     unsigned long long* mk;         // BW: this thread's ReLU-mask slots: mk[l * EPI_THREADS], l = radiance hidden layer (64 columns each)
-    float4* qp; float4* gp;         // BW: per-CTA scratch planes (quad layout)
+    uint4* qp;                      // BW: per-CTA fp16 scratch planes
     int bw;
     unsigned d_phase; long long* t_wait; long long* trace;
 };
@@ -273,9 +277,11 @@ __device__ __forceinline__ void emb_range(const float (&xs)[3], float (&e)[16]) 
 // ST: 16 consecutive columns of this thread's row -> stash plane `plane` (values are stored x `scale`)
 __device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, const float (&o)[16], float scale) {
     if (!c.st_row) return;
-    float4* dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + col0);
+    float4* dst; size_t step;
+    if (c.st_quad) { dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + (size_t)(col0 >> 2) * 512); step = 128; }
+    else           { dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + col0); step = 1; }
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(o[4 * j4] * scale, o[4 * j4 + 1] * scale, o[4 * j4 + 2] * scale, o[4 * j4 + 3] * scale);
+    for (int j4 = 0; j4 < 4; ++j4) dst[j4 * step] = make_float4(o[4 * j4] * scale, o[4 * j4 + 1] * scale, o[4 * j4 + 2] * scale, o[4 * j4 + 3] * scale);
 }
 
 // BW: entry k of v-bar_0 = (d emb / d x)^T-contracted total d L / d nabla of row r (x rs): x_c -> n_c, sin(f x_c) -> f cos(f x_c) n_c,
@@ -288,28 +294,37 @@ __device__ __forceinline__ float vbar0_entry(const Smem& S, int k, int r, const 
     return rem < 3 ?  nb * fr * S.EMBS[(k + 3) * TM + r] * (1.f / ACT_SCALE)
                    : -nb * fr * S.EMBS[(k - 3) * TM + r] * (1.f / ACT_SCALE);
 }
-// BW: 16 consecutive columns of this thread's row from stash plane `plane` (zeros on padding rows)
-__device__ __forceinline__ void load16(const EpiCtx& c, int plane, int col0, float (&v)[16]) {
-    if (c.st_row) {
-        const float4* p = reinterpret_cast<const float4*>(c.st_row + (size_t)plane * c.st_plane + col0);
+// BW: 16 consecutive columns of row r in a per-CTA fp16 scratch plane (coalesced: a warp instruction covers 32 rows x 16 B)
+__device__ __forceinline__ void qstore16(uint4* base, int plane, int col0, int r, const float (&v)[16]) {
+    uint4* p = base + (size_t)(plane * 32 + (col0 >> 3)) * TM + r;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) { const float4 q = p[j4]; v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w; }
-    } else {
+    for (int j8 = 0; j8 < 2; ++j8) {
+        unsigned w[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int i = 0; i < 4; ++i) { const __half2 h = __floats2half2_rn(v[8 * j8 + 2 * i], v[8 * j8 + 2 * i + 1]); w[i] = *reinterpret_cast<const unsigned*>(&h); }
+        p[(size_t)j8 * TM] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
-
-// BW: 16 consecutive columns of row r in a per-CTA quad-layout scratch plane (coalesced: a warp instruction covers 32 rows x 16 B)
-__device__ __forceinline__ void qstore16(float4* base, int plane, int col0, int r, const float (&v)[16], float scale) {
-    float4* p = base + (size_t)(plane * 64 + (col0 >> 2)) * TM + r;
+__device__ __forceinline__ void qload16(const uint4* base, int plane, int col0, int r, float (&v)[16]) {
+    const uint4* p = base + (size_t)(plane * 32 + (col0 >> 3)) * TM + r;
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) p[(size_t)j4 * TM] = make_float4(v[4 * j4] * scale, v[4 * j4 + 1] * scale, v[4 * j4 + 2] * scale, v[4 * j4 + 3] * scale);
+    for (int j8 = 0; j8 < 2; ++j8) {
+        const uint4 q = p[(size_t)j8 * TM];
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x; v[8 * j8 + 2 * i + 1] = f.y; }
+    }
 }
-__device__ __forceinline__ void qload16(const float4* base, int plane, int col0, int r, float (&v)[16]) {
-    const float4* p = base + (size_t)(plane * 64 + (col0 >> 2)) * TM + r;
+// BW: 16 consecutive columns of this thread's row from a (quad-layout) stash plane it wrote earlier in the tile
+__device__ __forceinline__ void stash_load16(const EpiCtx& c, int plane, int col0, float (&v)[16]) {
+    if (!c.st_row) {
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) { const float4 q = p[(size_t)j4 * TM]; v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w; }
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        return;
+    }
+    const float4* p = reinterpret_cast<const float4*>(c.st_row + (size_t)plane * c.st_plane + (size_t)(col0 >> 2) * 512);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) { const float4 q = p[j4 * 128]; v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w; }
 }
 // BW: softplus'(z_lyr) of 16 columns from the 16-bit codes the forward epilogue left in the per-CTA scratch
 __device__ __forceinline__ void sload16(const EpiCtx& c, int lyr, int col0, float (&v)[16]) {
@@ -447,7 +462,10 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 const float4 f4 = make_float4(fmaf(acc[4 * j4], us, b4.x), fmaf(acc[4 * j4 + 1], us, b4.y),
                                               fmaf(acc[4 * j4 + 2], us, b4.z), fmaf(acc[4 * j4 + 3], us, b4.w));
                 if (FULL) c.featp[(size_t)((col0 >> 2) + j4) * TM + r] = f4;
-                if (ST && c.st_row) reinterpret_cast<float4*>(c.st_row + (size_t)ST_FEAT * c.st_plane + col0)[j4] = f4;
+                if (ST && c.st_row) {
+                    if (c.st_quad) reinterpret_cast<float4*>(c.st_row + (size_t)ST_FEAT * c.st_plane + (size_t)((col0 >> 2) + j4) * 512)[0] = f4;
+                    else reinterpret_cast<float4*>(c.st_row + (size_t)ST_FEAT * c.st_plane + col0)[j4] = f4;
+                }
                 if (c.job->feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(c.job->feat + S.OIDX[r] * 256 + col0) + j4) = f4;
                 if (FULL) {
                     // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
@@ -458,7 +476,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + 2] = w4.z * d4[2] * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4[3] * ACT_SCALE;
                 }
             }
-            if (ST && FULL) { stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE); if (c.bw) qstore16(c.gp, 7, col0, r, o, 1.f / ACT_SCALE); }
+            if (ST && FULL) { stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD || KIND == K_BWD4) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -471,7 +489,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
                 }
             }
-            if (ST) { stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE); if (c.bw) qstore16(c.gp, 15 - c.g, col0, r, o, 1.f / ACT_SCALE); }
+            if (ST) { stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[k * TM + r] += acc[j] * us; }
@@ -504,12 +522,12 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 // feature part of h-bar_7, parked (x rs) in scratch plane 7 until the second-order sweep reaches layer 7
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = acc[j] * us;
-                qstore16(c.qp, 7, col0, r, o, 1.f);
+                qstore16(c.qp, 7, col0, r, o);
             } else if (KIND == K_SO || KIND == K_SO3 || KIND == K_SO7) {
                 // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
                 float sv[16], gv[16], q[16];
                 sload16(c, c.lyr, col0, sv);
-                qload16(c.gp, c.lyr, col0, r, gv);
+                stash_load16(c, ST_G + c.lyr, col0, gv);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float gb = acc[j] * us;
@@ -540,7 +558,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     for (int j = 0; j < 16; ++j) o[j] = fmaf(hb[j], sv[j], q[j]);
                     stash16(c, ST_ZB + 7, col0, o, c.irs);
                 } else {
-                    qstore16(c.qp, c.lyr, col0, r, q, 1.f);                              // parked (x rs) until the trunk reaches this layer
+                    qstore16(c.qp, c.lyr, col0, r, q);                                   // parked (x rs) until the trunk reaches this layer
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
@@ -767,10 +785,10 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.d_phase = 0;
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
+        c.st_m = 0; c.st_quad = job.st_quad;
         c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = job.rad != nullptr;
         c.bw = BW ? 1 : 0;
-        c.qp = reinterpret_cast<float4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES);
-        c.gp = reinterpret_cast<float4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES);
+        c.qp = reinterpret_cast<uint4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES);
         c.mk = reinterpret_cast<unsigned long long*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES) + (tid - 64);
         const bool has_rad = job.rad != nullptr;
 
@@ -802,7 +820,8 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     }
                 }
                 // padding rows of the last tile are written too (zero upstream gradient): the weight-gradient kernels read whole tiles
-                c.st_row = (ST && (size_t)w < job.st_mpad) ? job.st_wide + (size_t)w * 256 : nullptr;
+                c.st_m = w;
+                c.st_row = (ST && (size_t)w < job.st_mpad) ? job.st_wide + (job.st_quad ? stash_quad_index(w, 0) : (size_t)w * 256) : nullptr;
                 if (cq == 0) {
                     S.OIDX[r] = oidx;
                     S.X[r] = x0; S.X[TM + r] = x1; S.X[2 * TM + r] = x2;
@@ -856,7 +875,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 #pragma unroll
                 for (int j = 0; j < 16; ++j) e[j] = vbar0_entry(S, 16 * cq + j, r, c.nbar);
                 if (c.st_row && job.st_vb0) {
-                    float* vrow = job.st_vb0 + (size_t)((c.st_row - job.st_wide) >> 8) * 40;
+                    float* vrow = job.st_vb0 + (size_t)c.st_m * 40;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) if (16 * cq + j < 40) vrow[16 * cq + j] = e[j] * c.irs;
                 }
@@ -925,7 +944,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                             for (int cc = 0; cc < 3; ++cc) small_in[30 + cc] = nb[cc] * ACT_SCALE;
                         }
                         if (ST && cq == 0 && c.st_row && job.st_small) {
-                            float* srow = job.st_small + (size_t)((c.st_row - job.st_wide) >> 8) * 40;
+                            float* srow = job.st_small + (size_t)c.st_m * 40;
 #pragma unroll
                             for (int j = 0; j < 36; ++j) srow[j] = small_in[j] * (1.f / ACT_SCALE);
 #pragma unroll
@@ -962,7 +981,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                             }
                             S.BWV[6 * TM + r] = gs * c.rs;
                             if (c.st_row && job.st_t1)
-                                *reinterpret_cast<float4*>(job.st_t1 + (size_t)((c.st_row - job.st_wide) >> 8) * 4) = make_float4(gs, 0.f, 0.f, 0.f);
+                                *reinterpret_cast<float4*>(job.st_t1 + (size_t)c.st_m * 4) = make_float4(gs, 0.f, 0.f, 0.f);
                         }
                     }
                 }
@@ -1047,7 +1066,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                             if (BW) S.BWV[(3 + cc) * TM + r] *= rgb * (1.f - rgb);          // delta_4 (x rs) = d L/d radiance * sigmoid'
                         }
                         if (BW && c.st_row && job.st_t0)
-                            *reinterpret_cast<float4*>(job.st_t0 + (size_t)((c.st_row - job.st_wide) >> 8) * 4) =
+                            *reinterpret_cast<float4*>(job.st_t0 + (size_t)c.st_m * 4) =
                                 make_float4(S.BWV[3 * TM + r] * c.irs, S.BWV[4 * TM + r] * c.irs, S.BWV[5 * TM + r] * c.irs, 0.f);
                     }
                     if (BW && g + 1 < prog.n_gemm) {

@@ -707,7 +707,7 @@ struct WgradTask {
     int nbr;                    // output blocks along r
 };
 constexpr int MAX_WTASKS = 32;
-struct WgradTable { WgradTask t[MAX_WTASKS]; int n; int total_blocks; };
+struct WgradTable { WgradTask t[MAX_WTASKS]; int n; int total_blocks; int quad; };      // quad: the 256-wide planes are in the quad layout
 constexpr int WK = 16;          // samples per smem chunk
 
 __global__ void __launch_bounds__(256)
@@ -717,6 +717,7 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     int ti = 0;
     while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
     const WgradTask t = tab.t[ti];
+    const bool quad = tab.quad != 0;
     const int b = blockIdx.x - t.blk0;
     const int lb = (b / t.nbr) * 128, rb = (b % t.nbr) * 128;
     const long long m0 = (long long)blockIdx.y * rows_per_split;
@@ -734,19 +735,25 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     auto gload = [&](const float* Lp, const float* Rp, long long mm) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int idx = tid * 2 + e, row = idx >> 5, c4 = (idx & 31) * 4;
+            // row-major planes: a warp reads 512 B of one sample; quad layout: 4 consecutive samples x 8 column quads per warp instruction
+            // (64-byte segments; the shared-memory stores below stay conflict-free: each quarter warp hits 8 distinct 4-bank groups)
+            const int idx = tid * 2 + e;
+            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
+            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
             const long long m = mm + row;
             lreg[e] = make_float4(0.f, 0.f, 0.f, 0.f); rreg[e] = lreg[e];
             if (m < m1) {
-                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + m * t.ldl + lb + c4);
-                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + m * t.ldr + rb + c4);
+                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + ((quad && t.ldl == 256) ? stash_quad_index(m, lb + c4) : (size_t)m * t.ldl + lb + c4));
+                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + ((quad && t.ldr == 256) ? stash_quad_index(m, rb + c4) : (size_t)m * t.ldr + rb + c4));
             }
         }
     };
     auto sstore = [&](int buf) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int idx = tid * 2 + e, row = idx >> 5, c4 = (idx & 31) * 4;
+            const int idx = tid * 2 + e;
+            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
+            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
             *reinterpret_cast<float4*>(&Ls[buf][row][c4]) = lreg[e];
             *reinterpret_cast<float4*>(&Rs[buf][row][c4]) = rreg[e];
         }
@@ -805,6 +812,7 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     int ti = 0;
     while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
     const WgradTask t = tab.t[ti];
+    const bool quad = tab.quad != 0;
     const int b = blockIdx.x - t.blk0;
     const int lb = (b / t.nbr) * 128, rb = (b % t.nbr) * 128;
     const long long m0 = (long long)blockIdx.y * rows_per_split;
@@ -824,19 +832,25 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     auto gload = [&](const float* Lp, const float* Rp, long long mm) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int idx = tid * 2 + e, row = idx >> 5, c4 = (idx & 31) * 4;
+            // row-major planes: a warp reads 512 B of one sample; quad layout: 4 consecutive samples x 8 column quads per warp instruction
+            // (64-byte segments; the shared-memory stores below stay conflict-free: each quarter warp hits 8 distinct 4-bank groups)
+            const int idx = tid * 2 + e;
+            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
+            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
             const long long m = mm + row;
             lreg[e] = make_float4(0.f, 0.f, 0.f, 0.f); rreg[e] = lreg[e];
             if (m < m1) {
-                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + m * t.ldl + lb + c4);
-                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + m * t.ldr + rb + c4);
+                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + ((quad && t.ldl == 256) ? stash_quad_index(m, lb + c4) : (size_t)m * t.ldl + lb + c4));
+                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + ((quad && t.ldr == 256) ? stash_quad_index(m, rb + c4) : (size_t)m * t.ldr + rb + c4));
             }
         }
     };
     auto sstore = [&](int buf) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int idx = tid * 2 + e, row = idx >> 5, c4 = (idx & 31) * 4;
+            const int idx = tid * 2 + e;
+            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
+            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
             *reinterpret_cast<float4*>(&Ls[buf][row][c4]) = make_float4(to_tf32(lreg[e].x), to_tf32(lreg[e].y), to_tf32(lreg[e].z), to_tf32(lreg[e].w));
             *reinterpret_cast<float4*>(&Rs[buf][row][c4]) = make_float4(to_tf32(rreg[e].x), to_tf32(rreg[e].y), to_tf32(rreg[e].z), to_tf32(rreg[e].w));
         }
@@ -889,14 +903,34 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
 
 struct ColsumTask { const float* P; float* out; int ld, n; };
 constexpr int MAX_CTASKS = 24;
-struct ColsumTable { ColsumTask t[MAX_CTASKS]; int n; };
+struct ColsumTable { ColsumTask t[MAX_CTASKS]; int n; int quad; };
 __global__ void __launch_bounds__(256)
 colsum_kernel(const ColsumTable tab, long long m_total, int rows_per_split) {
     const ColsumTask t = tab.t[blockIdx.x];
-    const int c = threadIdx.x;
-    if (c >= t.n) return;
     const long long m0 = (long long)blockIdx.y * rows_per_split;
     long long m1 = m0 + rows_per_split; if (m1 > m_total) m1 = m_total;
+    if (tab.quad && t.ld == 256) {
+        // quad layout: warp w sums column quads w, w + 8, ... ; a warp instruction reads 32 rows x 16 B contiguously
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (m0 >= m1) return;                                                  // m0, m1 are multiples of the 128-row tile
+        for (int q = warp; q < 64; q += 8) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (long long mt = m0; mt < m1; mt += 128) {
+                const float4* p = reinterpret_cast<const float4*>(t.P + stash_quad_index(mt, 4 * q)) + lane;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float4 v = p[32 * i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+                a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+            }
+            if (lane == 0) { atomicAdd(t.out + 4 * q, a.x); atomicAdd(t.out + 4 * q + 1, a.y); atomicAdd(t.out + 4 * q + 2, a.z); atomicAdd(t.out + 4 * q + 3, a.w); }
+        }
+        return;
+    }
+    const int c = threadIdx.x;
+    if (c >= t.n) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     long long m = m0;
     for (; m + 3 < m1; m += 4) {
@@ -1153,7 +1187,7 @@ static TrainWs train_ws(void* base, long long n_rays, int P) {
 // patch once and leaves h_i, softplus'(z_i), g_i, the feature and the radiance activations in the stash planes the backward and
 // weight-gradient kernels read ("loaded mode").
 static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision, const float* pk, const PackF32& L, const float* tp,
-                          const PackTrain& T, const Stash& st, const TrainWs& w, cudaStream_t stream) {
+                          const PackTrain& T, const Stash& st, const TrainWs& w, int* quad_out, cudaStream_t stream) {
     static thread_local bool attr_set = false;
     static const bool fp32_bwd = [] { const char* e = getenv("NA_BWD"); return e && strcmp(e, "fp32") == 0; }();
     static const bool force_recompute = [] { const char* e = getenv("NA_BWD_RECOMPUTE"); return e && e[0] == '1'; }();
@@ -1168,6 +1202,7 @@ static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision,
         attr_set = true;
     }
     BwdJob job = job_;
+    *quad_out = 0;
     const long long total = (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;
     const long long tiles = (total + TM - 1) / TM;
@@ -1185,7 +1220,7 @@ static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision,
         // NA_BWD_TMEM=0 keeps the forward-only stash launch + the SIMT / mma.sync backward kernel ("loaded mode")
         const bool bw_tmem = [] { const char* e = getenv("NA_BWD_TMEM"); return !(e && e[0] == '0'); }();
         if (bw_tmem && !fp32_bwd) {
-            e.bw = 1; e.bw_bg_mask = job.apply_bg;
+            e.bw = 1; e.bw_bg_mask = job.apply_bg; e.st_quad = 1; *quad_out = 1;
             e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
             e.st_emb = st.n(NP_EMB); e.st_vb0 = st.n(NP_VB0); e.st_t0 = st.t(0); e.st_t1 = st.t(1);
             return launch_mlp(e, packed, fwd_precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream);
@@ -1203,11 +1238,11 @@ static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision,
 }
 
 // weight-gradient GEMMs + bias column sums of one mlp_bwd launch
-static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int train_surface, int train_radiance, float* gp,
+static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int train_surface, int train_radiance, float* gp, int quad,
                         cudaStream_t stream) {
     const GradPack G = grad_layout();
-    WgradTable wt; wt.n = 0; wt.total_blocks = 0;
-    ColsumTable ct; ct.n = 0;
+    WgradTable wt; wt.n = 0; wt.total_blocks = 0; wt.quad = quad;
+    ColsumTable ct; ct.n = 0; ct.quad = quad;
     auto addw = [&](const float* Lp, int ldl, int nl, const float* Rp, int ldr, int nr, const float* L2, const float* R2, size_t out, int ldo) {
         WgradTask& t = wt.t[wt.n++];
         t.L = Lp; t.R = Rp; t.L2 = L2; t.R2 = R2; t.out = gp + out; t.ldl = ldl; t.ldr = ldr; t.nl = nl; t.nr = nr; t.ldo = ldo;
@@ -1295,24 +1330,25 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     job.rays_o = rays_o; job.rays_d = w.dirs; job.n_rows = (int)n; job.t = d_all; job.t_stride = P;
     job.multires_view = desc->multires_view; job.bound_r = desc->bounding_radius;
     const bool has_eik = cfg->w_eikonal != 0.f;
+    int quad = 0;                                   // set by launch_mlp_bwd: the stash planes of this launch are in the quad layout
     if (!neus) {
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = w.g_rad;
         job.apply_bg = 1; job.has_rad = 1;
-        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
-        NA_TRY(launch_wgrad(st, (long long)M, 1, cfg->train_surface, cfg->train_radiance, gp, stream));
+        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, &quad, stream));
+        NA_TRY(launch_wgrad(st, (long long)M, 1, cfg->train_surface, cfg->train_radiance, gp, quad, stream));
     } else {
         // pass A: the P points of d_all (sdf -> alpha, nabla -> eikonal); pass B: the P-1 midpoints (radiance), neus.py:320-324
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = nullptr;
         job.apply_bg = 0; job.has_rad = 0;
         const char* dbg_pass = getenv("NA_BWD_DEBUG_PASS");                 // diagnostics: "A" / "B" runs only that pass
         if (cfg->train_surface && !(dbg_pass && dbg_pass[0] == 'B')) {
-            NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
-            NA_TRY(launch_wgrad(st, (long long)M, 0, 1, 0, gp, stream));
+            NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, &quad, stream));
+            NA_TRY(launch_wgrad(st, (long long)M, 0, 1, 0, gp, quad, stream));
         }
         if (dbg_pass && dbg_pass[0] == 'A') return NA_OK;
         job.P = P - 1; job.midpoints = 1; job.g_sdf = nullptr; job.g_nab = nullptr; job.g_rad = w.g_rad; job.has_rad = 1;
-        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, stream));
-        NA_TRY(launch_wgrad(st, (long long)n * (P - 1), 1, cfg->train_surface, cfg->train_radiance, gp, stream));
+        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, &quad, stream));
+        NA_TRY(launch_wgrad(st, (long long)n * (P - 1), 1, cfg->train_surface, cfg->train_radiance, gp, quad, stream));
     }
     return NA_OK;
 }
