@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NA_LIB_PATH') or os.path.join(_HERE, 'libnerfart_b200.so')    # NA_LIB_PATH: diagnostic builds (scripts/build_trace.sh)
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu', 'train.cu', 'clip_vit.cu', 'tgemm.cu']
+SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu', 'train.cu', 'clip_vit.cu', 'tgemm.cu', 'wgrad_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--compiler-options', '-fPIC', '-shared']
 

@@ -148,4 +148,7 @@ constexpr int ST_VB = 24;       // 24..31 v-bar_{i+1}
 constexpr int ST_FB = 33;       // d L / d feature
 constexpr int ST_D = 38;        // 38..41 delta_0..3 of the radiance hidden layers
 
+// one 256 x 256 weight-gradient task of csrc/wgrad_tc.cu: out[l][r] += sum_m L[p][m][l] * R[p][m][r] over p < npair
+struct WgTcTask { const float* L[2]; const float* R[2]; float* out; int ldo; int npair; };
+
 }  // namespace na

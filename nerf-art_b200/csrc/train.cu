@@ -1166,6 +1166,7 @@ struct TrainWs {
     size_t total;
 };
 size_t mlp_scratch_bytes();                                                         // csrc/api.cu
+int launch_wgrad_tc(const WgTcTask* tasks, int n_tasks, long long m_tiles, cudaStream_t stream);        // csrc/wgrad_tc.cu
 int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream);
 static TrainWs train_ws(void* base, long long n_rays, int P) {
     const size_t M = (size_t)n_rays * P, mpad = (M + TM - 1) / TM * TM;
@@ -1243,7 +1244,14 @@ static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int trai
     const GradPack G = grad_layout();
     WgradTable wt; wt.n = 0; wt.total_blocks = 0; wt.quad = quad;
     ColsumTable ct; ct.n = 0; ct.quad = quad;
+    static const int wgrad_mode = [] { const char* e = getenv("NA_WGRAD"); return !e ? 0 : (strcmp(e, "fp32") == 0 ? 2 : (strcmp(e, "mma") == 0 ? 1 : 0)); }();
+    WgTcTask tc[16]; int n_tc = 0;                 // 256 x 256 tasks on wide quad-layout planes -> tcgen05 (csrc/wgrad_tc.cu)
     auto addw = [&](const float* Lp, int ldl, int nl, const float* Rp, int ldr, int nr, const float* L2, const float* R2, size_t out, int ldo) {
+        if (quad && wgrad_mode == 0 && ldl == 256 && ldr == 256 && nl == 256 && nr == 256 && n_tc < 16) {
+            WgTcTask& c = tc[n_tc++];
+            c.L[0] = Lp; c.R[0] = Rp; c.L[1] = L2; c.R[1] = R2; c.out = gp + out; c.ldo = ldo; c.npair = L2 ? 2 : 1;
+            return;
+        }
         WgradTask& t = wt.t[wt.n++];
         t.L = Lp; t.R = Rp; t.L2 = L2; t.R2 = R2; t.out = gp + out; t.ldl = ldl; t.ldr = ldr; t.nl = nl; t.nr = nr; t.ldo = ldo;
         t.blk0 = wt.total_blocks; t.nbr = (nr + 127) / 128;
@@ -1271,15 +1279,17 @@ static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int trai
         for (int l = 0; l < 4; ++l) addc(st.w(PL_D + l), 256, 256, G.rad_b[l]);
         addc(st.t(0), 4, 4, G.rad_b4);
     }
-    if (wt.n == 0) return NA_OK;
     const long long tiles = (m_rows + TM - 1) / TM;
+    if (n_tc) NA_TRY(launch_wgrad_tc(tc, n_tc, tiles, stream));
+    if (wt.n == 0 && ct.n == 0) return NA_OK;
     int splits = (int)((4LL * num_sms() + wt.total_blocks - 1) / wt.total_blocks);
     if (splits > tiles) splits = (int)tiles;
     if (splits < 1) splits = 1;
     const int rows_per_split = (int)(((tiles + splits - 1) / splits) * TM);
     const long long m_total = tiles * TM;
-    static const bool fp32_wgrad = [] { const char* e = getenv("NA_WGRAD"); return e && strcmp(e, "fp32") == 0; }();
-    if (fp32_wgrad) wgrad_kernel<<<dim3(wt.total_blocks, splits), 256, 0, stream>>>(wt, m_total, rows_per_split);
+    const bool fp32_wgrad = wgrad_mode == 2;
+    if (wt.n == 0) {}
+    else if (fp32_wgrad) wgrad_kernel<<<dim3(wt.total_blocks, splits), 256, 0, stream>>>(wt, m_total, rows_per_split);
     else            wgrad_tf32_kernel<<<dim3(wt.total_blocks, splits), 256, 0, stream>>>(wt, m_total, rows_per_split);
     NA_CHECK_LAUNCH();
     int csplits = (int)(tiles < 64 ? tiles : 64);

@@ -4,6 +4,7 @@ Everything here is pointer plumbing around `libnerfart_b200.so`; tensors are all
 caching allocator and the current stream are shared with the caller (train.py / render.py of the reference).
 """
 import ctypes as C
+import os
 import torch
 
 from . import _lib
@@ -71,6 +72,8 @@ class NetEngine:
         eval so that optimiser steps and load_state_dict are always reflected."""
         L = _lib.lib()
         dev = self._device()
+        if getattr(self, '_pack_held', False) and self.packed is not None and self.packed.device == dev:
+            return self.packed
         nbytes = L.na_packed_weights_bytes(C.byref(self.desc))
         if self.packed is None or self.packed.device != dev or self.packed.numel() * 4 < nbytes:
             self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
@@ -78,6 +81,22 @@ class NetEngine:
         with torch.cuda.device(dev):
             check(L.na_pack_weights(C.byref(self.desc), C.byref(raw), ptr(self.packed), stream_ptr(dev)), 'na_pack_weights')
         return self.packed
+
+    def hold_pack(self):
+        """Context manager: pack once now and skip the per-call repack inside (the caller guarantees the parameters do not change).
+        Not used by the training loop at present (see models/frameworks/_finetune.py::backward_patches)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def _held():
+            self._pack_held = False
+            self.pack()
+            self._pack_held = True
+            try:
+                yield self
+            finally:
+                self._pack_held = False
+        return _held()
 
     def workspace(self, nbytes):
         dev = self._device()

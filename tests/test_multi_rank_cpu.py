@@ -65,6 +65,10 @@ class _FakeEngine:
     def __init__(self):
         self.calls = []
 
+    def hold_pack(self):
+        import contextlib
+        return contextlib.nullcontext(self)
+
     def grad_zero(self):
         self._gpack = torch.zeros(4, dtype=torch.float64); self._gscal = torch.zeros(2, dtype=torch.float64)
 
