@@ -301,7 +301,12 @@ __device__ __forceinline__ void qstore16(uint4* base, int plane, int col0, int r
     for (int j8 = 0; j8 < 2; ++j8) {
         unsigned w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const __half2 h = __floats2half2_rn(v[8 * j8 + 2 * i], v[8 * j8 + 2 * i + 1]); w[i] = *reinterpret_cast<const unsigned*>(&h); }
+        for (int i = 0; i < 4; ++i) {
+            // x 2^-8: the parked terms reach 1e4 (100 g-bar g); the clamp keeps an outlier finite instead of turning the patch into NaN
+            const __half2 h = __floats2half2_rn(fminf(fmaxf(v[8 * j8 + 2 * i] * 0.00390625f, -65000.f), 65000.f),
+                                                fminf(fmaxf(v[8 * j8 + 2 * i + 1] * 0.00390625f, -65000.f), 65000.f));
+            w[i] = *reinterpret_cast<const unsigned*>(&h);
+        }
         p[(size_t)j8 * TM] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -312,7 +317,7 @@ __device__ __forceinline__ void qload16(const uint4* base, int plane, int col0, 
         const uint4 q = p[(size_t)j8 * TM];
         const unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x; v[8 * j8 + 2 * i + 1] = f.y; }
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x * 256.f; v[8 * j8 + 2 * i + 1] = f.y * 256.f; }
     }
 }
 // BW: 16 consecutive columns of this thread's row from a (quad-layout) stash plane it wrote earlier in the tile
@@ -573,6 +578,9 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
             }
+            // single-product fp16 operands: keep an outlier finite (|x rs| > 4e3 would round to inf)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], -65000.f), 65000.f);
         } else {
             // radiance hidden layers: relu(16 z)
 #pragma unroll

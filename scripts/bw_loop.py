@@ -22,12 +22,12 @@ hold = eng.hold_pack() if os.environ.get('BW_LOOP_HOLD') else contextlib.nullcon
 t0 = time.time()
 with hold:
   for k in range(n_patch):
-    i = 1200 * k
+    i = 1200 * (k % 108)
     rop, rdp = ro[0, i:i + 1200].contiguous(), rd[0, i:i + 1200].contiguous()
     fwd, ab = render_patch(m, rop, rdp, N_samples=128, N_importance=64, max_upsample_steps=6, perturb=False)
     G = 1e-3 * torch.randn(1200, 3, device=dev, generator=gen)
     eng.render_bwd(rop, rdp, ab, fwd, G, w_eikonal=0.1, eikonal_count=1200 * 192, white_bkgd=False, speed_factor=m.speed_factor)
-    if k % 5 == 4:
+    if k % 50 == 49:
         torch.cuda.synchronize(); print('patch', k, f'{time.time() - t0:.2f} s', flush=True)
 torch.cuda.synchronize()
 pairs, scal = eng.unpack_grads()
