@@ -147,8 +147,18 @@ typedef struct NaSurfaceOut {             /* return values of ray_casting.surfac
 int         na_version(void);
 const char* na_error_string(int code);
 int         na_last_cuda_error(void);                 /* cudaError_t of the last NA_ERR_CUDA on this thread */
-int64_t     na_kernel_launch_count(void);
-int         na_debug_set_buffer(void* dev_int64x8);   /* diagnostics: cycle counters of CTA 0 of the tensor-core MLP kernel */             /* kernels launched by this library since load (bench "gpu_launches") */
+int64_t     na_kernel_launch_count(void);             /* kernels launched by this library since load (bench "gpu_launches") */
+int         na_debug_set_buffer(void* dev_int64x8);   /* diagnostics: cycle counters of CTA 0 of the tensor-core MLP kernel */
+/* Load every kernel image of the library on the current device now instead of at each kernel's first launch (the driver's
+ * default is lazy loading).  The Python engine calls it once per device; C callers should do the same before the first step. */
+int         na_preload_kernels(void);
+/* Stall diagnostics.  Every mbarrier wait of the tcgen05 kernels is bounded (8 s): a wait that can never complete ends the
+ * launch with a trap, i.e. a CUDA error, instead of blocking the stream forever.  na_diag_enable(1) additionally records, in
+ * host-mapped memory, per-launch CTA counters and every timed-out wait; na_diag_enable(2) also keeps an event per kernel launch
+ * (names the first launch that never finished); na_diag_enable(0) switches both off.  na_diag_dump
+ * writes a text report (<= cap bytes; returns the length) and may be called from a watchdog thread while a stream is stuck. */
+int         na_diag_enable(int on);
+int         na_diag_dump(char* buf_host, int cap);
 
 /* ---- weights: replaces nn.utils.weight_norm's per-forward W = g*v/||v|| (models/base.py:226-227,365-366) */
 size_t na_packed_weights_bytes(const NaNetDesc* desc);

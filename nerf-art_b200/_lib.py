@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get('NA_LIB_PATH') or os.path.join(_HERE, 'libnerfart_b200
 CSRC = os.path.join(_HERE, 'csrc')
 SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu', 'train.cu', 'clip_vit.cu', 'tgemm.cu', 'wgrad_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--compiler-options', '-fPIC', '-shared']
+              '--compiler-options', '-fPIC']
+LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '--compiler-options', '-fPIC']
 
 NA_FRAMEWORK_VOLSDF, NA_FRAMEWORK_NEUS = 0, 1
 NA_PRECISION_FP32, NA_PRECISION_TC, NA_PRECISION_TC2ACC, NA_PRECISION_TC_MIXED = 0, 1, 2, 3
@@ -76,17 +77,35 @@ class NaRawGrads(C.Structure):
 
 
 def build(verbose=False):
-    """Compile csrc/*.cu for sm_100a into libnerfart_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into libnerfart_b200.so (nvcc cross-compiles without a GPU).  One object per source,
+    compiled in parallel and rebuilt only when the source or a header changed; objects live in nerf-art_b200/build/ (git-ignored)."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + \
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + \
         [os.path.join(_HERE, '..', 'include', 'nerfart_b200.h')]
-    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + srcs
-    if verbose:
-        print(' '.join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    extra = os.environ.get('NA_NVCC_EXTRA', '').split()
+    objdir = os.path.join(_HERE, 'build' + ('_' + '_'.join(e.strip('-').replace('=', '_') for e in extra) if extra else ''))
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_time):
+            return obj, False
+        cmd = [nvcc] + NVCC_FLAGS + extra + ['-c', '-o', obj, src]
+        if verbose:
+            print(' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj, True
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(compile_one, srcs))
+    objs = [o for o, _ in res]
+    if any(c for _, c in res) or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        cmd = [nvcc] + LINK_FLAGS + ['-o', LIB_PATH] + objs
+        if verbose:
+            print(' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, cwd=CSRC)
     return LIB_PATH
 
 
@@ -106,6 +125,10 @@ def lib():
         L.na_error_string.argtypes = [C.c_int]
         L.na_last_cuda_error.restype = C.c_int
         L.na_kernel_launch_count.restype = C.c_int64
+        L.na_preload_kernels.restype = C.c_int
+        L.na_diag_enable.argtypes = [C.c_int]
+        L.na_diag_dump.argtypes = [C.c_char_p, C.c_int]
+        L.na_diag_dump.restype = C.c_int
         L.na_packed_weights_bytes.restype = C.c_size_t
         L.na_packed_weights_bytes.argtypes = [C.POINTER(NaNetDesc)]
         L.na_pack_weights.argtypes = [C.POINTER(NaNetDesc), C.POINTER(NaRawParams), C.c_void_p, C.c_void_p]
@@ -173,6 +196,32 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def diag_enable(level=1):
+    """Stall diagnostics (csrc/common.cuh).  1: per-launch CTA counters + a record of every timed-out mbarrier wait in
+    host-mapped memory; 2: also an event per kernel launch (names the first launch that never finished); 0: off."""
+    check(lib().na_diag_enable(int(level)), 'na_diag_enable')
+
+
+def diag_dump():
+    """Text report of na_diag_dump: callable from a watchdog thread while the stream is stuck, and after a launch failure."""
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().na_diag_dump(buf, len(buf))
+    return buf.raw[:n].decode(errors='replace')
+
+
+_preloaded = set()
+
+
+def preload_kernels(device):
+    """Force-load every kernel image of the library on `device` once (na_preload_kernels)."""
+    idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if idx in _preloaded:
+        return
+    with torch.cuda.device(idx):
+        check(lib().na_preload_kernels(), 'na_preload_kernels')
+    _preloaded.add(idx)
 
 
 def launch_count():

@@ -3,12 +3,45 @@
 #include "sampler.cuh"
 #include <atomic>
 #include <mutex>
+#include <cstdio>
+#include <cstring>
 
 namespace na {
 
 thread_local int g_last_cuda_error = 0;
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- stall diagnostics (common.cuh) -------------------------------------------------------------
+int g_diag_on = 0;
+static HangDiag* g_diag_host = nullptr;          // pinned, mapped
+static HangDiag* g_diag_dev = nullptr;
+static std::atomic<unsigned long long> g_diag_seq{0};
+constexpr int DIAG_RING = 8192;
+struct DiagMark { cudaEvent_t ev; const char* file; int line; unsigned long long n; };
+static DiagMark g_marks[DIAG_RING];
+static std::atomic<unsigned long long> g_mark_n{0};
+static std::mutex g_diag_mu;
+
+void diag_mark(const char* file, int line, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_diag_mu);
+    const unsigned long long n = g_mark_n.load();
+    DiagMark& m = g_marks[n % DIAG_RING];
+    if (!m.ev && cudaEventCreateWithFlags(&m.ev, cudaEventDisableTiming) != cudaSuccess) { m.ev = nullptr; cudaGetLastError(); return; }
+    if (cudaEventRecord(m.ev, stream) != cudaSuccess) { cudaGetLastError(); return; }
+    m.file = file; m.line = line; m.n = n;
+    g_mark_n.store(n + 1);
+}
+
+SpinCtx diag_next(int kernel, int grid) {
+    SpinCtx sc; sc.seq = g_diag_seq.fetch_add(1); sc.kernel = kernel; sc.diag = nullptr;
+    if (g_diag_on && g_diag_host) {
+        HangSlot& s = g_diag_host->slot[sc.seq % HANG_SLOTS];
+        s.seq = sc.seq; s.kernel = kernel; s.grid = grid; s.started = s.ready = s.finished = 0;
+        sc.diag = g_diag_dev;
+    }
+    return sc;
+}
 
 int num_sms() {
     static int cached[64] = {0};
@@ -135,6 +168,57 @@ extern "C" const char* na_error_string(int code) {
     }
 }
 extern "C" int na_last_cuda_error(void) { return g_last_cuda_error; }
+
+
+// Stall diagnostics (see common.cuh).  na_diag_enable(1): host-mapped record buffer + per-launch CTA counters; (2): also an event per launch.
+extern "C" int na_diag_enable(int on) {
+    if (on && !g_diag_host) {
+        void* h = nullptr; void* d = nullptr;
+        NA_TRY(check_cuda(cudaHostAlloc(&h, sizeof(HangDiag), cudaHostAllocMapped)));
+        memset(h, 0, sizeof(HangDiag));
+        NA_TRY(check_cuda(cudaHostGetDevicePointer(&d, h, 0)));
+        g_diag_host = (HangDiag*)h; g_diag_dev = (HangDiag*)d;
+    }
+    g_diag_on = on < 0 ? 0 : (on > 2 ? 2 : on);
+    return NA_OK;
+}
+// Text report: timed-out waits, tcgen05 launches whose CTAs have not all finished, and the oldest kernel launch (file:line of its
+// NA_CHECK_LAUNCH) whose completion event is still pending.  Safe to call from another host thread while the stream is stuck,
+// and after a trap (reads host memory and queries events only).  Returns the number of bytes written.
+extern "C" int na_diag_dump(char* buf, int cap) {
+    if (!buf || cap <= 0) return 0;
+    int o = 0;
+    auto put = [&](const char* fmt, auto... a) { if (o < cap - 1) { int w = snprintf(buf + o, (size_t)(cap - o), fmt, a...); if (w > 0) o += w < cap - o ? w : cap - o - 1; } };
+    if (!g_diag_host) { put("%s", "diagnostics not enabled\n"); return o; }
+    const HangDiag& D = *g_diag_host;
+    const unsigned nrec = D.n_rec < (unsigned)HANG_RECS ? D.n_rec : (unsigned)HANG_RECS;
+    put("timed-out waits: %u\n", D.n_rec);
+    for (unsigned i = 0; i < nrec; ++i) {
+        const HangRec& r = D.rec[i];
+        put("  seq %llu kernel %d block %d warp %d lane %d tag 0x%08x parity %u waited %.2f s\n", r.seq, r.kernel, r.block, r.warp, r.lane, r.tag, r.parity, r.waited_ns * 1e-9);
+    }
+    put("tcgen05 launches issued: %llu; unfinished:\n", g_diag_seq.load());
+    for (int i = 0; i < HANG_SLOTS; ++i) {
+        const HangSlot& s = D.slot[i];
+        if (s.kernel && s.finished != (unsigned)s.grid)
+            put("  seq %llu kernel %d grid %d started %u ready %u finished %u\n", s.seq, s.kernel, s.grid, s.started, s.ready, s.finished);
+    }
+    const unsigned long long n = g_mark_n.load();
+    const unsigned long long lo = n > DIAG_RING ? n - DIAG_RING : 0;
+    put("kernel launches traced: %llu\n", n);
+    int shown = 0;
+    for (unsigned long long k = lo; k < n && shown < 6; ++k) {
+        const DiagMark& m = g_marks[k % DIAG_RING];
+        if (!m.ev || m.n != k) continue;
+        const cudaError_t q = cudaEventQuery(m.ev);
+        if (q == cudaSuccess) continue;
+        const char* f = m.file; for (const char* c = m.file; *c; ++c) if (*c == '/') f = c + 1;
+        put("  pending launch #%llu at %s:%d (%s)\n", k, f, m.line, q == cudaErrorNotReady ? "not ready" : cudaGetErrorName(q));
+        ++shown;
+    }
+    cudaGetLastError();
+    return o;
+}
 extern "C" int64_t na_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
 
 static size_t pack_scale_off(const PackF32& L) { return (L.total + 63) / 64 * 64; }
@@ -347,4 +431,20 @@ extern "C" int na_sample_pdf(const float* bins, const float* weights, int64_t ro
 extern "C" int na_sample_cdf(const float* bins, const float* cdf, int64_t rows, int n, const float* u, int u_per_row, int n_out,
                              float* samples, int64_t* inds, void* stream) {
     return sample_rows(bins, cdf, rows, n, 0, u, u_per_row, n_out, samples, inds, stream);
+}
+
+namespace na {
+int preload_mlp_simt(); int preload_mlp_tc(); int preload_mlp_tmem(); int preload_wgrad_tc(); int preload_tgemm(); int preload_train();
+int preload_volsdf(); int preload_neus(); int preload_surface();
+namespace clipv { int preload_clip(); }
+}
+// Load every kernel image of the library on the current device now (cudaFuncGetAttributes forces the load) instead of at each
+// kernel's first launch.  Called once per device when an engine is created: with the driver's default lazy module loading the
+// first training step otherwise interleaves dozens of module loads with running persistent kernels.
+extern "C" int na_preload_kernels(void) {
+    NA_PRELOAD(wn_scale_kernel); NA_PRELOAD(pack_fill_kernel); NA_PRELOAD(get_rays_kernel);
+    NA_PRELOAD(error_bound_rows_kernel); NA_PRELOAD(sample_rows_kernel);
+    NA_TRY(preload_mlp_simt()); NA_TRY(preload_mlp_tc()); NA_TRY(preload_mlp_tmem()); NA_TRY(preload_wgrad_tc()); NA_TRY(preload_tgemm());
+    NA_TRY(preload_train()); NA_TRY(preload_volsdf()); NA_TRY(preload_neus()); NA_TRY(preload_surface()); NA_TRY(clipv::preload_clip());
+    return NA_OK;
 }

@@ -8,6 +8,8 @@
 // warp-per-row LayerNorm forward/backward, one CTA per (image, head) attention forward/backward over the 50 tokens,
 // im2col / col2im for the non-overlapping patches.  Activations the backward needs are kept in the caller's workspace.
 #include "common.cuh"
+#undef NA_DIAG_STREAM
+#define NA_DIAG_STREAM s
 
 namespace na {
 namespace clipv {
@@ -322,6 +324,20 @@ static int ln_bwd(const float* dy, const float* x, size_t stride, const float* w
                   size_t ostride, int rows, cudaStream_t s) {
     ln_bwd_kernel<<<(rows + 3) / 4, 128, 0, s>>>(dy, x, stride, w, stats, dres, dx, ostride, rows);
     NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
+int preload_clip() {
+    NA_PRELOAD((sgemm_kernel<true>));
+    NA_PRELOAD((sgemm_kernel<false>));
+    NA_PRELOAD(ln_fwd_kernel);
+    NA_PRELOAD(ln_bwd_kernel);
+    NA_PRELOAD(attn_fwd_kernel);
+    NA_PRELOAD(attn_bwd_kernel);
+    NA_PRELOAD(qgelu_bwd_kernel);
+    NA_PRELOAD(im2col_kernel);
+    NA_PRELOAD(tokens_kernel);
+    NA_PRELOAD(tokens_bwd_kernel);
     return NA_OK;
 }
 

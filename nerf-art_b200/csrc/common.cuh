@@ -16,13 +16,78 @@ inline int check_cuda(cudaError_t e) {
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return NA_ERR_CUDA; }
     return NA_OK;
 }
+// NA_DIAG_STREAM: the name of the launch stream at the NA_CHECK_LAUNCH() site (launch-trace diagnostics, below)
+#define NA_DIAG_STREAM stream
 #define NA_CHECK_LAUNCH()                                                     \
     do { na::count_launch();                                                  \
          cudaError_t _e = cudaGetLastError();                                 \
-         if (_e != cudaSuccess) { na::g_last_cuda_error = (int)_e; return NA_ERR_CUDA; } } while (0)
+         if (_e != cudaSuccess) { na::g_last_cuda_error = (int)_e; return NA_ERR_CUDA; } \
+         if (na::g_diag_on >= 2) na::diag_mark(__FILE__, __LINE__, (cudaStream_t)(NA_DIAG_STREAM)); } while (0)
 #define NA_TRY(x) do { int _r = (x); if (_r != NA_OK) return _r; } while (0)
+#define NA_PRELOAD(k) do { cudaFuncAttributes _a; NA_TRY(na::check_cuda(cudaFuncGetAttributes(&_a, k))); } while (0)
 
 int num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// Stall diagnostics.  Every mbarrier wait of the tcgen05 kernels is bounded (SPIN_LIMIT_NS of wall clock, %globaltimer): a wait
+// that can never complete ends the launch with a trap -- a CUDA error the caller sees -- instead of blocking the stream forever.
+// With na_diag_enable(1) the kernels additionally keep per-launch CTA counters and a record of every timed-out wait in
+// host-mapped pinned memory (readable after the trap, and from a watchdog thread while the GPU is stuck), and the host side
+// keeps an event per kernel launch so that the first launch that never finished can be named (na_diag_dump).
+// ---------------------------------------------------------------------------------------------
+struct HangRec { unsigned long long seq; int kernel, block, warp, lane; unsigned tag, parity; unsigned long long waited_ns; };
+struct HangSlot { unsigned long long seq; int kernel, grid; unsigned started, ready, finished, pad; };
+constexpr int HANG_SLOTS = 64, HANG_RECS = 48;
+struct HangDiag { unsigned n_rec, pad; HangRec rec[HANG_RECS]; HangSlot slot[HANG_SLOTS]; };
+struct SpinCtx { HangDiag* diag; unsigned long long seq; int kernel; };
+enum DiagKernel { DK_MLP_TMEM = 1, DK_WGRAD_TC = 2, DK_TGEMM = 3, DK_MLP_TC = 4 };
+constexpr unsigned long long SPIN_LIMIT_NS = 8000000000ull;
+extern int g_diag_on;                                 // 0 off, 1 device-side records + CTA counters, 2 + an event per kernel launch
+void diag_mark(const char* file, int line, cudaStream_t stream);
+SpinCtx diag_next(int kernel, int grid);               // host: sequence number + (when enabled) a fresh slot for the next launch
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+static __device__ __noinline__ void spin_timeout(const SpinCtx sc, unsigned tag, unsigned parity, unsigned long long waited) {
+    if (sc.diag && (threadIdx.x & 31) == 0) {
+        const unsigned i = atomicAdd_system(&sc.diag->n_rec, 1u);
+        if (i < (unsigned)HANG_RECS) {
+            HangRec& r = sc.diag->rec[i];
+            r.seq = sc.seq; r.kernel = sc.kernel; r.block = (int)(blockIdx.x + gridDim.x * blockIdx.y); r.warp = (int)(threadIdx.x >> 5);
+            r.lane = (int)(threadIdx.x & 31); r.tag = tag; r.parity = parity; r.waited_ns = waited;
+        }
+        __threadfence_system();
+    }
+    // leave the other stuck warps of the grid time to file their own records before the trap takes the context down
+    const unsigned long long t0 = global_ns();
+    while (global_ns() - t0 < 500000000ull) __nanosleep(1000000);
+    __trap();
+}
+__device__ __forceinline__ unsigned mbar_try_wait_(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// bounded mbarrier wait; `tag` names the wait site in the diagnostics (role << 24 | ...)
+__device__ __forceinline__ void mbar_wait_guarded(unsigned bar, unsigned parity, const SpinCtx& sc, unsigned tag) {
+    if (mbar_try_wait_(bar, parity)) return;
+    unsigned polls = 0; unsigned long long t0 = 0;
+    while (!mbar_try_wait_(bar, parity)) {
+        if ((++polls & 0x3ffu) == 0) {
+            const unsigned long long t = global_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > SPIN_LIMIT_NS) spin_timeout(sc, tag, parity, t - t0);
+        }
+    }
+}
+__device__ __forceinline__ void diag_count(const SpinCtx& sc, int which) {       // 0 started, 1 ready (TMEM allocated), 2 finished
+    if (sc.diag && threadIdx.x == 0) {
+        HangSlot& s = sc.diag->slot[sc.seq % HANG_SLOTS];
+        atomicAdd_system(which == 0 ? &s.started : (which == 1 ? &s.ready : &s.finished), 1u);
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // network geometry (fixed; NaNetDesc documents where it comes from)

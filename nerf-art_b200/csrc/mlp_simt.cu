@@ -303,4 +303,9 @@ int launch_mlp_simt(const EvalJob& job, const float* packed, const PackF32& L, f
     return NA_OK;
 }
 
+int preload_mlp_simt() {
+    NA_PRELOAD(mlp_simt_kernel);
+    return NA_OK;
+}
+
 }  // namespace na

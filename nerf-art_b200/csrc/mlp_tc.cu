@@ -773,4 +773,14 @@ int launch_mlp_tc(const EvalJob& job_, const unsigned char* packed_base, size_t 
     return NA_OK;
 }
 
+int preload_mlp_tc() {
+    NA_PRELOAD((mlp_tc_kernel<false, false>));
+    NA_PRELOAD((mlp_tc_kernel<true, false>));
+    NA_PRELOAD((mlp_tc_kernel<false, true>));
+    NA_PRELOAD((mlp_tc_kernel<true, true>));
+    NA_PRELOAD(plane_absmax_kernel);
+    NA_PRELOAD(tc_pack_kernel);
+    return NA_OK;
+}
+
 }  // namespace na

@@ -80,7 +80,6 @@ __device__ __forceinline__ unsigned mbar_try_wait(unsigned bar, unsigned parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -202,6 +201,7 @@ struct EpiCtx {
     uint4* qp;                      // BW: per-CTA fp16 scratch planes
     int bw;
     unsigned d_phase; long long* t_wait; long long* trace;
+    SpinCtx sc;
 };
 
 // this warp's part of K-block kb of the next A operand is in TMEM (and its part of D columns [64kb, 64kb+64) is consumed)
@@ -377,7 +377,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         {                                                            // pass c16 reads N-quarter c16 of D
             const long long t0 = clock64();
-            mbar_wait(c.d_bar + 8u * (unsigned)c16, c.d_phase);
+            mbar_wait_guarded(c.d_bar + 8u * (unsigned)c16, c.d_phase, c.sc, 0x45000000u | ((unsigned)c.g << 8) | (unsigned)c16);
             *c.t_wait += clock64() - t0;
             tc_fence_after();
             NA_TRACE_E(c.trace, c.g, c16, 0);
@@ -640,14 +640,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar, c16, c.lane);
     }
-    for (int k = N_PASS; k < 4; ++k) mbar_wait(c.d_bar + 8u * (unsigned)k, c.d_phase);      // keep the other barriers' phases in step
+    for (int k = N_PASS; k < 4; ++k) mbar_wait_guarded(c.d_bar + 8u * (unsigned)k, c.d_phase, c.sc, 0x45800000u | ((unsigned)c.g << 8) | (unsigned)k);      // keep the other barriers' phases in step
     if (N_PASS < 4) tc_fence_after();
 }
 
 template <bool FULL, bool ST, bool BW>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
-                const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch) {
+                const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch, const SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -662,6 +662,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.kb_ready[k]), EPI_THREADS / 32);   // one arrive per epilogue warp
         fence_barrier_init();
     }
+    diag_count(sc, 0);
     if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), 512);
     // bias rows and head weights -> shared memory (hidden-layer biases pre-multiplied by ACT_SCALE)
     for (int i = tid; i < N_BIAS_ROWS * 256; i += THREADS) {
@@ -680,6 +681,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_d = S.tmem_base;
+    diag_count(sc, 1);
 
     if (warp == 0) {
         // ================= weight producer =================
@@ -693,7 +695,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     for (int kb = 0; kb < n_kb; ++kb)
                         for (int sp = 0; sp < n_sp; ++sp, ++it) {
                             const unsigned slot = it % NS, ph = (it / NS) & 1;
-                            mbar_wait(smem_u32(&S.empty_bar[slot]), ph ^ 1);
+                            mbar_wait_guarded(smem_u32(&S.empty_bar[slot]), ph ^ 1, sc, 0x50000000u | ((unsigned)g << 8) | slot);
                             mbar_expect_tx(smem_u32(&S.full_bar[slot]), sb);
                             bulk_g2s(smem_u32(S.Wst + slot * STAGE_BYTES), src + (size_t)(kb * 2 + sp) * sb, sb, smem_u32(&S.full_bar[slot]));
                         }
@@ -720,10 +722,10 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     // the weights first (the ring runs K-blocks ahead, so these return at once), then the A operand: the MMAs go out
                     // right behind the epilogue's signal
                     { const long long t0 = clock64();
-                      mbar_wait(smem_u32(&S.full_bar[slot0]), ph0);
-                      if (prods == 3) mbar_wait(smem_u32(&S.full_bar[slot1]), ph1);
+                      mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
+                      if (prods == 3) mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
                       t_full += clock64() - t0; }
-                    { const long long t0 = clock64(); mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase); t_a += clock64() - t0; }
+                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
                     tc_fence_after();
                     NA_TRACE_M(tr, g, kb, 0);
                     if (elect_one()) {
@@ -770,7 +772,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     it += prods == 3 ? 2 : 1;
                     NA_TRACE_M(tr, g, kb, 1);
                 }
-                for (int kb = n_kb; kb < 4; ++kb) mbar_wait(smem_u32(&S.kb_ready[kb]), a_phase);     // keep the phases in step
+                for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);     // keep the phases in step
                 a_phase ^= 1;
                 if (prog.g[g].n64) {
                     if (elect_one()) { for (int k = 0; k < 4; ++k) umma_commit(smem_u32(&S.d_ready[k])); }
@@ -790,7 +792,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.sdim = small_dim(job.multires_view);
         c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4); c.radw_s = smem_u32(S.RADW);
         c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
-        c.d_phase = 0;
+        c.d_phase = 0; c.sc = sc;
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
         c.st_m = 0; c.st_quad = job.st_quad;
@@ -1112,6 +1114,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 512); }
+    diag_count(sc, 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1258,11 +1261,22 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     if (scratch_bytes < mlp_tmem_scratch_bytes(grid)) return NA_ERR_WORKSPACE;
     const float* usc = (const float*)(image + T.unscale_off);
     if (job.st_wide && !job.want_full) return NA_ERR_BAD_ARG;
-    if (job.bw)             mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
-    else if (job.st_wide)   mlp_tmem_kernel<true, true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
-    else if (job.want_full) mlp_tmem_kernel<true, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
-    else                    mlp_tmem_kernel<false, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch);
+    const SpinCtx sc = diag_next(DK_MLP_TMEM, grid);
+    if (job.bw)             mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else if (job.st_wide)   mlp_tmem_kernel<true, true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else if (job.want_full) mlp_tmem_kernel<true, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else                    mlp_tmem_kernel<false, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
+int preload_mlp_tmem() {
+    NA_PRELOAD((tm::mlp_tmem_kernel<false, false, false>));
+    NA_PRELOAD((tm::mlp_tmem_kernel<true, false, false>));
+    NA_PRELOAD((tm::mlp_tmem_kernel<true, true, false>));
+    NA_PRELOAD((tm::mlp_tmem_kernel<true, true, true>));
+    NA_PRELOAD(tm::pack_kernel);
+    NA_PRELOAD(tm::absmax_kernel);
     return NA_OK;
 }
 

@@ -204,6 +204,13 @@ static NeusWs neus_ws_layout(const NaNeusCfg& c, long long n_rays) {
     return w;
 }
 
+int preload_neus() {
+    NA_PRELOAD(neus_init_kernel);
+    NA_PRELOAD(neus_upsample_kernel);
+    NA_PRELOAD(neus_composite_kernel);
+    return NA_OK;
+}
+
 }  // namespace na
 
 using namespace na;

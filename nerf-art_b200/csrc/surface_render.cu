@@ -207,6 +207,18 @@ static int ray_cast(const NaNetDesc* desc, const void* packed, const NaSurfaceCf
     return NA_OK;
 }
 
+int preload_surface() {
+    NA_PRELOAD(march_depths_kernel);
+    NA_PRELOAD(root_scan_kernel);
+    NA_PRELOAD(secant_update_kernel);
+    NA_PRELOAD(root_finalize_kernel);
+    NA_PRELOAD(sphere_init_kernel);
+    NA_PRELOAD(sphere_step_kernel);
+    NA_PRELOAD(sphere_points_kernel);
+    NA_PRELOAD(surface_finish_kernel);
+    return NA_OK;
+}
+
 }  // namespace na
 
 using namespace na;

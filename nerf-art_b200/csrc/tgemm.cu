@@ -43,7 +43,6 @@ __device__ __forceinline__ unsigned mbar_try_wait(unsigned bar, unsigned parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -105,7 +104,7 @@ struct __align__(1024) Smem {
 
 __global__ void __launch_bounds__(THREADS, 1)
 tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg, float* __restrict__ C, int M, int N, int K,
-             const float* __restrict__ bias, float* __restrict__ C_raw, int act, const float* __restrict__ R, int kb_per_split) {
+             const float* __restrict__ bias, float* __restrict__ C_raw, int act, const float* __restrict__ R, int kb_per_split, const SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -119,11 +118,13 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
         mbar_init(smem_u32(&S.acc_ready), 1);
         fence_barrier_init();
     }
+    diag_count(sc, 0);
     if (warp == 1) tmem_alloc(smem_u32(&S.tmem_base), 64);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_d = S.tmem_base;
+    diag_count(sc, 1);
 
     if (warp == 0) {
         // ---- weight producer: one 8 KB tile per stage
@@ -131,7 +132,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
             const unsigned char* src = Bimg + ((size_t)n_tile * nkb_total + kb0) * B_BYTES;
             for (int i = 0; i < nkb; ++i) {
                 const unsigned slot = i % NST, ph = (i / NST) & 1;
-                mbar_wait(smem_u32(&S.empty[slot]), ph ^ 1);
+                mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, sc, 0x50000000u | (unsigned)i);
                 mbar_expect_tx(smem_u32(&S.full[slot]), B_BYTES);
                 bulk_g2s(smem_u32(S.B[slot]), src + (size_t)i * B_BYTES, B_BYTES, smem_u32(&S.full[slot]));
             }
@@ -140,7 +141,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
         // ---- MMA issuer
         for (int i = 0; i < nkb; ++i) {
             const unsigned slot = i % NST, ph = (i / NST) & 1;
-            mbar_wait(smem_u32(&S.full[slot]), ph);
+            mbar_wait_guarded(smem_u32(&S.full[slot]), ph, sc, 0x4d000000u | (unsigned)i);
             tc_fence_after();
             if (elect_one()) {
                 const unsigned long long ad = umma_desc(smem_u32(S.A[slot])), bd = umma_desc(smem_u32(S.B[slot]));
@@ -162,7 +163,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
         for (int i = 0; i < nkb + AHEAD; ++i) {
             if (i < nkb) {
                 const unsigned slot = i % NST, ph = (i / NST) & 1;
-                mbar_wait(smem_u32(&S.empty[slot]), ph ^ 1);
+                mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, sc, 0x4c000000u | (unsigned)i);
                 const unsigned dst = smem_u32(S.A[slot]) + dst_row;
                 if (live) {
 #pragma unroll
@@ -179,7 +180,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
                 mbar_arrive(smem_u32(&S.full[(i - AHEAD) % NST]));
             }
         }
-        mbar_wait(smem_u32(&S.acc_ready), 0);
+        mbar_wait_guarded(smem_u32(&S.acc_ready), 0, sc, 0x45000000u);
         tc_fence_after();
         const unsigned t_lane = tmem_d + ((unsigned)(32 * q) << 16);
         const bool split = gridDim.z > 1, lead = blockIdx.z == 0;
@@ -229,6 +230,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 64); }
+    diag_count(sc, 2);
 }
 
 // src: fp32 [rows][cols] row-major.  transpose == 0: operand Bt[n][k] = src[n][k] (N = rows, K = cols);
@@ -283,8 +285,14 @@ int tgemm(const float* A, const unsigned char* img, float* C, int M, int N, int 
     const int kb_per_split = (nkb + splits - 1) / splits;
     splits = (nkb + kb_per_split - 1) / kb_per_split;
     if (splits > 1) NA_TRY(check_cuda(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), stream)));
-    tgemm_kernel<<<dim3(n_tiles, m_tiles, splits), THREADS, smem, stream>>>(A, img, C, M, N, K, bias, raw, act, R, kb_per_split);
+    tgemm_kernel<<<dim3(n_tiles, m_tiles, splits), THREADS, smem, stream>>>(A, img, C, M, N, K, bias, raw, act, R, kb_per_split, diag_next(DK_TGEMM, n_tiles * m_tiles * splits));
     NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
+int preload_tgemm() {
+    NA_PRELOAD(tg::tgemm_kernel);
+    NA_PRELOAD(tg::pack_tiles_kernel);
     return NA_OK;
 }
 

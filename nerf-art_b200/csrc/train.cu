@@ -1299,6 +1299,21 @@ static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int trai
     return NA_OK;
 }
 
+int preload_train() {
+    NA_PRELOAD((mlp_bwd_kernel<true, false>));
+    NA_PRELOAD((mlp_bwd_kernel<false, false>));
+    NA_PRELOAD((mlp_bwd_kernel<true, true>));
+    NA_PRELOAD((mlp_bwd_kernel<false, true>));
+    NA_PRELOAD(wgrad_kernel);
+    NA_PRELOAD(wgrad_tf32_kernel);
+    NA_PRELOAD(colsum_kernel);
+    NA_PRELOAD(unpack_grads_kernel);
+    NA_PRELOAD(volsdf_composite_bwd_kernel);
+    NA_PRELOAD(neus_composite_bwd_kernel);
+    NA_PRELOAD(normalize_dirs_train_kernel);
+    return NA_OK;
+}
+
 }  // namespace na
 
 using namespace na;

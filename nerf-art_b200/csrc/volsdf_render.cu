@@ -276,6 +276,14 @@ static VolsdfWs volsdf_ws_layout(const NaVolsdfCfg& c, long long n_rays) {
     return w;
 }
 
+int preload_volsdf() {
+    NA_PRELOAD(normalize_dirs_kernel);
+    NA_PRELOAD(init_depths_kernel);
+    NA_PRELOAD(volsdf_sampler_kernel);
+    NA_PRELOAD(volsdf_composite_kernel);
+    return NA_OK;
+}
+
 }  // namespace na
 
 using namespace na;

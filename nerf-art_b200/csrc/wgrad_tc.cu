@@ -37,7 +37,6 @@ __device__ __forceinline__ unsigned mbar_try_wait(unsigned bar, unsigned parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -95,7 +94,7 @@ __device__ __forceinline__ unsigned op_addr(unsigned base, int row, int k) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-wgrad_tc_kernel(const Table tab) {
+wgrad_tc_kernel(const Table tab, const SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -110,14 +109,17 @@ wgrad_tc_kernel(const Table tab) {
         mbar_init(smem_u32(&S.acc_ready), 1);
         fence_barrier_init();
     }
+    diag_count(sc, 0);
     if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_d = S.tmem_base;
+    diag_count(sc, 1);
     if (n_stage <= 0) {                                                    // uniform: nothing to do for this split
         __syncthreads();
         if (warp == 0) tmem_dealloc(tmem_d, 512);
+        diag_count(sc, 2);
         return;
     }
 
@@ -125,7 +127,7 @@ wgrad_tc_kernel(const Table tab) {
         // ---- MMA issuer: per stage 4 K-steps x 2 accumulators
         for (int i = 0; i < n_stage; ++i) {
             const unsigned slot = i % NST, ph = (i / NST) & 1;
-            mbar_wait(smem_u32(&S.full[slot]), ph);
+            mbar_wait_guarded(smem_u32(&S.full[slot]), ph, sc, 0x4d000000u | (unsigned)(i & 0xffffff));
             tc_fence_after();
             if (elect_one()) {
                 const unsigned base = smem_u32(S.st[slot]);
@@ -161,7 +163,7 @@ wgrad_tc_kernel(const Table tab) {
         for (int i = 0; i < n_stage; ++i) {
             if (i + 1 < n_stage) gload(i + 1, nxt);
             const unsigned slot = i % NST, ph = (i / NST) & 1;
-            mbar_wait(smem_u32(&S.empty[slot]), ph ^ 1);
+            mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, sc, 0x4c000000u | (unsigned)(i & 0xffffff));
             const unsigned base = smem_u32(S.st[slot]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -182,7 +184,7 @@ wgrad_tc_kernel(const Table tab) {
             for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
         }
         // ---- epilogue: warp lw reads TMEM lanes 32 * (warp % 4) .., columns 128 * (lw / 4) .. + 128 of the 512
-        mbar_wait(smem_u32(&S.acc_ready), 0);
+        mbar_wait_guarded(smem_u32(&S.acc_ready), 0, sc, 0x45000000u);
         tc_fence_after();
         const int q = warp & 3, cs = lw >> 2;                              // cs 0,1 -> accumulator 0 (l < 128), 2,3 -> accumulator 1
         const int l = 32 * q + lane + (cs >= 2 ? 128 : 0);
@@ -201,6 +203,7 @@ wgrad_tc_kernel(const Table tab) {
     tc_fence_before();
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_d, 512); }
+    diag_count(sc, 2);
 }
 
 }  // namespace wg
@@ -226,8 +229,13 @@ int launch_wgrad_tc(const WgTcTask* tasks, int n_tasks, long long m_tiles, cudaS
     if (splits > m_tiles) splits = (int)m_tiles;
     tab.tiles_per_split = (int)((m_tiles + splits - 1) / splits);
     splits = (int)((m_tiles + tab.tiles_per_split - 1) / tab.tiles_per_split);
-    wgrad_tc_kernel<<<dim3(n_tasks, splits), THREADS, smem, stream>>>(tab);
+    wgrad_tc_kernel<<<dim3(n_tasks, splits), THREADS, smem, stream>>>(tab, diag_next(DK_WGRAD_TC, n_tasks * splits));
     NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+
+int preload_wgrad_tc() {
+    NA_PRELOAD(wg::wgrad_tc_kernel);
     return NA_OK;
 }
 

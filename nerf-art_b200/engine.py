@@ -72,6 +72,8 @@ class NetEngine:
         eval so that optimiser steps and load_state_dict are always reflected."""
         L = _lib.lib()
         dev = self._device()
+        if os.environ.get('NA_PRELOAD', '1') != '0':
+            _lib.preload_kernels(dev)              # once per device: every kernel image is resident before the first launch
         if getattr(self, '_pack_held', False) and self.packed is not None and self.packed.device == dev:
             return self.packed
         nbytes = L.na_packed_weights_bytes(C.byref(self.desc))

@@ -178,42 +178,59 @@ class RadianceNet(nn.Module):
 # optimiser / scheduler helpers the reference's train.py imports from models.base (base.py:486-584)
 # ---------------------------------------------------------------------------------------------------
 def get_optimizer(args, model):
-    """Adam over model.parameters() with args.training.lr (number) or a per-child dict of learning rates."""
+    """reference base.py:486-521.  args.training.lr is a number (one Adam group) or a dict: 'default' plus keys naming a direct
+    parameter of the model (e.g. ln_beta / ln_s) or a child module; the default group comes FIRST in optimizer.param_groups (the
+    order reference optimizer checkpoints are saved with); an unknown key raises RuntimeError('wrong lr key:', name)."""
+    import numbers
     from torch import optim
     lr = args.training.lr
-    if isinstance(lr, (int, float)):
-        return optim.Adam(model.parameters(), lr=float(lr))
-    if isinstance(lr, dict):
-        groups, default_lr = [], lr.pop('default')
-        named = dict(model.named_children())
-        used = set()
-        for name, value in lr.items():
-            if name not in named:
-                raise RuntimeError('wrong lr key:', name)
-            groups.append({'params': named[name].parameters(), 'lr': value}); used.add(name)
-        rest = [p for n, m in named.items() if n not in used for p in m.parameters()]
-        rest += [p for n, p in model.named_parameters(recurse=False)]
-        groups.append({'params': rest})
-        return optim.Adam(groups, lr=default_lr)
-    raise NotImplementedError
+    if isinstance(lr, numbers.Number):
+        return optim.Adam(model.parameters(), lr=lr)
+    if not isinstance(lr, dict):
+        raise NotImplementedError
+    default_lr = lr.pop('default')
+    groups, taken = [], set()
+    for key, value in lr.items():
+        if key in model._parameters:
+            taken.add(key)
+            groups.append({'params': getattr(model, key), 'lr': value})
+        elif key in model._modules:
+            child = getattr(model, key)
+            taken.update(f'{key}.{n}' for n, _ in child.named_parameters())
+            groups.append({'params': child.parameters(), 'lr': value})
+        else:
+            raise RuntimeError('wrong lr key:', key)
+    rest = [p for n, p in model.named_parameters() if n not in taken]
+    return optim.Adam(params=[{'params': rest, 'lr': default_lr}] + groups, lr=default_lr)
+
+
+def _warmup_cosine(total_steps, warmup_steps, min_factor):
+    """reference CosineAnnealWarmUpSchedulerLambda, base.py:524-535."""
+    assert 0 <= min_factor < 1
+
+    def factor(it):
+        if it < warmup_steps:
+            return it / warmup_steps
+        return min_factor + (1 - min_factor) * 0.5 * (np.cos(np.pi * (it - warmup_steps) / (total_steps - warmup_steps)) + 1.0)
+    return factor
+
+
+def _exponential_step(total_steps, min_factor):
+    """reference ExponentialSchedulerLambda, base.py:538-544: min_factor ** clip(it / total, 0, 1)."""
+    assert 0 <= min_factor < 1
+    return lambda it: np.exp(np.clip(it / total_steps, 0, 1) * np.log(min_factor))
 
 
 def get_scheduler(args, optimizer, last_epoch=-1):
-    """exponential_step / multistep / warmupcosine as selected by args.training.scheduler.type."""
+    """reference base.py:547-584: 'multistep' | 'warmupcosine' | 'exponential_step' from args.training.scheduler; min_factor defaults
+    to 0.1 through setdefault (so it also appears in the saved config); like the reference, 'exponential_step' ignores last_epoch."""
     from torch.optim import lr_scheduler
     sc = args.training.scheduler
-    stype = sc.type
-    if stype == 'multistep':
+    if sc.type == 'multistep':
         return lr_scheduler.MultiStepLR(optimizer, sc.milestones, gamma=sc.gamma, last_epoch=last_epoch)
-    if stype == 'exponential_step':
-        num_iters, min_factor = args.training.num_iters, sc.min_factor
-        return lr_scheduler.LambdaLR(optimizer, lambda it: min_factor ** (it / num_iters), last_epoch=last_epoch)
-    if stype == 'warmupcosine':
-        num_iters, warm, min_factor = args.training.num_iters, sc.warmup_steps, sc.setdefault('min_factor', 0.1) if hasattr(sc, 'setdefault') else 0.1
-
-        def fn(it):
-            if it < warm:
-                return it / max(warm, 1)
-            return min_factor + 0.5 * (1 - min_factor) * (1 + math.cos(math.pi * min((it - warm) / max(num_iters - warm, 1), 1.0)))
-        return lr_scheduler.LambdaLR(optimizer, fn, last_epoch=last_epoch)
-    raise NotImplementedError(stype)
+    if sc.type == 'warmupcosine':
+        return lr_scheduler.LambdaLR(optimizer, _warmup_cosine(args.training.num_iters, sc.warmup_steps, sc.setdefault('min_factor', 0.1)),
+                                     last_epoch=last_epoch)
+    if sc.type == 'exponential_step':
+        return lr_scheduler.LambdaLR(optimizer, _exponential_step(args.training.num_iters, sc.setdefault('min_factor', 0.1)))
+    raise NotImplementedError

@@ -181,6 +181,42 @@ class Trainer(nn.Module):
         return OrderedDict([('losses', losses), ('extras', extras)])
 
 
+    def val(self, logger, ret, to_img_fn, it, render_kwargs_test):
+        """reference Trainer.val (volsdf.py:840-876): two TensorBoard figures from the detailed validation render -- the per-ray
+        beta heat map and the number of upsampling iterations each ray used (iter_usage == -1, never converged, is shown as
+        max_upsample_steps + 1).  Host-side logging of the caller (train.py:205-206); needs matplotlib and the reference's
+        utils.io_util.gallery (train.py's own tree)."""
+        import matplotlib.pyplot as plt
+        from utils import io_util
+
+        def tiled(per_ray):                                     # [B,N,1] -> gallery of the B validation images, [H',W',1]
+            maps = to_img_fn(per_ray).permute(0, 2, 3, 1).data.cpu().numpy()
+            return io_util.gallery(maps, int(np.sqrt(maps.shape[0])))
+
+        def heat_map(img, lo, hi, ticks, labels, tag):
+            fig = plt.figure(figsize=(5, 3), dpi=100)
+            ax = fig.add_subplot(111)
+            bar = fig.colorbar(ax.imshow(img, vmin=lo, vmax=hi), ticks=ticks)
+            bar.ax.set_yticklabels(labels)
+            logger.add_figure(fig, tag, it)
+
+        beta_map = tiled(ret['beta_map'])
+        beta = self.model.forward_ab()[1].data.cpu().numpy().item()
+        beta_max = beta_map.max().item()
+        ticks = np.linspace(beta, beta_max, 10).tolist() if beta_max != beta else [beta]
+        labels = ['{:.4f}'.format(b) for b in ticks]
+        labels[0] = 'beta={:.4f}'.format(beta)
+        heat_map(beta_map, beta, beta_max, ticks, labels, 'val/beta_heat_map')
+
+        max_iter = render_kwargs_test['max_upsample_steps']
+        usage = tiled(ret['iter_usage'].unsqueeze(-1))
+        usage[usage == -1] = max_iter + 1
+        ticks = list(range(max_iter + 2))
+        labels = ['{:d}'.format(b) for b in ticks]
+        labels[-1] = 'not converged'
+        heat_map(usage, 0, max_iter + 1, ticks, labels, 'val/upsample_iters')
+
+
 def get_model(args, render_target=None):
     """reference volsdf.get_model, volsdf.py:943-994: same defaults injected into `args`, same five-tuple."""
     model_config = {
