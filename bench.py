@@ -8,8 +8,11 @@ compositing).  metric value = n_rays * 192 / t  (SURVEY.md 8d "full-MLP samples/
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|tc]
 Multi-GPU: launched by torchrun, one rank per GPU; the rays of ONE frame are block-partitioned over the ranks (strong
 scaling) and the rendered RGB tiles are all-gathered over NCCL at the end of every step (north star).
-`--impl reference` times the CPU oracle port (oracle/nerfart_oracle.py; the reference is Python and cannot travel to
-the GPU box) on the host cores, on a bounded ray sample of the same frame.
+`--impl reference` times the UNMODIFIED reference's own `volume_render` (PyTorch, CPU, all host threads) on a bounded strided ray
+sample of the same frame; the reference tree travels to the GPU box as oracle/_ref/reference (oracle/build_ref.sh).  Where no
+staged copy exists the numpy oracle port (oracle/nerfart_oracle.py) is timed instead and the line says kind "port".
+The main line additionally carries `reference_gpu`: the same unmodified reference code on the same B200 (plain PyTorch CUDA),
+on every 8th ray of the frame -- the "before" number BASELINE.md asks for -- with the rgb L-inf between the two renders.
 """
 import argparse
 import json
@@ -33,8 +36,16 @@ P = N_SAMPLES + N_IMPORTANCE
 # matmul MACs x 2.  SDF-only evaluations skip the unused 256-wide feature head (918 016 instead of 1 049 088).
 F_SDF = 2 * (39 * 256 + 256 * 256 * 2 + 256 * 217 + 256 * 256 * 4 + 256)
 F_FULL = 2 * (524544 + 459008 + 265216)
-# measured DRAM bytes per sample (SDF-only, full) of the MLP kernel by precision mode -- profiles/r1n_tmem_v2.md
-TRAFFIC_B_PER_SAMPLE = {'tc': (14568448 / 1048576, (134657024 + 492769280) / 262144)}
+
+
+def traffic_capture():
+    """DRAM bytes per sample (SDF-only, full) of the MLP kernel from the dated `ncu --set full` capture committed under profiles/
+    (dram__bytes_read.sum + dram__bytes_write.sum per launch / samples per launch); None when no capture file is present."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'traffic_capture.json')))
+    except Exception:
+        return None
+
 RENDER_KW = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=False, white_bkgd=False,
                  max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, epsilon=0.1, max_bisection_steps=10,
                  require_nablas=True, calc_normal=True, detailed_output=False)
@@ -96,6 +107,30 @@ def make_inputs():
     return c2w, K
 
 
+REF_KW = dict(RENDER_KW, rayschunk=2048)                 # render.py:488,614: rayschunk default 2048
+
+
+def reference_baseline(n_rays_sample, device='cpu', stride_sel=None):
+    """The UNMODIFIED reference's volume_render (oracle/ref_runner.py) on a strided ray sample of the same frame, on `device`.
+    Returns (samples/s, seconds, rgb [n,3] numpy, selected ray indices) or None when no reference tree is staged."""
+    import ref_runner
+    import fixtures as fx
+    from helpers import make_volsdf
+    if ref_runner.reference_root() is None:
+        return None
+    torch.set_num_threads(os.cpu_count())
+    model = ref_runner.build_model('volsdf', make_volsdf(0.1, 0.0).state_dict(), fx.volsdf_kwargs(0.1), device=device)
+    c2w, K = make_inputs()
+    rr = ref_runner.load()['rend_util']
+    ro, rd, _ = rr.get_rays(c2w[None].to(device), K[None].to(device), H, W, -1)
+    sel = np.linspace(0, H * W - 1, n_rays_sample).astype(np.int64) if stride_sel is None else stride_sel
+    st = torch.as_tensor(sel, device=device)
+    if device != 'cpu':                                   # warm-up on a small slice (cuBLAS / allocator start-up is not the reference's cost)
+        ref_runner.volume_render('volsdf', model, ro[:, st[:256]], rd[:, st[:256]], **REF_KW)
+    rgb, _, _, dt = ref_runner.volume_render('volsdf', model, ro[:, st], rd[:, st], **REF_KW)
+    return len(sel) * P / dt, dt, rgb[0].detach().cpu().numpy(), sel
+
+
 def cpu_baseline(n_rays_sample, repeats=1):
     """The oracle port on the host cores, on a strided ray sample of the same frame.  Returns (samples/s, seconds)."""
     import nerfart_oracle as orc
@@ -119,18 +154,22 @@ def run_reference(args, rank, world):
         return
     n_sample = 256
     times = []
+    import ref_runner
+    kind = 'reference' if ref_runner.reference_root() is not None else 'port'
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_baseline(n_sample)
+        dt = reference_baseline(n_sample)[1] if kind == 'reference' else cpu_baseline(n_sample)[1]
         if i >= args.warmup:
             times.append(dt)
     t = float(np.sum(times))
     value = n_sample * P * args.steps / t
+    what = ("the unmodified reference's volume_render (PyTorch fp32, CPU, rayschunk 2048)" if kind == 'reference'
+            else 'numpy+BLAS fp32 oracle port of the reference (no staged reference tree)')
     line = {'impl': 'reference', 'metric': 'MLP samples/sec (VolSDF 480x270x128)', 'value': value, 'unit': 'samples/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, extra={'sample': f'{n_sample} of {H*W} rays (strided), same 128+64 samples/ray'}),
-            'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
-                             'sample': f'{n_sample} strided rays of the 480x270 frame per step, numpy+BLAS fp32 oracle port of the reference'},
+            'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': kind,
+                             'sample': f'{n_sample} strided rays of the 480x270 frame per step, {what}'},
             'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -274,10 +313,12 @@ def main():
         peak = pk['bf16_tflops']
         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/r1n_tmem_v2.md:
         # dram__bytes_read.sum + dram__bytes_write.sum = 13.9 B/sample SDF-only, 5.5 KB/sample full), scaled to this launch size.
-        traffic = TRAFFIC_B_PER_SAMPLE.get(os.environ.get('NA_PRECISION', 'tc'))
+        cap = traffic_capture()
+        traffic = None if cap is None or cap.get('precision') != args.precision else (cap['sdf_only_bytes_per_sample'], cap['full_bytes_per_sample'])
         roof = {'bound': 'tensor', 'kernel': 'mlp kernel, SDF-only mode', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': ach / peak, 'traffic': None if traffic is None else traffic[0] * m,
-                'traffic_src': 'profiles/r2e_tmem_v3.md (ncu --set full, bytes/sample x samples_per_launch)', 'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
+                'traffic_src': None if traffic is None else f"profiles/traffic_capture.json: {cap['source']} ({cap['date']}); bytes/sample x samples_per_launch",
+                'peak_kind': f'{pk_kind} bf16 burst (MEASURED_PEAKS.json)',
                 'flop_per_sample': F_SDF, 'samples_per_launch': m, 'launch_ms': t_k * 1e3,
                 'full_mode': {'traffic': None if traffic is None else traffic[1] * (m // 4), 'achieved': (m // 4) * F_FULL / t_f / 1e12, 'flop_per_sample': F_FULL, 'launch_ms': t_f * 1e3,
                               'frac': (m // 4) * F_FULL / t_f / 1e12 / peak},
@@ -285,13 +326,28 @@ def main():
                 'frame_frac_of_peak': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL) / (t_dev / args.steps) / 1e12 / peak / world}
         del x, v
     cpu = None
+    ref_gpu = None
     if rank == 0 and not args.no_cpu_baseline:
         import nerfart_oracle as orc
         from helpers import oracle_net
         n_cpu = 512
-        v, dt = cpu_baseline(n_cpu)
-        cpu = {'value': v, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': f'{n_cpu} strided rays of the same frame ({dt:.1f} s), numpy+BLAS fp32 oracle port of the reference'}
+        rb = reference_baseline(n_cpu)
+        if rb is not None:
+            cpu = {'value': rb[0], 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                   'sample': f"{n_cpu} strided rays of the same frame ({rb[1]:.1f} s), the unmodified reference's volume_render (PyTorch fp32, CPU)",
+                   'rgb_linf_vs_reference': float(np.abs(img[torch.as_tensor(rb[3], device=dev)].cpu().numpy() - rb[2]).max())}
+            # the same unmodified reference code on this B200 (plain PyTorch CUDA): every 8th ray of the frame
+            sel8 = np.arange(0, n_rays, 8, dtype=np.int64)
+            rg = reference_baseline(len(sel8), device=str(dev), stride_sel=sel8)
+            ref_gpu = {'value': rg[0], 'unit': 'samples/s', 'kind': 'reference', 'device': torch.cuda.get_device_name(dev),
+                       'sample': f'every 8th ray of the frame ({len(sel8)} rays, {rg[1]:.2f} s), unmodified reference PyTorch CUDA path, rayschunk 2048',
+                       'ms_per_frame_extrapolated': 1e3 * rg[1] * n_rays / len(sel8),
+                       'rgb_linf_ours_vs_reference_gpu': float(np.abs(img[torch.as_tensor(sel8, device=dev)].cpu().numpy() - rg[2]).max())}
+            torch.cuda.empty_cache()
+        else:
+            v, dt = cpu_baseline(n_cpu)
+            cpu = {'value': v, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                   'sample': f'{n_cpu} strided rays of the same frame ({dt:.1f} s), numpy+BLAS fp32 oracle port of the reference'}
         # parity spot check of the rendered frame on the same sample (reported, not timed)
         sel = np.linspace(0, n_rays - 1, n_cpu).astype(np.int64)
         ro, rd = orc.get_rays(c2w_h.numpy(), K_h.numpy(), H, W)
@@ -306,7 +362,7 @@ def main():
                 'all_evals_per_s': n_rays * (4 * N_SAMPLES + P) * args.steps / t_dev,
                 'e2e': {'value': samples / t_e2e, 'unit': 'samples/s', 'ms_per_step': 1e3 * t_e2e / args.steps,
                         'h2d_bytes_per_step': 2 * 16 * 4, 'd2h_bytes_per_step': n_rays * 3 * 4},
-                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu}
+                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

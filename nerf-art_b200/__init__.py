@@ -8,13 +8,6 @@ contract name `nerf-art_b200`).  Layout:
 """
 import os
 
-# Load every kernel image when the CUDA context is created instead of at each kernel's first launch.  With the driver's default
-# (lazy) loading, the first fine-tune step of a process -- dozens of first launches of persistent tcgen05 kernels back to back --
-# intermittently stopped making progress on B200 (profiles/r2w_train_backward.md); eager loading is the pre-CUDA-11.7 behaviour
-# and costs a little start-up time.  Only a default: an explicit CUDA_MODULE_LOADING wins, and it has no effect if the process
-# initialised CUDA before importing this package.
-os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')
-
 from . import _lib                                   # noqa: F401
 from ._lib import build, lib, launch_count           # noqa: F401
 

@@ -4,12 +4,11 @@ kernels (clip_vit.py), one text-feature cache (text.py), the three CLIP losses (
 `build_loss_dict(target_hw, device)` returns what the reference's Trainer builds at volsdf.py:639-645.  It needs the
 third-party `clip` package and its ViT-B/32 weights (README.md:27; fetched by `clip.load` on first use) for the TEXT tower
 and as the source of the image-tower weights; offline neither exists, and this function raises instead of substituting
-anything.  `torchvision`'s pretrained VGG16 (criteria/perp_loss.py) is outside the kernel scope: it
-is used as is when its weights are available, else the perceptual term is dropped with a warning.
+anything.  The VGG16 perceptual term (criteria/perp_loss.py) is `perceptual.VGGPerceptualLoss` (cuDNN convolutions, SURVEY.md 8f
+rank 3); it raises when the ImageNet weights cannot be found -- the term is never dropped silently.
 """
-import warnings
-
 from .clip_vit import ClipVisionB32
+from .perceptual import VGGPerceptualLoss                                         # noqa: F401
 from .text import TextFeatures
 from .losses import CLIPLoss, ContrastiveLoss, PatchNCELoss, DirectionLoss       # noqa: F401
 
@@ -30,10 +29,5 @@ def build_loss_dict(target_hw, device):
     model = model.float().eval()
     tower = ClipVisionB32.from_openai(model, device)
     text = TextFeatures(lambda strings: model.encode_text(clip.tokenize(strings).to(device)))
-    perceptual = None
-    try:
-        from criteria.perp_loss import VGGPerceptualLoss        # the reference's module, unchanged (out of kernel scope)
-        perceptual = VGGPerceptualLoss().to(device)
-    except Exception as e:                                       # pragma: no cover
-        warnings.warn(f'perceptual (VGG16) loss unavailable, term dropped: {e}')
+    perceptual = VGGPerceptualLoss().to(device)                 # raises when the VGG16 weights are unavailable (see perceptual.py)
     return make_loss_dict(tower, text, target_hw, perceptual)

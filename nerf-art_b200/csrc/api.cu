@@ -200,7 +200,7 @@ extern "C" int na_diag_dump(char* buf, int cap) {
     put("tcgen05 launches issued: %llu; unfinished:\n", g_diag_seq.load());
     for (int i = 0; i < HANG_SLOTS; ++i) {
         const HangSlot& s = D.slot[i];
-        if (s.kernel && s.finished != (unsigned)s.grid)
+        if (s.kernel && s.finished != (unsigned)s.grid && s.seq + HANG_SLOTS > g_diag_seq.load())
             put("  seq %llu kernel %d grid %d started %u ready %u finished %u\n", s.seq, s.kernel, s.grid, s.started, s.ready, s.finished);
     }
     const unsigned long long n = g_mark_n.load();

@@ -37,7 +37,7 @@ int num_sms();
 // ---------------------------------------------------------------------------------------------
 struct HangRec { unsigned long long seq; int kernel, block, warp, lane; unsigned tag, parity; unsigned long long waited_ns; };
 struct HangSlot { unsigned long long seq; int kernel, grid; unsigned started, ready, finished, pad; };
-constexpr int HANG_SLOTS = 64, HANG_RECS = 48;
+constexpr int HANG_SLOTS = 1024, HANG_RECS = 48;
 struct HangDiag { unsigned n_rec, pad; HangRec rec[HANG_RECS]; HangSlot slot[HANG_SLOTS]; };
 struct SpinCtx { HangDiag* diag; unsigned long long seq; int kernel; };
 enum DiagKernel { DK_MLP_TMEM = 1, DK_WGRAD_TC = 2, DK_TGEMM = 3, DK_MLP_TC = 4 };
@@ -46,7 +46,7 @@ extern int g_diag_on;                                 // 0 off, 1 device-side re
 void diag_mark(const char* file, int line, cudaStream_t stream);
 SpinCtx diag_next(int kernel, int grid);               // host: sequence number + (when enabled) a fresh slot for the next launch
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && (!defined(__CUDA_ARCH__) || __CUDA_ARCH__ >= 900)
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 static __device__ __noinline__ void spin_timeout(const SpinCtx sc, unsigned tag, unsigned parity, unsigned long long waited) {
     if (sc.diag && (threadIdx.x & 31) == 0) {

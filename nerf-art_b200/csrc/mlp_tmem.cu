@@ -59,7 +59,10 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 
 enum BwOp { OP_FWD = 0, OP_DR, OP_FB, OP_HB, OP_SO, OP_TR };      // OP_FWD: forward program, dispatched on the program index
 struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, img, op, lyr, pad0, pad1; };   // img: weight image (unscale index)
-struct Program { int n_gemm; int nsplit; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
+struct Program { int n_gemm; int nsplit; int corr_first; float debias; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
+// corr_first: three-product GEMMs accumulate the two small correction products of ALL K-blocks first and the hi*hi products last, so that
+// only 16 of the layer's 48 accumulator updates happen at full magnitude (the tensor core's fp32 accumulate truncates: the error grows
+// linearly with the number of full-magnitude updates); costs a second load of each W_hi stage.  debias: see launch_mlp_tmem.
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -378,6 +381,11 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         {                                                            // pass c16 reads N-quarter c16 of D
             const long long t0 = clock64();
             mbar_wait_guarded(c.d_bar + 8u * (unsigned)c16, c.d_phase, c.sc, 0x45000000u | ((unsigned)c.g << 8) | (unsigned)c16);
+            if (N_PASS < 4) {
+                // a GEMM whose epilogue reads fewer than four N-quarters (the 64-wide reverse GEMM 0: its four d_ready commits are
+                // issued together): consume the other phases here, before anything is signalled to the MMA warp
+                for (int k = N_PASS; k < 4; ++k) mbar_wait_guarded(c.d_bar + 8u * (unsigned)k, c.d_phase, c.sc, 0x45800000u | ((unsigned)c.g << 8) | (unsigned)k);
+            }
             *c.t_wait += clock64() - t0;
             tc_fence_after();
             NA_TRACE_E(c.trace, c.g, c16, 0);
@@ -640,8 +648,6 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar, c16, c.lane);
     }
-    for (int k = N_PASS; k < 4; ++k) mbar_wait_guarded(c.d_bar + 8u * (unsigned)k, c.d_phase, c.sc, 0x45800000u | ((unsigned)c.g << 8) | (unsigned)k);      // keep the other barriers' phases in step
-    if (N_PASS < 4) tc_fence_after();
 }
 
 template <bool FULL, bool ST, bool BW>
@@ -692,13 +698,15 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     const unsigned char* src = wimg + prog.g[g].w_off;
                     const unsigned sb = prog.g[g].stage_bytes;
                     const int n_kb = prog.g[g].n_kb, n_sp = prog.g[g].prods == 3 ? 2 : 1;
-                    for (int kb = 0; kb < n_kb; ++kb)
-                        for (int sp = 0; sp < n_sp; ++sp, ++it) {
-                            const unsigned slot = it % NS, ph = (it / NS) & 1;
-                            mbar_wait_guarded(smem_u32(&S.empty_bar[slot]), ph ^ 1, sc, 0x50000000u | ((unsigned)g << 8) | slot);
-                            mbar_expect_tx(smem_u32(&S.full_bar[slot]), sb);
-                            bulk_g2s(smem_u32(S.Wst + slot * STAGE_BYTES), src + (size_t)(kb * 2 + sp) * sb, sb, smem_u32(&S.full_bar[slot]));
-                        }
+                    // stage sequence: [hi(kb) | lo(kb)] per K-block; with corr_first the hi stages of a three-product GEMM follow once more
+                    const int n_seq = n_kb * n_sp + ((prog.corr_first && n_sp == 2) ? n_kb : 0);
+                    for (int q = 0; q < n_seq; ++q, ++it) {
+                        const int st = q < n_kb * n_sp ? (n_sp == 2 ? q : 2 * q) : 2 * (q - n_kb * n_sp);      // stage index in the image: 2 kb + {0 hi, 1 lo}
+                        const unsigned slot = it % NS, ph = (it / NS) & 1;
+                        mbar_wait_guarded(smem_u32(&S.empty_bar[slot]), ph ^ 1, sc, 0x50000000u | ((unsigned)g << 8) | slot);
+                        mbar_expect_tx(smem_u32(&S.full_bar[slot]), sb);
+                        bulk_g2s(smem_u32(S.Wst + slot * STAGE_BYTES), src + (size_t)st * sb, sb, smem_u32(&S.full_bar[slot]));
+                    }
                 }
         }
     } else if (warp == 1) {
@@ -715,7 +723,70 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 const int n_kb = prog.g[g].n_kb, prods = prog.g[g].prods;
                 const unsigned idesc = prog.g[g].n64 ? IDESC_N64 : IDESC_N256;
                 const unsigned t_in = tmem_d + (unsigned)(g & 1) * 256u, t_out = tmem_d + (unsigned)((g + 1) & 1) * 256u;
-                for (int kb = 0; kb < n_kb; ++kb) {
+                // A GEMM with fewer than four K-blocks (the 39-wide encoding inputs, n_kb == 1) still gets all four kb_ready barriers
+                // signalled by its producer stage (tile-input stage / write_vbar0, all four at once).  Those phases must be consumed
+                // BEFORE this GEMM's MMAs are issued: once D is committed the epilogue starts signalling the same barriers for the
+                // next GEMM, and a second completion before this warp's wait flips the parity back -- the wait would then never
+                // return (mbarrier phase aliasing; this was the intermittent first-step stall, profiles/r3a_stall_root_cause.md).
+                for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);
+                const bool corr_first = prog.corr_first && prods == 3;
+                if (corr_first) {
+                    // ---- phase A: lo*hi and hi*lo of every K-block, as the K-blocks of A arrive (stages [W_hi | W_lo])
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        const unsigned slot0 = it % NS, ph0 = (it / NS) & 1, slot1 = (it + 1) % NS, ph1 = ((it + 1) / NS) & 1;
+                        const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
+                        { const long long t0 = clock64();
+                          mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
+                          mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
+                          t_full += clock64() - t0; }
+                        { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                        tc_fence_after();
+                        NA_TRACE_M(tr, g, kb, 0);
+                        if (elect_one()) {
+                            const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES), bd1 = umma_desc(wst + slot1 * STAGE_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks + 8u, bd0 + 2 * ks, idesc, (kb | ks) != 0);     // lo * hi
+                            umma_commit(smem_u32(&S.empty_bar[slot0]));
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd1 + 2 * ks, idesc, 1);                       // hi * lo
+                            umma_commit(smem_u32(&S.empty_bar[slot1]));
+                        }
+                        __syncwarp();
+                        it += 2;
+                        NA_TRACE_M(tr, g, kb, 1);
+                    }
+                    // ---- phase B: hi*hi of every K-block on top (W_hi stages again); the last one in N-parts with their own commits
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        const unsigned slot0 = it % NS, ph0 = (it / NS) & 1;
+                        const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
+                        { const long long t0 = clock64();
+                          mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d050000u | ((unsigned)g << 8) | (unsigned)kb);
+                          t_full += clock64() - t0; }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES);
+                            if (kb + 1 < n_kb || prog.g[g].n64) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_out, a_hi + 16u * ks, bd0 + 2 * ks, idesc, 1);
+                            } else {
+                                const int nsp = prog.nsplit;
+                                const unsigned ncol = 256u / (unsigned)nsp, idn = nsp == 4 ? IDESC_N64 : IDESC_N128;
+                                for (int np = 0; np < nsp; ++np) {
+                                    const unsigned t_dn = t_out + ncol * np;
+                                    const unsigned long long b0 = bd0 + (unsigned long long)(np * (int)(ncol * 128u / 16u));
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b0 + 2 * ks, idn, 1);
+                                    if (nsp == 4) umma_commit(smem_u32(&S.d_ready[np]));
+                                    else { umma_commit(smem_u32(&S.d_ready[2 * np])); umma_commit(smem_u32(&S.d_ready[2 * np + 1])); }
+                                }
+                            }
+                            umma_commit(smem_u32(&S.empty_bar[slot0]));
+                        }
+                        __syncwarp();
+                        it += 1;
+                    }
+                }
+                for (int kb = 0; kb < (corr_first ? 0 : n_kb); ++kb) {
                     const unsigned slot0 = it % NS, ph0 = (it / NS) & 1;
                     const unsigned slot1 = (it + 1) % NS, ph1 = ((it + 1) / NS) & 1;
                     const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
@@ -772,7 +843,6 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     it += prods == 3 ? 2 : 1;
                     NA_TRACE_M(tr, g, kb, 1);
                 }
-                for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);     // keep the phases in step
                 a_phase ^= 1;
                 if (prog.g[g].n64) {
                     if (elect_one()) { for (int k = 0; k < 4; ++k) umma_commit(smem_u32(&S.d_ready[k])); }
@@ -875,6 +945,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
             }
             for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
+            epi_bar_sync();                                   // EMBS / X / V / BWV of this tile: written above by other warps, read from GEMM 3 on
 
             float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
             float small_in[36];
@@ -897,6 +968,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
             for (int g = 0; g < prog.n_gemm; ++g) {
                 const int op = BW ? (int)prog.g[g].op : (int)OP_FWD;
                 c.g = g; c.us = unscale[prog.g[g].img];          // us = 2^-(weight shift) / ACT_SCALE
+                if (prog.g[g].prods == 3) c.us *= prog.debias;
                 c.lyr = prog.g[g].lyr;
                 c.signal = g + 1 < prog.n_gemm;
                 c.need_lo = c.signal ? (prog.g[g + 1].prods == 3) : 0;
@@ -1233,6 +1305,12 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     Program prog; prog.n_gemm = 0;
     static const char* nsplit_env = getenv("NA_TM_NSPLIT");                   // diagnostics: "2" = N-halves (the r1n scheme), default quarters
     prog.nsplit = (nsplit_env && nsplit_env[0] == '2') ? 2 : 4;
+    // NA_TM_ORDER=0: K-block-interleaved products (the r2 scheme).  NA_TM_DEBIAS=<x>: experimental multiplicative compensation of the
+    // accumulate truncation of three-product GEMMs, D *= 1 + x * 2^-24 (0 = off)
+    static const char* order_env = getenv("NA_TM_ORDER");
+    static const char* debias_env = getenv("NA_TM_DEBIAS");
+    prog.corr_first = (order_env && order_env[0] == '0') ? 0 : 1;
+    prog.debias = 1.f + (debias_env ? (float)atof(debias_env) : 0.f) * 5.9604645e-8f;
     const int last = !job.want_full ? (job.feat ? 8 : 7) : (job.rad ? 20 : 16);
     for (int g = 0; g <= last; ++g) {
         Gemm t; t.w_off = T.w_off[g]; t.stage_bytes = (unsigned)T.N[g] * 128u; t.n_kb = (unsigned char)T.n_kb[g];

@@ -32,6 +32,7 @@ class NetEngine:
         self.desc = NaNetDesc(NA_FRAMEWORK_VOLSDF if framework == 'volsdf' else NA_FRAMEWORK_NEUS,
                               int(multires_view), float(bounding_radius), 0.0)
         self.packed = None
+        self._pack_key = None
         self._ws = None
         self._dummy = None
         from . import default_precision
@@ -68,37 +69,30 @@ class NetEngine:
         return raw, keep
 
     def pack(self):
-        """Fold weight-norm etc. into the GEMM-ready planes.  Cheap (2 launches); called at the start of every render /
-        eval so that optimiser steps and load_state_dict are always reflected."""
+        """Fold weight-norm etc. into the GEMM-ready planes (na_pack_weights, 7 launches).  Called at the start of every render /
+        eval, but the launches are issued only when the parameters changed since the last pack: every parameter tensor's
+        (data_ptr, torch version counter) and the launch stream are compared -- optimiser steps, load_state_dict and .to() all bump one --
+        so a 90-view render.py run or the 109 renders of one fine-tune step pack once.  `invalidate()` forces a re-pack after
+        writes torch cannot see (e.g. a foreign kernel writing through data_ptr)."""
         L = _lib.lib()
         dev = self._device()
         if os.environ.get('NA_PRELOAD', '1') != '0':
             _lib.preload_kernels(dev)              # once per device: every kernel image is resident before the first launch
-        if getattr(self, '_pack_held', False) and self.packed is not None and self.packed.device == dev:
+        raw, keep = self._raw_params()
+        key = (str(dev), torch.cuda.current_stream(dev).cuda_stream) + tuple((t.data_ptr(), t._version) for t in keep)
+        if self.packed is not None and self.packed.device == dev and key == self._pack_key and os.environ.get('NA_PACK_ALWAYS') != '1':
             return self.packed
         nbytes = L.na_packed_weights_bytes(C.byref(self.desc))
         if self.packed is None or self.packed.device != dev or self.packed.numel() * 4 < nbytes:
             self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
-        raw, keep = self._raw_params()
         with torch.cuda.device(dev):
             check(L.na_pack_weights(C.byref(self.desc), C.byref(raw), ptr(self.packed), stream_ptr(dev)), 'na_pack_weights')
+        self._pack_key = key
         return self.packed
 
-    def hold_pack(self):
-        """Context manager: pack once now and skip the per-call repack inside (the caller guarantees the parameters do not change).
-        Not used by the training loop at present (see models/frameworks/_finetune.py::backward_patches)."""
-        import contextlib
-
-        @contextlib.contextmanager
-        def _held():
-            self._pack_held = False
-            self.pack()
-            self._pack_held = True
-            try:
-                yield self
-            finally:
-                self._pack_held = False
-        return _held()
+    def invalidate(self):
+        """Force the next pack() to re-fold the weights."""
+        self._pack_key = None
 
     def workspace(self, nbytes):
         dev = self._device()

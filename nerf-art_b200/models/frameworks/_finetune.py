@@ -110,8 +110,7 @@ def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *
     # one process per GPU: patches are dealt round-robin to the ranks, the packed gradient is summed once per step
     # (replaces DDP's bucketed all-reduce, train.py:155)
     world, rank = parallel.world_rank()
-    # (the weights are re-packed by every render_patch call: 0.3 ms per patch.  Packing once per step -- NetEngine.hold_pack -- was
-    # measured and backed out: with it the two-step bench intermittently stopped making progress on the GPU, cause not yet found)
+    # (NetEngine.pack() re-folds the weights only when a parameter changed: once per step, not once per patch)
     for pi, i in enumerate(range(0, n, batch_size)):
         if pi % world != rank:
             continue

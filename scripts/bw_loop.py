@@ -18,7 +18,7 @@ with torch.no_grad():
 eng = m.engine(); eng.grad_zero()
 gen = torch.Generator(device=dev); gen.manual_seed(5)
 import contextlib
-hold = eng.hold_pack() if os.environ.get('BW_LOOP_HOLD') else contextlib.nullcontext()
+hold = contextlib.nullcontext()       # (NetEngine.pack() is version-tracked: the weights are folded once)
 t0 = time.time()
 with hold:
   for k in range(n_patch):

@@ -58,3 +58,46 @@ def test_build_loss_dict_fails_loudly_without_clip():
         pass
     with pytest.raises(RuntimeError, match='clip'):
         build_loss_dict([480, 270], 'cpu')
+
+
+def test_perceptual_loss_never_drops_silently(monkeypatch, tmp_path):
+    """criteria/perp_loss.py is part of the optimised objective (volsdf.py:898-900): without the VGG16 weights construction raises."""
+    from nerfart_b200.criteria import perceptual
+    monkeypatch.delenv('NA_VGG16_WEIGHTS', raising=False)
+    monkeypatch.setattr(torch.hub, 'get_dir', lambda: str(tmp_path))
+    import torchvision.models as tvm
+
+    def offline(*a, **k):
+        raise OSError('no network')
+    monkeypatch.setattr(tvm, 'vgg16', offline)
+    with pytest.raises(RuntimeError, match='not dropped silently'):
+        perceptual.VGGPerceptualLoss()
+    assert perceptual.VGGPerceptualLoss(weights='random:1') is not None
+
+
+REF_PERP = '/root/reference/criteria/perp_loss.py'
+
+
+@pytest.mark.skipif(not __import__('os').path.exists(REF_PERP), reason='reference tree not present')
+def test_perceptual_loss_equals_the_reference_module_on_the_same_weights(monkeypatch):
+    """VGGPerceptualLoss against the UNMODIFIED criteria/perp_loss.py holding the same (seeded) VGG16 weights: loss and image
+    gradient bit-identical on CPU (same ops in the same order; the reference's unused conv4 block is skipped here)."""
+    import importlib.util
+    import torchvision.models as tvm
+    from nerfart_b200.criteria.perceptual import VGGPerceptualLoss, _load_state
+    sd = _load_state('random:3')
+    real = tvm.vgg16
+
+    def seeded_vgg16(pretrained=False, **kw):
+        m = real(weights=None)
+        full = m.state_dict(); full.update(sd); m.load_state_dict(full)
+        return m
+    monkeypatch.setattr(tvm, 'vgg16', seeded_vgg16)
+    spec = importlib.util.spec_from_file_location('ref_perp_loss', REF_PERP)
+    ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref)
+    R, M = ref.VGGPerceptualLoss().eval(), VGGPerceptualLoss(weights='random:3').eval()
+    torch.manual_seed(0)
+    a = torch.rand(1, 3, 60, 34, requires_grad=True); b = torch.rand(1, 3, 60, 34)
+    lr = R(a, b); gr, = torch.autograd.grad(lr, a)
+    lm = M(a, b); gm, = torch.autograd.grad(lm, a)
+    assert float(lr.detach()) == float(lm.detach()) and torch.equal(gr, gm) and float(gr.abs().max()) > 0

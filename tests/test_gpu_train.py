@@ -199,13 +199,15 @@ class _Args(dict):
     __getattr__ = dict.__getitem__
 
 
-def test_trainer_forward_finetune_step_volsdf(monkeypatch):
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_trainer_forward_finetune_step_volsdf(monkeypatch, precision):
     """Trainer.forward (fine-tune branch) with an injected differentiable style loss: same protocol as the reference
-    (loss already back-propagated, .grad populated, optimizer.zero_grad() called inside), gradients equal to the oracle's."""
+    (loss already back-propagated, .grad populated, optimizer.zero_grad() called inside), gradients equal to the oracle's.
+    Both the fp32 mode and the DEFAULT tensor-core mode ('tc': tcgen05 forward + backward program + tcgen05 weight gradients)."""
     from nerfart_b200.models.frameworks import volsdf as pv, _finetune
     monkeypatch.setattr(_finetune, 'BATCH_SIZE', 500)
     m = make_volsdf(0.1, 0.5, device=DEV).train()
-    m.engine().precision = 'fp32'
+    m.engine().precision = precision
     H = W = 24
     target = torch.full((1, H * W, 3), 0.25, device=DEV)
     wts = torch.linspace(0.5, 1.5, H * W * 3, device=DEV).reshape(1, 3, H, W)
@@ -249,16 +251,17 @@ def test_trainer_forward_finetune_step_volsdf(monkeypatch):
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         worst = max(worst, rel_err(p.grad.cpu().numpy(), np.asarray(total[k]).reshape(tuple(p.shape))))
-    print('Trainer.forward: worst relative parameter-gradient error vs oracle', worst)
-    assert worst < REL_TOL
+    print(f'Trainer.forward [{precision}]: worst relative parameter-gradient error vs oracle', worst)
+    assert worst < TOL[precision][0]
     opt.step()
 
 
-def test_trainer_forward_finetune_step_neus(monkeypatch):
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_trainer_forward_finetune_step_neus(monkeypatch, precision):
     from nerfart_b200.models.frameworks import neus as pn, _finetune
     monkeypatch.setattr(_finetune, 'BATCH_SIZE', 300)
     m = make_neus(0.05, 0.5, device=DEV).train()
-    m.engine().precision = 'fp32'
+    m.engine().precision = precision
     H = W = 20
     target = torch.full((1, H * W, 3), 0.25, device=DEV)
 
@@ -299,6 +302,6 @@ def test_trainer_forward_finetune_step_neus(monkeypatch):
             assert p.grad is None, k
             continue
         worst = max(worst, rel_err(p.grad.cpu().numpy(), np.asarray(total[k]).reshape(tuple(p.shape))))
-    print('NeuS Trainer.forward: worst relative parameter-gradient error vs oracle', worst)
-    assert worst < REL_TOL
+    print(f'NeuS Trainer.forward [{precision}]: worst relative parameter-gradient error vs oracle', worst)
+    assert worst < TOL[precision][0]
     opt.step()
