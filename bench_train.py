@@ -193,11 +193,11 @@ def main(args):
         line = {'metric': 'MLP samples/sec (VolSDF 480x270x128 fine-tune step)', 'value': n_rays * P * args.steps / t, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': ('backward: forward + backward-data GEMMs of a patch in one tcgen05 launch (f16 operands, f32 accumulate), weight-gradient GEMMs tcgen05 tf32; ' if args.precision != 'fp32' else 'backward: f32 recompute + tf32 mma.sync; ') + 'CLIP tower linear layers tcgen05 tf32; forward: ' + args.precision, 'data': 'synthetic',
+                'dtype': ('backward: forward + backward-data GEMMs of a patch in one tcgen05 launch (f16 operands, f32 accumulate), weight-gradient GEMMs tcgen05 f16/bf16 operands from a 16-bit stash, f32 accumulate; ' if args.precision != 'fp32' else 'backward: f32 recompute + tf32 mma.sync; ') + 'CLIP tower linear layers tcgen05 tf32; forward: ' + args.precision, 'data': 'synthetic',
                 'config': {'workload': f'VolSDF fine-tune step {H}x{W} ({n_rays} rays), 128+64 samples/ray, pass 1 + pass 2 in 108 patches of '
                                        '1200 rays, eikonal on, perturb on, style=' + style + (' (3 CLIP losses, seeded random ViT-B/32 weights + stand-in text features, no VGG)' if style == 'clip' else ' (weighted MSE)') + ', Adam step',
                            'parallelism': f'patch round-robin x{world}' + (' + NCCL all-reduce of the packed gradient' if world > 1 else ''),
-                           'l2': 'per-patch stash (11.8 GB) >> 126 MB L2; no explicit flush'},
+                           'l2': 'per-patch stash (5.0 GB) >> 126 MB L2; no explicit flush'},
                 'phases_ms': {'pass1_render': 1e3 * t_p1, 'pass2_patch_forward': 1e3 * t_pfwd, 'pass2_backward': 1e3 * t_bwd,
                               'style_loss_forward': 1e3 * t_style,
                               'other (style backward, unpack, Adam, host)': 1e3 * (t / args.steps - t_p1 - t_pfwd - t_bwd - t_style)},
@@ -205,10 +205,10 @@ def main(args):
                         'h2d_bytes_per_step': 2 * 64 + n_rays * 12, 'd2h_bytes_per_step': 4,
                         'note': 'the step is timed through Trainer.forward with pinned-host camera / target image in and the loss out'},
                 'gpu_launches': int(launches), 'clocks': clk,
-                'roofline': {'bound': 'tensor', 'kernel': 'tm::mlp_tmem_kernel<BW> + wg::wgrad_tc_kernel (pass-2 backward)',
+                'roofline': {'bound': 'tensor', 'kernel': 'tm::mlp_tmem_kernel<BW> + wf::wgrad_f16_kernel (pass-2 backward)',
                              'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops'], 'traffic': None,
                              'flop_per_sample': F_BWD, 'note': 'algorithmic backward FLOPs / time inside render_bwd; the 41 tile GEMMs of a patch (forward re-evaluation + backward-data) run '
-                             'on tcgen05 in one launch, the 12 wide weight-gradient GEMMs on tcgen05 kind::tf32 (5 narrow ones on legacy mma.sync TF32)', 'peak_kind': f'{kind} bf16 burst'},
+                             'on tcgen05 in one launch, all weight-gradient GEMMs on tcgen05 kind::f16 fed by TMA from the 16-bit stash', 'peak_kind': f'{kind} bf16 burst'},
                 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -249,7 +249,13 @@ typedef struct NaRawGrads {       /* where na_unpack_grads writes; same layer or
 } NaRawGrads;
 
 size_t na_grad_pack_bytes(const NaNetDesc* desc);
+/* workspace of one render_bwd call: for any arithmetic mode (the maximum), or for the mode the call will use (tensor-core modes hold
+ * the patch's activation stash as 16-bit planes: 21.6 KB per sample; fp32 mode: 43 KB per sample) */
 size_t na_train_workspace_bytes(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray);
+size_t na_train_workspace_bytes_mode(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray, int32_t precision);
+/* diagnostics / unit test of the weight-gradient GEMM kernel (csrc/wgrad_f16.cu): planes16 = two 16-bit planes [2][m_pad][256]
+ * (plane 0 = L, plane 1 = R; m_pad a multiple of 128), out[256][256] += L^T R over m_rows samples, bias_out[256] += column sums of L */
+int na_debug_wgrad_f16(const void* planes16, int64_t m_pad, int64_t m_rows, int l_bf16, int r_bf16, float* out, float* bias_out, void* stream);
 
 /* rays [n,3] (directions un-normalised, as passed to the forward), alpha_beta = {1/beta, beta} (forward_ab),
  * d_all / sdf [n,P], radiance / nablas [n,P,3] = extras d_vals, implicit_surface, radiance, implicit_nablas of the forward

@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NA_LIB_PATH') or os.path.join(_HERE, 'libnerfart_b200.so')    # NA_LIB_PATH: diagnostic builds (scripts/build_trace.sh)
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu', 'train.cu', 'clip_vit.cu', 'tgemm.cu', 'wgrad_tc.cu']
+SOURCES = ['api.cu', 'mlp_simt.cu', 'volsdf_render.cu', 'neus_render.cu', 'surface_render.cu', 'mlp_tc.cu', 'mlp_tmem.cu', 'train.cu', 'clip_vit.cu', 'tgemm.cu', 'wgrad_f16.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--compiler-options', '-fPIC']
 LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '--compiler-options', '-fPIC']
@@ -165,6 +165,9 @@ def lib():
         L.na_grad_pack_bytes.argtypes = [C.POINTER(NaNetDesc)]
         L.na_train_workspace_bytes.restype = C.c_size_t
         L.na_train_workspace_bytes.argtypes = [C.POINTER(NaNetDesc), C.c_int64, C.c_int32]
+        L.na_debug_wgrad_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.na_train_workspace_bytes_mode.restype = C.c_size_t
+        L.na_train_workspace_bytes_mode.argtypes = [C.POINTER(NaNetDesc), C.c_int64, C.c_int32, C.c_int32]
         for fn in (L.na_volsdf_render_bwd, L.na_neus_render_bwd):
             fn.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaTrainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -434,7 +434,7 @@ extern "C" int na_sample_cdf(const float* bins, const float* cdf, int64_t rows, 
 }
 
 namespace na {
-int preload_mlp_simt(); int preload_mlp_tc(); int preload_mlp_tmem(); int preload_wgrad_tc(); int preload_tgemm(); int preload_train();
+int preload_mlp_simt(); int preload_mlp_tc(); int preload_mlp_tmem(); int preload_wgrad_f16(); int preload_tgemm(); int preload_train();
 int preload_volsdf(); int preload_neus(); int preload_surface();
 namespace clipv { int preload_clip(); }
 }
@@ -444,7 +444,7 @@ namespace clipv { int preload_clip(); }
 extern "C" int na_preload_kernels(void) {
     NA_PRELOAD(wn_scale_kernel); NA_PRELOAD(pack_fill_kernel); NA_PRELOAD(get_rays_kernel);
     NA_PRELOAD(error_bound_rows_kernel); NA_PRELOAD(sample_rows_kernel);
-    NA_TRY(preload_mlp_simt()); NA_TRY(preload_mlp_tc()); NA_TRY(preload_mlp_tmem()); NA_TRY(preload_wgrad_tc()); NA_TRY(preload_tgemm());
+    NA_TRY(preload_mlp_simt()); NA_TRY(preload_mlp_tc()); NA_TRY(preload_mlp_tmem()); NA_TRY(preload_wgrad_f16()); NA_TRY(preload_tgemm());
     NA_TRY(preload_train()); NA_TRY(preload_volsdf()); NA_TRY(preload_neus()); NA_TRY(preload_surface()); NA_TRY(clipv::preload_clip());
     return NA_OK;
 }

@@ -163,6 +163,9 @@ size_t train_pack_off(int multires_view);           // bytes from the start of t
 // ---------------------------------------------------------------------------------------------
 // where the points of one MLP launch come from, and where results go
 // ---------------------------------------------------------------------------------------------
+// opaque storage of a CUtensorMap (cuda.h) inside kernel parameters
+struct alignas(64) TmaMap { unsigned long long v[16]; };
+
 struct EvalJob {
     // explicit points (na_sdf_eval / na_full_eval): x != nullptr, m points
     const float* x;  const float* view;  long long m;
@@ -182,38 +185,40 @@ struct EvalJob {
     int   want_full;                                 // 0: SDF only; 1: + nablas (+ radiance if rad != nullptr)
     int   multires_view;
     long long* dbg;                                  // optional cycle counters (na_debug_set_buffer), else nullptr
-    // activation stash for the backward pass (csrc/train.cu; tensor-core modes, want_full == 1): sample-major fp32 planes
-    // [plane][st_mpad][256] indexed by the launch's flat sample number; nullptr = not written
-    float* st_wide;  size_t st_mpad;
-    int st_quad;                                     // 1: wide planes in the quad layout (stash_quad_index below) instead of [m][256]
-    float* st_small;                                 // [st_mpad][40]: the small radiance inputs x | embed(view) | nabla
-    // backward in the same launch (csrc/mlp_tmem.cu, BW program; needs the stash): upstream gradients per sample (nullable = 0),
-    // the remaining stash planes, and the sphere-background mask of d L / d sdf (volsdf.py:349-357)
+    // Stash for the backward pass of a training patch (csrc/mlp_tmem.cu BW program -> csrc/wgrad_f16.cu): every (delta, input) pair a
+    // weight gradient needs, as sample-major 16-bit planes [plane][st_mpad][256] indexed by the launch's flat sample number
+    // (row-major, 512 B per sample: the layout the weight-gradient kernel's TMA boxes read); nullptr = not written.
+    // All planes are bf16: the backward quantities (z-bar, v-bar, deltas, feature-bar) need its range (they follow the upstream
+    // gradient, 1e-30 .. 1e4), and tcgen05 kind::f16 does not take an fp16 operand against a bf16 one (illegal instruction).
+    // The wide planes are written with TMA tensor stores (st_store_map: boxes of 16 columns x 32 samples, one per epilogue warp and
+    // pass): direct stores would be 32-byte pieces at a 512-byte stride, 32 LSU wavefronts per warp instruction.
+    unsigned short* st_wide;  size_t st_mpad;
+    TmaMap st_store_map;
+    unsigned short* st_small;                        // [st_mpad][64] (36 / 12 used): the small radiance inputs x | embed(view) | nabla
+    // backward in the same launch (BW program): upstream gradients per sample (nullable = 0), the remaining stash planes, and the
+    // sphere-background mask of d L / d sdf (volsdf.py:349-357)
     int bw;  int bw_bg_mask;
     const float* bw_gsdf;  const float* bw_gnab;  const float* bw_grad;
-    float* st_emb;  float* st_vb0;                   // [st_mpad][40]: encoding, v-bar_0
-    float* st_t0;  float* st_t1;                     // [st_mpad][4]: delta of the radiance output layer; masked d L / d sdf
+    unsigned short* st_emb;  unsigned short* st_vb0; // [st_mpad][64] (39 used): encoding (fwd format), v-bar_0 (bf16)
+    float* st_t0;  float* st_t1;                     // [st_mpad][4] fp32: delta of the radiance output layer; masked d L / d sdf
 };
-
-// quad layout of a wide stash plane: tile of 128 samples x column quad, float4 at ((m / 128) * 64 + col / 4) * 128 + m % 128 -- the
-// tcgen05 epilogues (thread = sample row) then store 32 rows x 16 B contiguously per warp instruction
-__host__ __device__ inline size_t stash_quad_index(long long m, int col) {
-    return ((size_t)(m >> 7) * 64 + (size_t)(col >> 2)) * 512 + (size_t)(m & 127) * 4 + (size_t)(col & 3);
-}
 
 // planes of EvalJob::st_wide a forward launch fills (the backward kernels of csrc/train.cu add theirs; see the enum there)
 constexpr int ST_IN = 0;        // 0..7   h_i = output of SDF layer i (layer 3: [h_3 | emb])
 constexpr int ST_G = 16;        // 16..23 g_i = reverse-sweep value u_i * softplus'(z_i)
 constexpr int ST_FEAT = 32;     // geometry feature
 constexpr int ST_YS = 34;       // 34..37 outputs of radiance layers 0..3
-constexpr int ST_S = 42;        // 42..49 softplus'(z_i)
 // ... and the planes the backward program adds (same numbering as the enum in csrc/train.cu)
 constexpr int ST_ZB = 8;        // 8..15  z-bar_i
 constexpr int ST_VB = 24;       // 24..31 v-bar_{i+1}
 constexpr int ST_FB = 33;       // d L / d feature
 constexpr int ST_D = 38;        // 38..41 delta_0..3 of the radiance hidden layers
 
-// one 256 x 256 weight-gradient task of csrc/wgrad_tc.cu: out[l][r] += sum_m L[p][m][l] * R[p][m][r] over p < npair
-struct WgTcTask { const float* L[2]; const float* R[2]; float* out; int ldo; int npair; };
+constexpr int ST_N_WIDE = 42;   // wide planes of the 16-bit stash
+constexpr int ST_NLD = 64;      // row stride (elements) of the narrow 16-bit planes
+
+// one weight-gradient task of csrc/wgrad_f16.cu: out[l][r] += sum_m L[p][m][l] * R[p][m][r] over p < npair, (+ bias_out[l] += sum_m L[0][m][l]);
+// planes by number in the wide stash buffer (R: in the narrow buffer when r_narrow), *_bf16: element format of the plane (else fp16)
+struct WgF16Task { int l_plane[2], r_plane[2], l_bf16[2], r_bf16[2]; int npair, r_narrow, n_valid, ldo; float* out; float* bias_out; };
 
 }  // namespace na

@@ -23,6 +23,7 @@
 // quadrant take 16 of every 64 columns.
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -58,11 +59,15 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 #endif
 
 enum BwOp { OP_FWD = 0, OP_DR, OP_FB, OP_HB, OP_SO, OP_TR };      // OP_FWD: forward program, dispatched on the program index
-struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, img, op, lyr, pad0, pad1; };   // img: weight image (unscale index)
-struct Program { int n_gemm; int nsplit; int corr_first; float debias; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
-// corr_first: three-product GEMMs accumulate the two small correction products of ALL K-blocks first and the hi*hi products last, so that
-// only 16 of the layer's 48 accumulator updates happen at full magnitude (the tensor core's fp32 accumulate truncates: the error grows
-// linearly with the number of full-magnitude updates); costs a second load of each W_hi stage.  debias: see launch_mlp_tmem.
+struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, img, op, lyr, pad0, pad1; float debias; };   // img: weight image (unscale index); debias: see launch_mlp_tmem
+struct Program { int n_gemm; int nsplit; int corr_first; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
+// corr_first (product order of a three-product GEMM; the tensor core's fp32 accumulate truncates toward zero, so the error is a BIAS that
+// grows linearly with the number of accumulator updates made at full magnitude -- profiles/r3b_tc_accumulation.md):
+//   0  K-block-interleaved hi*hi, lo*hi, hi*lo (all 48 updates of a 256-deep layer at full magnitude)
+//   1  the two small correction products of ALL K-blocks first, hi*hi last (16 full-magnitude updates; 24 MMAs exposed after the
+//      last K-block of A arrives; every W_hi stage is loaded twice)
+//   2  corrections of K-blocks 0..n-2 as they arrive, then their hi*hi (runs under the previous epilogue's last pass), then the last
+//      K-block as lo*hi, hi*lo, hi*hi per N-quarter (16 + 8 updates at (nearly) full magnitude; same exposed tail as order 0)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -191,11 +196,13 @@ struct EpiCtx {
     unsigned t_lane; int r, cq, g; float us; int sdim;
     unsigned bias_s, w8_s, w4_s, radw_s, kb_bar, d_bar;
     int signal, need_lo, lane;
-    float* st_row;                  // ST: this thread's row in plane 0 of the stash (row-major: st_wide + m * 256; quad layout: the row's
-                                    // slot in column quad 0 of its tile), nullptr beyond the allocation
-    size_t st_plane;                // ST: floats per plane
+    unsigned short* st_row;         // ST: this thread's row in plane 0 of the 16-bit stash (st_wide + m * 256), nullptr beyond the allocation
+    size_t st_plane;                // ST: elements per plane
     long long st_m;                 // ST: flat sample index of the row
-    int st_quad;
+    const TmaMap* st_map;           // ST: tensor map of the wide planes (store boxes: 16 columns x 32 samples)
+    unsigned st_stg;                // ST: this warp's two 1 KB staging buffers in shared memory
+    int st_row0;                    // ST: first sample (row of the plane) of this warp's 32 lanes in the current tile
+    mutable unsigned st_cnt;        // ST: TMA stores issued by this warp so far (buffer parity)
     // BW: per-row power-of-two scale of the upstream gradient (the backward is linear in it and rows are independent, so every
     // backward quantity of the row is carried x rs in the fp16 operands and stored x irs) and the row's total d L / d nabla (x rs)
     float rs, irs, nbar[3];
@@ -277,14 +284,45 @@ __device__ __forceinline__ void emb_range(const float (&xs)[3], float (&e)[16]) 
     }
 }
 
-// ST: 16 consecutive columns of this thread's row -> stash plane `plane` (values are stored x `scale`)
-__device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, const float (&o)[16], float scale) {
-    if (!c.st_row) return;
-    float4* dst; size_t step;
-    if (c.st_quad) { dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + (size_t)(col0 >> 2) * 512); step = 128; }
-    else           { dst = reinterpret_cast<float4*>(c.st_row + (size_t)plane * c.st_plane + col0); step = 1; }
+// 16 floats -> 16 packed bf16 values
+__device__ __forceinline__ void pack16(const float (&o)[16], float scale, uint4& lo, uint4& hi) {
+    unsigned w[8];
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) dst[j4 * step] = make_float4(o[4 * j4] * scale, o[4 * j4 + 1] * scale, o[4 * j4 + 2] * scale, o[4 * j4 + 3] * scale);
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i] * scale, o[2 * i + 1] * scale);
+        w[i] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    lo = make_uint4(w[0], w[1], w[2], w[3]); hi = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void sts128(unsigned addr, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// ST: 16 consecutive columns of every row of this warp (32 samples x 32 B) -> stash plane `plane`, values x `scale`.  The rows are
+// staged in shared memory (lane = row, 32 B each) and written by ONE TMA tensor store per warp (box 16 columns x 32 samples): the
+// store engine scatters the 32-byte pieces over the 512-byte-strided rows of the plane, the LSU sees two conflict-free 16-byte
+// shared-memory stores per thread.  Two staging buffers per warp; a buffer is reused once the store before last has read it.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, const float (&o)[16], float scale) {
+    uint4 lo, hi;
+    pack16(o, scale, lo, hi);
+    const unsigned buf = c.st_stg + (c.st_cnt & 1u) * 1024u;
+    if (c.lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    sts128(buf + (unsigned)c.lane * 32u, lo); sts128(buf + (unsigned)c.lane * 32u + 16u, hi);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (c.lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     :: "l"(c.st_map), "r"(col0), "r"((int)((size_t)plane * (c.st_plane >> 8)) + c.st_row0), "r"(buf) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    ++c.st_cnt;
+}
+// all TMA stores of this warp are complete and visible to its later global loads (called by all 32 lanes)
+__device__ __forceinline__ void stash_flush(const EpiCtx& c) {
+    if (c.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncwarp();
 }
 
 // BW: entry k of v-bar_0 = (d emb / d x)^T-contracted total d L / d nabla of row r (x rs): x_c -> n_c, sin(f x_c) -> f cos(f x_c) n_c,
@@ -323,16 +361,20 @@ __device__ __forceinline__ void qload16(const uint4* base, int plane, int col0, 
         for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x * 256.f; v[8 * j8 + 2 * i + 1] = f.y * 256.f; }
     }
 }
-// BW: 16 consecutive columns of this thread's row from a (quad-layout) stash plane it wrote earlier in the tile
+// BW: 16 consecutive columns of this thread's row from a stash plane this warp stored earlier in the tile (after stash_flush);
+// L1-bypassing loads: the plane was written by the TMA engine
 __device__ __forceinline__ void stash_load16(const EpiCtx& c, int plane, int col0, float (&v)[16]) {
-    if (!c.st_row) {
+    const uint4* p = reinterpret_cast<const uint4*>(c.st_row + (size_t)plane * c.st_plane + col0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        return;
+    for (int j8 = 0; j8 < 2; ++j8) {
+        const uint4 q = __ldcg(p + j8);
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[8 * j8 + 2 * i] = f.x; v[8 * j8 + 2 * i + 1] = f.y;
+        }
     }
-    const float4* p = reinterpret_cast<const float4*>(c.st_row + (size_t)plane * c.st_plane + (size_t)(col0 >> 2) * 512);
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) { const float4 q = p[j4 * 128]; v[4 * j4] = q.x; v[4 * j4 + 1] = q.y; v[4 * j4 + 2] = q.z; v[4 * j4 + 3] = q.w; }
 }
 // BW: softplus'(z_lyr) of 16 columns from the 16-bit codes the forward epilogue left in the per-CTA scratch
 __device__ __forceinline__ void sload16(const EpiCtx& c, int lyr, int col0, float (&v)[16]) {
@@ -449,16 +491,6 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             }
             if (ST) {
                 stash16(c, ST_IN + c.g, col0, o, 1.f / ACT_SCALE);
-                if (!c.bw) {                 // the BW program reads softplus' from the codes in the per-CTA scratch instead
-                    float sv[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float ru = rcp_approx(1.f + t[j]);
-                        sv[j] = z16[j] >= 0.f ? ru : 1.f - ru;
-                        if (KIND == K_FWD3 && col0 + j >= SKIP_H) sv[j] = 0.f;
-                    }
-                    stash16(c, ST_S + c.g, col0, sv, 1.f);
-                }
             }
             if (KIND == K_FWD7) {
 #pragma unroll
@@ -469,16 +501,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 }
             }
         } else if (KIND == K_FEAT) {
+            float fst[16];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 b4 = lds128(bias + (unsigned)(col0 + 4 * j4) * 4u);
                 const float4 f4 = make_float4(fmaf(acc[4 * j4], us, b4.x), fmaf(acc[4 * j4 + 1], us, b4.y),
                                               fmaf(acc[4 * j4 + 2], us, b4.z), fmaf(acc[4 * j4 + 3], us, b4.w));
                 if (FULL) c.featp[(size_t)((col0 >> 2) + j4) * TM + r] = f4;
-                if (ST && c.st_row) {
-                    if (c.st_quad) reinterpret_cast<float4*>(c.st_row + (size_t)ST_FEAT * c.st_plane + (size_t)((col0 >> 2) + j4) * 512)[0] = f4;
-                    else reinterpret_cast<float4*>(c.st_row + (size_t)ST_FEAT * c.st_plane + col0)[j4] = f4;
-                }
+                if (ST) { fst[4 * j4] = f4.x; fst[4 * j4 + 1] = f4.y; fst[4 * j4 + 2] = f4.z; fst[4 * j4 + 3] = f4.w; }
                 if (c.job->feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(c.job->feat + S.OIDX[r] * 256 + col0) + j4) = f4;
                 if (FULL) {
                     // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
@@ -489,6 +519,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     o[4 * j4 + 2] = w4.z * d4[2] * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4[3] * ACT_SCALE;
                 }
             }
+            if (ST) stash16(c, ST_FEAT, col0, fst, 1.f);
             if (ST && FULL) { stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD || KIND == K_BWD4) {
 #pragma unroll
@@ -540,6 +571,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
                 float sv[16], gv[16], q[16];
                 sload16(c, c.lyr, col0, sv);
+                if (c.lyr == 0 && c16 == 0) stash_flush(c);          // the g planes (stored during the reverse sweep) are read back from here on
                 stash_load16(c, ST_G + c.lyr, col0, gv);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -652,18 +684,20 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 
 template <bool FULL, bool ST, bool BW>
 __global__ void __launch_bounds__(THREADS, 1)
-mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
+mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
                 const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch, const SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ST (training stash): the weight ring is one stage shorter and the fifth 32 KB slot is the staging area of the TMA stores
+    constexpr unsigned NSK = ST ? (unsigned)NS - 1u : (unsigned)NS;
     const bool explicit_pts = job.x != nullptr;
     const long long total = explicit_pts ? job.m
                           : (long long)(job.n_rows_dev ? min(*job.n_rows_dev, job.n_rows) : job.n_rows) * job.P;
     const long long n_tiles = (total + TM - 1) / TM;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
+        for (int s = 0; s < (int)NSK; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
         for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.d_ready[k]), 1);
         for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&S.kb_ready[k]), EPI_THREADS / 32);   // one arrive per epilogue warp
         fence_barrier_init();
@@ -699,10 +733,15 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                     const unsigned sb = prog.g[g].stage_bytes;
                     const int n_kb = prog.g[g].n_kb, n_sp = prog.g[g].prods == 3 ? 2 : 1;
                     // stage sequence: [hi(kb) | lo(kb)] per K-block; with corr_first the hi stages of a three-product GEMM follow once more
-                    const int n_seq = n_kb * n_sp + ((prog.corr_first && n_sp == 2) ? n_kb : 0);
+                    const int order = n_sp == 2 ? prog.corr_first : 0;
+                    const int n_seq = order == 0 ? n_kb * n_sp : (order == 1 ? 3 * n_kb : 3 * n_kb - 1);
                     for (int q = 0; q < n_seq; ++q, ++it) {
-                        const int st = q < n_kb * n_sp ? (n_sp == 2 ? q : 2 * q) : 2 * (q - n_kb * n_sp);      // stage index in the image: 2 kb + {0 hi, 1 lo}
-                        const unsigned slot = it % NS, ph = (it / NS) & 1;
+                        // stage index in the image: 2 kb + {0 hi, 1 lo}
+                        int st;
+                        if (order == 0) st = n_sp == 2 ? q : 2 * q;
+                        else if (order == 1) st = q < 2 * n_kb ? q : 2 * (q - 2 * n_kb);
+                        else { const int na = 2 * (n_kb - 1); st = q < na ? q : (q < na + n_kb - 1 ? 2 * (q - na) : 2 * (n_kb - 1) + (q - na - (n_kb - 1))); }
+                        const unsigned slot = it % NSK, ph = (it / NSK) & 1;
                         mbar_wait_guarded(smem_u32(&S.empty_bar[slot]), ph ^ 1, sc, 0x50000000u | ((unsigned)g << 8) | slot);
                         mbar_expect_tx(smem_u32(&S.full_bar[slot]), sb);
                         bulk_g2s(smem_u32(S.Wst + slot * STAGE_BYTES), src + (size_t)st * sb, sb, smem_u32(&S.full_bar[slot]));
@@ -729,11 +768,13 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 // next GEMM, and a second completion before this warp's wait flips the parity back -- the wait would then never
                 // return (mbarrier phase aliasing; this was the intermittent first-step stall, profiles/r3a_stall_root_cause.md).
                 for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);
-                const bool corr_first = prog.corr_first && prods == 3;
+                const int order = prods == 3 ? prog.corr_first : 0;
+                const bool corr_first = order != 0;
+                const int n_a = order == 1 ? n_kb : n_kb - 1;          // K-blocks whose corrections / hi*hi go through phases A / B
                 if (corr_first) {
-                    // ---- phase A: lo*hi and hi*lo of every K-block, as the K-blocks of A arrive (stages [W_hi | W_lo])
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        const unsigned slot0 = it % NS, ph0 = (it / NS) & 1, slot1 = (it + 1) % NS, ph1 = ((it + 1) / NS) & 1;
+                    // ---- phase A: lo*hi and hi*lo of K-blocks 0..n_a-1, as the K-blocks of A arrive (stages [W_hi | W_lo])
+                    for (int kb = 0; kb < n_a; ++kb) {
+                        const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1, slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
                         const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                         { const long long t0 = clock64();
                           mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
@@ -755,9 +796,9 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         it += 2;
                         NA_TRACE_M(tr, g, kb, 1);
                     }
-                    // ---- phase B: hi*hi of every K-block on top (W_hi stages again); the last one in N-parts with their own commits
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        const unsigned slot0 = it % NS, ph0 = (it / NS) & 1;
+                    // ---- phase B: hi*hi of those K-blocks on top (W_hi stages again); order 1: the last one in N-parts with their own commits
+                    for (int kb = 0; kb < n_a; ++kb) {
+                        const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1;
                         const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                         { const long long t0 = clock64();
                           mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d050000u | ((unsigned)g << 8) | (unsigned)kb);
@@ -786,9 +827,48 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         it += 1;
                     }
                 }
+                if (order == 2) {
+                    // ---- phase C: the last K-block: lo*hi, hi*lo, hi*hi per N-part, each part with its own commit
+                    const int kb = n_kb - 1;
+                    const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1, slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
+                    const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
+                    { const long long t0 = clock64();
+                      mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
+                      mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
+                      t_full += clock64() - t0; }
+                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                    tc_fence_after();
+                    NA_TRACE_M(tr, g, kb, 0);
+                    if (elect_one()) {
+                        const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES), bd1 = umma_desc(wst + slot1 * STAGE_BYTES);
+                        const bool whole = prog.g[g].n64;                      // 64-wide GEMM: one part, d_ready committed after the loop
+                        const int nsp = whole ? 1 : prog.nsplit;
+                        const unsigned ncol = 256u / (unsigned)nsp, idn = whole ? idesc : (nsp == 4 ? IDESC_N64 : IDESC_N128);
+                        for (int np = 0; np < nsp; ++np) {
+                            const unsigned t_dn = t_out + (whole ? 0u : ncol * np);
+                            const unsigned long long boff = whole ? 0ull : (unsigned long long)(np * (int)(ncol * 128u / 16u));
+                            const unsigned long long b0 = bd0 + boff, b1 = bd1 + boff;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks + 8u, b0 + 2 * ks, idn, (kb | ks) != 0);        // lo * hi
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b1 + 2 * ks, idn, 1);                          // hi * lo
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_ts(t_dn, a_hi + 16u * ks, b0 + 2 * ks, idn, 1);                          // hi * hi
+                            if (!whole) {
+                                if (nsp == 4) umma_commit(smem_u32(&S.d_ready[np]));
+                                else { umma_commit(smem_u32(&S.d_ready[2 * np])); umma_commit(smem_u32(&S.d_ready[2 * np + 1])); }
+                            }
+                        }
+                        umma_commit(smem_u32(&S.empty_bar[slot0]));
+                        umma_commit(smem_u32(&S.empty_bar[slot1]));
+                    }
+                    __syncwarp();
+                    it += 2;
+                    NA_TRACE_M(tr, g, kb, 1);
+                }
                 for (int kb = 0; kb < (corr_first ? 0 : n_kb); ++kb) {
-                    const unsigned slot0 = it % NS, ph0 = (it / NS) & 1;
-                    const unsigned slot1 = (it + 1) % NS, ph1 = ((it + 1) / NS) & 1;
+                    const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1;
+                    const unsigned slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
                     const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                     // the weights first (the ring runs K-blocks ahead, so these return at once), then the A operand: the MMAs go out
                     // right behind the epilogue's signal
@@ -865,7 +945,8 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
         c.d_phase = 0; c.sc = sc;
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
-        c.st_m = 0; c.st_quad = job.st_quad;
+        c.st_m = 0; c.st_map = &job.st_store_map; c.st_cnt = 0; c.st_row0 = 0;
+        c.st_stg = smem_u32(S.Wst) + (unsigned)(NS - 1) * STAGE_BYTES + (unsigned)(warp - 2) * 2048u;
         c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = job.rad != nullptr;
         c.bw = BW ? 1 : 0;
         c.qp = reinterpret_cast<uint4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES);
@@ -901,7 +982,8 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 }
                 // padding rows of the last tile are written too (zero upstream gradient): the weight-gradient kernels read whole tiles
                 c.st_m = w;
-                c.st_row = (ST && (size_t)w < job.st_mpad) ? job.st_wide + (job.st_quad ? stash_quad_index(w, 0) : (size_t)w * 256) : nullptr;
+                c.st_row = (ST && (size_t)w < job.st_mpad) ? job.st_wide + (size_t)w * 256 : nullptr;
+                c.st_row0 = (int)(tile * TM) + 32 * q;
                 if (cq == 0) {
                     S.OIDX[r] = oidx;
                     S.X[r] = x0; S.X[TM + r] = x1; S.X[2 * TM + r] = x2;
@@ -936,10 +1018,11 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         for (int cc = 0; cc < 3; ++cc) { S.BWV[cc * TM + r] = gn[cc] * c.rs; S.BWV[(3 + cc) * TM + r] = gr[cc] * c.rs; }
                         S.BWV[6 * TM + r] = gs;                                          // masked and scaled at the sdf head (g == 7)
                     }
-                    if (c.st_row && job.st_emb) {
-                        float* erow = job.st_emb + (size_t)w * 40;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (16 * cq + j < 40) erow[16 * cq + j] = e[j] * (1.f / ACT_SCALE);
+                    if (c.st_row && job.st_emb) {                                      // 64 columns: zero beyond the 39 entries
+                        uint4 lo, hi;
+                        pack16(e, 1.f / ACT_SCALE, lo, hi);
+                        uint4* erow = reinterpret_cast<uint4*>(job.st_emb + (size_t)w * ST_NLD + 16 * cq);
+                        __stcs(erow, lo); __stcs(erow + 1, hi);
                     }
                 }
                 store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
@@ -956,9 +1039,10 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 #pragma unroll
                 for (int j = 0; j < 16; ++j) e[j] = vbar0_entry(S, 16 * cq + j, r, c.nbar);
                 if (c.st_row && job.st_vb0) {
-                    float* vrow = job.st_vb0 + (size_t)c.st_m * 40;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (16 * cq + j < 40) vrow[16 * cq + j] = e[j] * c.irs;
+                    uint4 lo, hi;
+                    pack16(e, c.irs, lo, hi);
+                    uint4* vrow = reinterpret_cast<uint4*>(job.st_vb0 + (size_t)c.st_m * ST_NLD + 16 * cq);
+                    __stcs(vrow, lo); __stcs(vrow + 1, hi);
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) e[j] *= ACT_SCALE;
@@ -968,7 +1052,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
             for (int g = 0; g < prog.n_gemm; ++g) {
                 const int op = BW ? (int)prog.g[g].op : (int)OP_FWD;
                 c.g = g; c.us = unscale[prog.g[g].img];          // us = 2^-(weight shift) / ACT_SCALE
-                if (prog.g[g].prods == 3) c.us *= prog.debias;
+                c.us *= prog.g[g].debias;
                 c.lyr = prog.g[g].lyr;
                 c.signal = g + 1 < prog.n_gemm;
                 c.need_lo = c.signal ? (prog.g[g + 1].prods == 3) : 0;
@@ -1025,12 +1109,16 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) small_in[30 + cc] = nb[cc] * ACT_SCALE;
                         }
-                        if (ST && cq == 0 && c.st_row && job.st_small) {
-                            float* srow = job.st_small + (size_t)c.st_m * 40;
+                        if (ST && c.st_row && job.st_small) {                           // 64 columns, zero beyond the 36 inputs
+                            float part[16];
 #pragma unroll
-                            for (int j = 0; j < 36; ++j) srow[j] = small_in[j] * (1.f / ACT_SCALE);
+                            for (int j = 0; j < 16; ++j) part[j] = 0.f;
 #pragma unroll
-                            for (int j = 36; j < 40; ++j) srow[j] = 0.f;
+                            for (int j = 0; j < 36; ++j) if (j >> 4 == cq) part[j & 15] = small_in[j];
+                            uint4 lo, hi;
+                            pack16(part, 1.f / ACT_SCALE, lo, hi);
+                            uint4* srow = reinterpret_cast<uint4*>(job.st_small + (size_t)c.st_m * ST_NLD + 16 * cq);
+                            __stcs(srow, lo); __stcs(srow + 1, hi);
                         }
                         epi_gemm<K_RAD0, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 20) {
@@ -1066,6 +1154,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                                 *reinterpret_cast<float4*>(job.st_t1 + (size_t)c.st_m * 4) = make_float4(gs, 0.f, 0.f, 0.f);
                         }
                     }
+                    if (BW) epi_bar_sync();                   // BWV[6] (masked d L / d sdf) is read by every column quarter in the trunk
                 }
                 if (FULL && g == 16) {
                     if (has_rad) {
@@ -1150,6 +1239,9 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                         if (BW && c.st_row && job.st_t0)
                             *reinterpret_cast<float4*>(job.st_t0 + (size_t)c.st_m * 4) =
                                 make_float4(S.BWV[3 * TM + r] * c.irs, S.BWV[4 * TM + r] * c.irs, S.BWV[5 * TM + r] * c.irs, 0.f);
+                    } else if (BW && cq == 0 && c.st_row && job.st_t0) {
+                        // padding row of the last tile: the weight-gradient kernels read whole tiles, its delta_4 is zero
+                        *reinterpret_cast<float4*>(job.st_t0 + (size_t)c.st_m * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (BW && g + 1 < prog.n_gemm) {
                         epi_bar_sync();                                   // delta_4 of every row
@@ -1181,6 +1273,7 @@ mlp_tmem_kernel(const EvalJob job, const float* __restrict__ pk, const PackF32 L
                 }
             }
         }
+        if (ST) stash_flush(c);
         if (job.dbg && blockIdx.x == 0 && tid == 64) { job.dbg[3] = clock64() - t_e0; job.dbg[4] = t_d; }
     }
     tc_fence_before();
@@ -1295,7 +1388,6 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     if (!attr_set) {
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         attr_set = true;
     }
@@ -1307,16 +1399,21 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     prog.nsplit = (nsplit_env && nsplit_env[0] == '2') ? 2 : 4;
     // NA_TM_ORDER=0: K-block-interleaved products (the r2 scheme).  NA_TM_DEBIAS=<x>: experimental multiplicative compensation of the
     // accumulate truncation of three-product GEMMs, D *= 1 + x * 2^-24 (0 = off)
+    // NA_TM_ORDER=0|1|2: product order of the three-product GEMMs (see Program).  NA_TM_DEBIAS=<x>: the accumulate-truncation bias of a
+    // 256-deep three-product GEMM is compensated by D *= 1 + x * 2^-24 (scaled by K-blocks / 4 for shallower GEMMs); defaults are the
+    // calibrations of profiles/r3b_tc_accumulation.md for each order; 0 switches the compensation off
     static const char* order_env = getenv("NA_TM_ORDER");
     static const char* debias_env = getenv("NA_TM_DEBIAS");
-    prog.corr_first = (order_env && order_env[0] == '0') ? 0 : 1;
-    prog.debias = 1.f + (debias_env ? (float)atof(debias_env) : 0.f) * 5.9604645e-8f;
+    prog.corr_first = order_env ? (order_env[0] == '0' ? 0 : (order_env[0] == '1' ? 1 : 2)) : 0;
+    static const float debias_default[3] = {14.f, 4.f, 8.f};      // (1 + x 2^-24 is representable in steps of 2)
+    const float debias_x = debias_env ? (float)atof(debias_env) : debias_default[prog.corr_first];
     const int last = !job.want_full ? (job.feat ? 8 : 7) : (job.rad ? 20 : 16);
     for (int g = 0; g <= last; ++g) {
         Gemm t; t.w_off = T.w_off[g]; t.stage_bytes = (unsigned)T.N[g] * 128u; t.n_kb = (unsigned char)T.n_kb[g];
         t.prods = (unsigned char)((mixed && g >= 8) ? 1 : 3);
         if (prods_env && (int)strlen(prods_env) > g) t.prods = prods_env[g] == '1' ? 1 : 3;
         t.n64 = T.N[g] == 64; t.img = (unsigned char)g; t.op = OP_FWD; t.lyr = 0; t.pad0 = t.pad1 = 0;
+        t.debias = t.prods == 3 ? 1.f + debias_x * 5.9604645e-8f * (float)t.n_kb * 0.25f : 1.f;
         prog.g[prog.n_gemm++] = t;
     }
     if (job.bw) {
@@ -1324,7 +1421,7 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
         if (!job.st_wide || !job.want_full || !STASH) return NA_ERR_BAD_ARG;
         auto add = [&](int img, int op, int lyr) {
             Gemm t; t.w_off = T.w_off[img]; t.stage_bytes = (unsigned)T.N[img] * 128u; t.n_kb = (unsigned char)T.n_kb[img];
-            t.prods = 1; t.n64 = 0; t.img = (unsigned char)img; t.op = (unsigned char)op; t.lyr = (unsigned char)lyr; t.pad0 = t.pad1 = 0;
+            t.prods = 1; t.n64 = 0; t.img = (unsigned char)img; t.op = (unsigned char)op; t.lyr = (unsigned char)lyr; t.pad0 = t.pad1 = 0; t.debias = 1.f;
             prog.g[prog.n_gemm++] = t;
         };
         if (job.rad) {
@@ -1341,7 +1438,7 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     if (job.st_wide && !job.want_full) return NA_ERR_BAD_ARG;
     const SpinCtx sc = diag_next(DK_MLP_TMEM, grid);
     if (job.bw)             mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
-    else if (job.st_wide)   mlp_tmem_kernel<true, true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else if (job.st_wide)   return NA_ERR_UNSUPPORTED;               // the stash is written by the BW program only
     else if (job.want_full) mlp_tmem_kernel<true, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     else                    mlp_tmem_kernel<false, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     NA_CHECK_LAUNCH();
@@ -1351,7 +1448,6 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
 int preload_mlp_tmem() {
     NA_PRELOAD((tm::mlp_tmem_kernel<false, false, false>));
     NA_PRELOAD((tm::mlp_tmem_kernel<true, false, false>));
-    NA_PRELOAD((tm::mlp_tmem_kernel<true, true, false>));
     NA_PRELOAD((tm::mlp_tmem_kernel<true, true, true>));
     NA_PRELOAD(tm::pack_kernel);
     NA_PRELOAD(tm::absmax_kernel);

@@ -31,11 +31,10 @@ enum {
     PL_FB = 33,     // dL/d feature
     PL_YS = 34,     // ys_1..4: outputs of radiance layers 0..3                                                    planes 34..37
     PL_D = 38,      // delta_0..3: dL/d(pre-activation) of radiance layers 0..3                                    planes 38..41
-    PL_S = 42,      // softplus'(z_0..7), written by the tcgen05 forward launch of the patch (loaded mode)          planes 42..49
-    N_WIDE = 50
+    N_WIDE = 42
 };
-static_assert(PL_IN == ST_IN && PL_G == ST_G && PL_FEAT == ST_FEAT && PL_YS == ST_YS && PL_S == ST_S && PL_ZB == ST_ZB && PL_VB == ST_VB &&
-              PL_FB == ST_FB && PL_D == ST_D, "stash plane numbering (common.cuh)");
+static_assert(PL_IN == ST_IN && PL_G == ST_G && PL_FEAT == ST_FEAT && PL_YS == ST_YS && PL_ZB == ST_ZB && PL_VB == ST_VB &&
+              PL_FB == ST_FB && PL_D == ST_D && N_WIDE == ST_N_WIDE, "stash plane numbering (common.cuh)");
 constexpr int NLD = 40;     // row stride of the narrow planes EMB, VB0, SMALL
 enum { NP_EMB = 0, NP_VB0 = 1, NP_SMALL = 2 };
 struct Stash {
@@ -189,13 +188,15 @@ __device__ __forceinline__ void st2(float* __restrict__ plane, int row, int col,
     *reinterpret_cast<float2*>(plane + (size_t)row * 256 + col) = make_float2(a, b);
 }
 
-template <bool TF32, bool LOADED>
+template <bool TF32>
 __global__ void __launch_bounds__(NT, 1)
 mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, const float* __restrict__ tp, const PackTrain T,
                const Stash st, float* __restrict__ scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrainSmem& Q = *reinterpret_cast<TrainSmem*>(smem_raw);
     MlpSmem& S = Q.s;
+    constexpr bool LOADED = false;      // (a former mode that took the forward activations from a tcgen05 launch; the tensor-core
+                                        // modes now run the whole backward in csrc/mlp_tmem.cu + csrc/wgrad_f16.cu)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long total = (long long)job.n_rows * job.P;
     const long long n_tiles = (total + TM - 1) / TM;
@@ -210,7 +211,7 @@ mlp_bwd_kernel(const BwdJob job, const float* __restrict__ pk, const PackF32 L, 
         const size_t row0 = (size_t)tile * TM;
         auto WP = [&](int p) { return st.w(p) + row0 * 256; };
         // softplus' of SDF layer i as a [TM][256] tile: the forward launch's stash plane (loaded mode) or this CTA's scratch
-        auto SPL = [&](int layer) -> float* { return LOADED ? WP(PL_S + layer) : SP + layer * 256 * TM; };
+        auto SPL = [&](int layer) -> float* { return SP + layer * 256 * TM; };
         // ---- 0. points, upstream gradients, positional encoding ---------------------------------------------------
         if (tid < TM) {
             const int m = tid;
@@ -707,7 +708,7 @@ struct WgradTask {
     int nbr;                    // output blocks along r
 };
 constexpr int MAX_WTASKS = 32;
-struct WgradTable { WgradTask t[MAX_WTASKS]; int n; int total_blocks; int quad; };      // quad: the 256-wide planes are in the quad layout
+struct WgradTable { WgradTask t[MAX_WTASKS]; int n; int total_blocks; };
 constexpr int WK = 16;          // samples per smem chunk
 
 __global__ void __launch_bounds__(256)
@@ -717,7 +718,6 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     int ti = 0;
     while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
     const WgradTask t = tab.t[ti];
-    const bool quad = tab.quad != 0;
     const int b = blockIdx.x - t.blk0;
     const int lb = (b / t.nbr) * 128, rb = (b % t.nbr) * 128;
     const long long m0 = (long long)blockIdx.y * rows_per_split;
@@ -735,16 +735,16 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     auto gload = [&](const float* Lp, const float* Rp, long long mm) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            // row-major planes: a warp reads 512 B of one sample; quad layout: 4 consecutive samples x 8 column quads per warp instruction
+            // row-major planes: a warp reads 512 B of one sample
             // (64-byte segments; the shared-memory stores below stay conflict-free: each quarter warp hits 8 distinct 4-bank groups)
             const int idx = tid * 2 + e;
-            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
-            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
+            const int row = idx >> 5;
+            const int c4 = (idx & 31) * 4;
             const long long m = mm + row;
             lreg[e] = make_float4(0.f, 0.f, 0.f, 0.f); rreg[e] = lreg[e];
             if (m < m1) {
-                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + ((quad && t.ldl == 256) ? stash_quad_index(m, lb + c4) : (size_t)m * t.ldl + lb + c4));
-                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + ((quad && t.ldr == 256) ? stash_quad_index(m, rb + c4) : (size_t)m * t.ldr + rb + c4));
+                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + (size_t)m * t.ldl + lb + c4);
+                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + (size_t)m * t.ldr + rb + c4);
             }
         }
     };
@@ -752,8 +752,8 @@ wgrad_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int idx = tid * 2 + e;
-            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
-            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
+            const int row = idx >> 5;
+            const int c4 = (idx & 31) * 4;
             *reinterpret_cast<float4*>(&Ls[buf][row][c4]) = lreg[e];
             *reinterpret_cast<float4*>(&Rs[buf][row][c4]) = rreg[e];
         }
@@ -812,7 +812,6 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     int ti = 0;
     while (ti + 1 < tab.n && (int)blockIdx.x >= tab.t[ti + 1].blk0) ++ti;
     const WgradTask t = tab.t[ti];
-    const bool quad = tab.quad != 0;
     const int b = blockIdx.x - t.blk0;
     const int lb = (b / t.nbr) * 128, rb = (b % t.nbr) * 128;
     const long long m0 = (long long)blockIdx.y * rows_per_split;
@@ -832,16 +831,16 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
     auto gload = [&](const float* Lp, const float* Rp, long long mm) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            // row-major planes: a warp reads 512 B of one sample; quad layout: 4 consecutive samples x 8 column quads per warp instruction
+            // row-major planes: a warp reads 512 B of one sample
             // (64-byte segments; the shared-memory stores below stay conflict-free: each quarter warp hits 8 distinct 4-bank groups)
             const int idx = tid * 2 + e;
-            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
-            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
+            const int row = idx >> 5;
+            const int c4 = (idx & 31) * 4;
             const long long m = mm + row;
             lreg[e] = make_float4(0.f, 0.f, 0.f, 0.f); rreg[e] = lreg[e];
             if (m < m1) {
-                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + ((quad && t.ldl == 256) ? stash_quad_index(m, lb + c4) : (size_t)m * t.ldl + lb + c4));
-                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + ((quad && t.ldr == 256) ? stash_quad_index(m, rb + c4) : (size_t)m * t.ldr + rb + c4));
+                if (lb + c4 < t.nl) lreg[e] = *reinterpret_cast<const float4*>(Lp + (size_t)m * t.ldl + lb + c4);
+                if (rb + c4 < t.nr) rreg[e] = *reinterpret_cast<const float4*>(Rp + (size_t)m * t.ldr + rb + c4);
             }
         }
     };
@@ -849,8 +848,8 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int idx = tid * 2 + e;
-            const int row = quad ? ((((tid >> 5) & 3) << 2) | (tid & 3)) : (idx >> 5);
-            const int c4 = quad ? ((((tid >> 7) + 2 * e) << 3) | ((tid & 31) >> 2)) * 4 : (idx & 31) * 4;
+            const int row = idx >> 5;
+            const int c4 = (idx & 31) * 4;
             *reinterpret_cast<float4*>(&Ls[buf][row][c4]) = make_float4(to_tf32(lreg[e].x), to_tf32(lreg[e].y), to_tf32(lreg[e].z), to_tf32(lreg[e].w));
             *reinterpret_cast<float4*>(&Rs[buf][row][c4]) = make_float4(to_tf32(rreg[e].x), to_tf32(rreg[e].y), to_tf32(rreg[e].z), to_tf32(rreg[e].w));
         }
@@ -903,32 +902,12 @@ wgrad_tf32_kernel(const WgradTable tab, long long m_total, int rows_per_split) {
 
 struct ColsumTask { const float* P; float* out; int ld, n; };
 constexpr int MAX_CTASKS = 24;
-struct ColsumTable { ColsumTask t[MAX_CTASKS]; int n; int quad; };
+struct ColsumTable { ColsumTask t[MAX_CTASKS]; int n; };
 __global__ void __launch_bounds__(256)
 colsum_kernel(const ColsumTable tab, long long m_total, int rows_per_split) {
     const ColsumTask t = tab.t[blockIdx.x];
     const long long m0 = (long long)blockIdx.y * rows_per_split;
     long long m1 = m0 + rows_per_split; if (m1 > m_total) m1 = m_total;
-    if (tab.quad && t.ld == 256) {
-        // quad layout: warp w sums column quads w, w + 8, ... ; a warp instruction reads 32 rows x 16 B contiguously
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (m0 >= m1) return;                                                  // m0, m1 are multiples of the 128-row tile
-        for (int q = warp; q < 64; q += 8) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (long long mt = m0; mt < m1; mt += 128) {
-                const float4* p = reinterpret_cast<const float4*>(t.P + stash_quad_index(mt, 4 * q)) + lane;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const float4 v = p[32 * i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-                a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
-            }
-            if (lane == 0) { atomicAdd(t.out + 4 * q, a.x); atomicAdd(t.out + 4 * q + 1, a.y); atomicAdd(t.out + 4 * q + 2, a.z); atomicAdd(t.out + 4 * q + 3, a.w); }
-        }
-        return;
-    }
     const int c = threadIdx.x;
     if (c >= t.n) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -1160,98 +1139,138 @@ __global__ void normalize_dirs_train_kernel(const float* __restrict__ d, float* 
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+// Workspace of one render_bwd call.  fp32 mode: the fp32 stash written by mlp_bwd_kernel + its per-CTA scratch.  Tensor-core modes:
+// the 16-bit stash written by the BW program of csrc/mlp_tmem.cu (42 wide planes of 512 B per sample + 3 narrow ones), its outputs
+// and its per-CTA scratch.
 struct TrainWs {
-    float* dirs; float* g_sdf; float* g_nab; float* g_rad; float* stash; float* scratch;
-    float* f_sdf; float* f_rad; float* fwd_scratch; size_t fwd_scratch_bytes;       // loaded mode: outputs / scratch of the forward launch
+    float* dirs; float* g_sdf; float* g_nab; float* g_rad;
+    float* stash; float* scratch;                                                   // fp32 mode
+    unsigned short* wide16; unsigned short* narrow16; float* tiny; size_t mpad;     // tensor-core modes
+    float* f_sdf; float* f_rad; float* fwd_scratch; size_t fwd_scratch_bytes;
     size_t total;
 };
 size_t mlp_scratch_bytes();                                                         // csrc/api.cu
-int launch_wgrad_tc(const WgTcTask* tasks, int n_tasks, long long m_tiles, cudaStream_t stream);        // csrc/wgrad_tc.cu
+int launch_wgrad_f16(const WgF16Task* tasks, int n_tasks, const unsigned short* wide, int n_wide_planes, const unsigned short* narrow,
+                     int n_narrow_planes, long long mpad, long long m_rows, cudaStream_t stream);       // csrc/wgrad_f16.cu
+int make_stash_store_map(TmaMap* out, const unsigned short* wide, int n_wide_planes, long long mpad);
+int launch_wgrad_tiny(const unsigned short* in7, const unsigned short* vb7, const unsigned short* ys3, const float* t0, const float* t1,
+                      float* w8_sdf, float* b8_sdf, float* rad_w4, float* rad_b4, long long m_rows, int fwd_bf16, cudaStream_t stream);
 int launch_mlp(const EvalJob& job, const void* packed, int precision, float* scratch, size_t scratch_bytes, cudaStream_t stream);
-static TrainWs train_ws(void* base, long long n_rays, int P) {
+static bool bwd_on_tensor_cores(int precision) {
+    static const bool fp32_bwd = [] { const char* e = getenv("NA_BWD"); return e && strcmp(e, "fp32") == 0; }();
+    static const bool force_recompute = [] { const char* e = getenv("NA_BWD_RECOMPUTE"); return e && e[0] == '1'; }();
+    return precision != NA_PRECISION_FP32 && !fp32_bwd && !force_recompute;
+}
+static TrainWs train_ws(void* base, long long n_rays, int P, bool tc) {
     const size_t M = (size_t)n_rays * P, mpad = (M + TM - 1) / TM * TM;
     unsigned char* p = (unsigned char*)base; size_t o = 0;
-    TrainWs w;
+    TrainWs w = {};
     auto take = [&](size_t bytes) { float* r = (float*)(p + o); o += align256(bytes); return r; };
+    w.mpad = mpad;
     w.dirs = take((size_t)n_rays * 3 * 4);
     w.g_sdf = take(M * 4); w.g_nab = take(M * 12); w.g_rad = take(M * 12);
-    w.stash = take(stash_floats(mpad) * 4);
-    w.scratch = take((size_t)num_sms() * 16 * 256 * TM * 4);
-    w.f_sdf = take(M * 4); w.f_rad = take(M * 12);
-    w.fwd_scratch_bytes = mlp_scratch_bytes(); w.fwd_scratch = take(w.fwd_scratch_bytes);
+    if (tc) {
+        w.wide16 = (unsigned short*)take((size_t)N_WIDE * mpad * 256 * 2);
+        w.narrow16 = (unsigned short*)take((size_t)3 * mpad * ST_NLD * 2);
+        w.tiny = take((size_t)2 * mpad * 4 * 4);
+        w.f_sdf = take(M * 4); w.f_rad = take(M * 12);
+        w.fwd_scratch_bytes = mlp_scratch_bytes(); w.fwd_scratch = take(w.fwd_scratch_bytes);
+    } else {
+        w.stash = take(stash_floats(mpad) * 4);
+        w.scratch = take((size_t)num_sms() * 16 * 256 * TM * 4);
+    }
     w.total = o;
     return w;
 }
 
-// NA_BWD=fp32: all-fp32 backward GEMMs.  cfg.precision == NA_PRECISION_FP32 (or NA_BWD_RECOMPUTE=1): the backward kernel recomputes
-// the forward pass of every tile on the fp32 FMA pipe (the first version); tensor-core modes: the tcgen05 forward kernel (csrc/mlp_tmem.cu, stash-out mode) re-evaluates the
-// patch once and leaves h_i, softplus'(z_i), g_i, the feature and the radiance activations in the stash planes the backward and
-// weight-gradient kernels read ("loaded mode").
-static int launch_mlp_bwd(const BwdJob& job_, const void* packed, int precision, const float* pk, const PackF32& L, const float* tp,
-                          const PackTrain& T, const Stash& st, const TrainWs& w, int* quad_out, cudaStream_t stream) {
-    static thread_local bool attr_set = false;
+// fp32 mode (cfg.precision == NA_PRECISION_FP32, or NA_BWD_RECOMPUTE=1 / NA_BWD=fp32): mlp_bwd_kernel recomputes the forward pass of every
+// tile on the fp32 FMA pipe and runs the backward-data GEMMs on mma.sync TF32 (NA_BWD=fp32: FFMA too), leaving an fp32 stash.
+static int launch_mlp_bwd(const BwdJob& job, const float* pk, const PackF32& L, const float* tp, const PackTrain& T, const Stash& st,
+                          const TrainWs& w, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
     static const bool fp32_bwd = [] { const char* e = getenv("NA_BWD"); return e && strcmp(e, "fp32") == 0; }();
-    static const bool force_recompute = [] { const char* e = getenv("NA_BWD_RECOMPUTE"); return e && e[0] == '1'; }();
-    const bool recompute = force_recompute || precision == NA_PRECISION_FP32;
-    const int fwd_precision = precision == NA_PRECISION_TC_MIXED ? NA_PRECISION_TC : precision;    // softplus' needs the 3-product forward
     const size_t smem = sizeof(TrainSmem);
-    if (!attr_set) {
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        attr_set = true;
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        attr_set[dev] = true;
     }
-    BwdJob job = job_;
-    *quad_out = 0;
     const long long total = (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;
     const long long tiles = (total + TM - 1) / TM;
     const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
-    if (!recompute) {
-        EvalJob e = {};
-        e.rays_o = job.rays_o; e.rays_d = job.rays_d; e.n_rows = job.n_rows; e.P = job.P;
-        e.t = job.t; e.t_stride = job.t_stride; e.t_off = 0; e.midpoints = job.midpoints;
-        e.o_stride = job.P; e.o_off = 0;
-        e.sdf = w.f_sdf; e.rad = job.has_rad ? w.f_rad : nullptr;
-        e.apply_bg = 0;                                   // raw network sdf: the background mask below compares it with R - |x| itself
-        e.bound_r = job.bound_r; e.want_full = 1; e.multires_view = job.multires_view;
-        e.st_wide = st.wide; e.st_mpad = st.mpad; e.st_small = st.n(NP_SMALL);
-        // default: the 20 backward GEMMs run in the same tcgen05 launch (BW program of csrc/mlp_tmem.cu) and mlp_bwd_kernel is not used;
-        // NA_BWD_TMEM=0 keeps the forward-only stash launch + the SIMT / mma.sync backward kernel ("loaded mode")
-        const bool bw_tmem = [] { const char* e = getenv("NA_BWD_TMEM"); return !(e && e[0] == '0'); }();
-        if (bw_tmem && !fp32_bwd) {
-            e.bw = 1; e.bw_bg_mask = job.apply_bg; e.st_quad = 1; *quad_out = 1;
-            e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
-            e.st_emb = st.n(NP_EMB); e.st_vb0 = st.n(NP_VB0); e.st_t0 = st.t(0); e.st_t1 = st.t(1);
-            return launch_mlp(e, packed, fwd_precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream);
-        }
-        NA_TRY(launch_mlp(e, packed, fwd_precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream));
-        job.f_sdf = w.f_sdf; job.f_rad = w.f_rad;
-        if (fp32_bwd) mlp_bwd_kernel<false, true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
-        else          mlp_bwd_kernel<true, true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
-    } else {
-        if (fp32_bwd) mlp_bwd_kernel<false, false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
-        else          mlp_bwd_kernel<true, false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
-    }
+    if (fp32_bwd) mlp_bwd_kernel<false><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
+    else          mlp_bwd_kernel<true><<<grid, NT, smem, stream>>>(job, pk, L, tp, T, st, w.scratch);
     NA_CHECK_LAUNCH();
     return NA_OK;
 }
 
-// weight-gradient GEMMs + bias column sums of one mlp_bwd launch
-static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int train_surface, int train_radiance, float* gp, int quad,
-                        cudaStream_t stream) {
+// Tensor-core modes: ONE tcgen05 launch per patch (BW program of csrc/mlp_tmem.cu: forward re-evaluation with three-product operands,
+// then the 20 backward-data GEMMs), which leaves every (delta, input) pair in the bf16 stash; then the weight gradients
+// (csrc/wgrad_f16.cu).
+static int tc_backward(const BwdJob& job, const void* packed, int precision, const TrainWs& w, int train_surface, int train_radiance,
+                       float* gp, cudaStream_t stream) {
+    const int fwd_bf16 = 1;
+    const long long M = (long long)job.n_rows * job.P;
+    if (M <= 0) return NA_OK;
+    const size_t mpad = w.mpad;
+    unsigned short* nar = w.narrow16;
+    auto wp = [&](int p) { return w.wide16 + (size_t)p * mpad * 256; };
+    EvalJob e = {};
+    e.rays_o = job.rays_o; e.rays_d = job.rays_d; e.n_rows = job.n_rows; e.P = job.P;
+    e.t = job.t; e.t_stride = job.t_stride; e.t_off = 0; e.midpoints = job.midpoints;
+    e.o_stride = job.P; e.o_off = 0;
+    e.sdf = w.f_sdf; e.rad = job.has_rad ? w.f_rad : nullptr;
+    e.apply_bg = 0;                                   // raw network sdf: the background mask compares it with R - |x| itself
+    e.bound_r = job.bound_r; e.want_full = 1; e.multires_view = job.multires_view;
+    e.st_wide = w.wide16; e.st_mpad = mpad;
+    NA_TRY(make_stash_store_map(&e.st_store_map, w.wide16, N_WIDE, (long long)mpad));
+    e.st_emb = nar + (size_t)NP_EMB * mpad * ST_NLD; e.st_vb0 = nar + (size_t)NP_VB0 * mpad * ST_NLD; e.st_small = nar + (size_t)NP_SMALL * mpad * ST_NLD;
+    e.st_t0 = w.tiny; e.st_t1 = w.tiny + mpad * 4;
+    e.bw = 1; e.bw_bg_mask = job.apply_bg;
+    e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
+    const int fwd_precision = (precision == NA_PRECISION_TC_MIXED || precision == NA_PRECISION_TC2ACC) ? NA_PRECISION_TC : precision;   // softplus' needs the 3-product forward
+    NA_TRY(launch_mlp(e, packed, fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream));
+
     const GradPack G = grad_layout();
-    WgradTable wt; wt.n = 0; wt.total_blocks = 0; wt.quad = quad;
-    ColsumTable ct; ct.n = 0; ct.quad = quad;
+    WgF16Task tk[16]; int n = 0;
+    // L = a backward plane (bf16) or g_i (forward), R = the matching forward plane or v-bar (bf16)
+    auto add = [&](int l0, int l0_bf, int r0, int r0_bf, int l1, int l1_bf, int r1, int r1_bf, int npair, int r_narrow, int n_valid,
+                   size_t out, int ldo, size_t bias, bool has_bias) {
+        WgF16Task& t = tk[n++];
+        t.l_plane[0] = l0; t.r_plane[0] = r0; t.l_plane[1] = l1; t.r_plane[1] = r1;
+        t.l_bf16[0] = l0_bf; t.r_bf16[0] = r0_bf; t.l_bf16[1] = l1_bf; t.r_bf16[1] = r1_bf;
+        t.npair = npair; t.r_narrow = r_narrow; t.n_valid = n_valid; t.out = gp + out; t.ldo = ldo; t.bias_out = has_bias ? gp + bias : nullptr;
+    };
+    const int F = fwd_bf16;
+    const int sdim = small_dim(job.multires_view);
+    if (train_surface) {
+        // layer 0: [z-bar_0 x emb] + [g_0 x v-bar_0] (39-wide right operands); bias_0 = colsum(z-bar_0)
+        add(PL_ZB + 0, 1, NP_EMB, F, PL_G + 0, F, NP_VB0, 1, 2, 1, EMB, G.sdf_w[0], NLD, G.sdf_b[0], true);
+        for (int i = 1; i < 8; ++i)
+            add(PL_ZB + i, 1, PL_IN + i - 1, F, PL_G + i, F, PL_VB + i - 1, 1, 2, 0, 256, G.sdf_w[i], 256, G.sdf_b[i], true);
+        if (job.has_rad) add(PL_FB, 1, PL_IN + 7, F, 0, 0, 0, 0, 1, 0, 256, G.w8_feat, 256, G.b8_feat, true);
+    }
+    if (train_radiance && job.has_rad) {
+        add(PL_D + 0, 1, PL_FEAT, F, 0, 0, 0, 0, 1, 0, 256, G.rad_w0f, 256, G.rad_b[0], true);
+        add(PL_D + 0, 1, NP_SMALL, F, 0, 0, 0, 0, 1, 1, sdim, G.rad_w0s, NLD, 0, false);
+        for (int l = 1; l < 4; ++l) add(PL_D + l, 1, PL_YS + l - 1, F, 0, 0, 0, 0, 1, 0, 256, G.rad_w[l], 256, G.rad_b[l], true);
+    }
+    NA_TRY(launch_wgrad_f16(tk, n, w.wide16, N_WIDE, nar, 3, (long long)mpad, M, stream));
+    // rows whose left operand is a tiny fp32 plane: SDF head row 0 (+ the u-bar_7 column sums), radiance output layer
+    NA_TRY(launch_wgrad_tiny(train_surface ? wp(PL_IN + 7) : nullptr, wp(PL_VB + 7), (train_radiance && job.has_rad) ? wp(PL_YS + 3) : nullptr,
+                             e.st_t0, e.st_t1, gp + G.w8_sdf, gp + G.b8_sdf, gp + G.rad_w4, gp + G.rad_b4, M, fwd_bf16, stream));
+    return NA_OK;
+}
+
+// weight-gradient GEMMs + bias column sums of one mlp_bwd launch
+static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int train_surface, int train_radiance, float* gp, cudaStream_t stream) {
+    const GradPack G = grad_layout();
+    WgradTable wt; wt.n = 0; wt.total_blocks = 0;
+    ColsumTable ct; ct.n = 0;
     static const int wgrad_mode = [] { const char* e = getenv("NA_WGRAD"); return !e ? 0 : (strcmp(e, "fp32") == 0 ? 2 : (strcmp(e, "mma") == 0 ? 1 : 0)); }();
-    WgTcTask tc[16]; int n_tc = 0;                 // 256 x 256 tasks on wide quad-layout planes -> tcgen05 (csrc/wgrad_tc.cu)
     auto addw = [&](const float* Lp, int ldl, int nl, const float* Rp, int ldr, int nr, const float* L2, const float* R2, size_t out, int ldo) {
-        if (quad && wgrad_mode == 0 && ldl == 256 && ldr == 256 && nl == 256 && nr == 256 && n_tc < 16) {
-            WgTcTask& c = tc[n_tc++];
-            c.L[0] = Lp; c.R[0] = Rp; c.L[1] = L2; c.R[1] = R2; c.out = gp + out; c.ldo = ldo; c.npair = L2 ? 2 : 1;
-            return;
-        }
         WgradTask& t = wt.t[wt.n++];
         t.L = Lp; t.R = Rp; t.L2 = L2; t.R2 = R2; t.out = gp + out; t.ldl = ldl; t.ldr = ldr; t.nl = nl; t.nr = nr; t.ldo = ldo;
         t.blk0 = wt.total_blocks; t.nbr = (nr + 127) / 128;
@@ -1280,7 +1299,6 @@ static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int trai
         addc(st.t(0), 4, 4, G.rad_b4);
     }
     const long long tiles = (m_rows + TM - 1) / TM;
-    if (n_tc) NA_TRY(launch_wgrad_tc(tc, n_tc, tiles, stream));
     if (wt.n == 0 && ct.n == 0) return NA_OK;
     int splits = (int)((4LL * num_sms() + wt.total_blocks - 1) / wt.total_blocks);
     if (splits > tiles) splits = (int)tiles;
@@ -1300,10 +1318,8 @@ static int launch_wgrad(const Stash& st, long long m_rows, int has_rad, int trai
 }
 
 int preload_train() {
-    NA_PRELOAD((mlp_bwd_kernel<true, false>));
-    NA_PRELOAD((mlp_bwd_kernel<false, false>));
-    NA_PRELOAD((mlp_bwd_kernel<true, true>));
-    NA_PRELOAD((mlp_bwd_kernel<false, true>));
+    NA_PRELOAD((mlp_bwd_kernel<true>));
+    NA_PRELOAD((mlp_bwd_kernel<false>));
     NA_PRELOAD(wgrad_kernel);
     NA_PRELOAD(wgrad_tf32_kernel);
     NA_PRELOAD(colsum_kernel);
@@ -1320,10 +1336,22 @@ using namespace na;
 
 extern "C" size_t na_grad_pack_bytes(const NaNetDesc* desc) { (void)desc; return grad_layout().total * sizeof(float); }
 
-extern "C" size_t na_train_workspace_bytes(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray) {
+extern "C" size_t na_train_workspace_bytes_mode(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray, int32_t precision) {
     (void)desc;
     if (n_rays <= 0 || points_per_ray <= 1) return 0;
-    return train_ws(nullptr, n_rays, points_per_ray).total;
+    return train_ws(nullptr, n_rays, points_per_ray, bwd_on_tensor_cores(precision)).total;
+}
+extern "C" int na_debug_wgrad_f16(const void* planes16, int64_t m_pad, int64_t m_rows, int l_bf16, int r_bf16, float* out, float* bias_out, void* stream) {
+    if (!planes16 || !out || m_pad <= 0 || m_rows <= 0 || m_rows > m_pad) return NA_ERR_BAD_ARG;
+    WgF16Task t = {};
+    t.l_plane[0] = 0; t.r_plane[0] = 1; t.l_bf16[0] = l_bf16; t.r_bf16[0] = r_bf16; t.npair = 1; t.r_narrow = 0; t.n_valid = 256; t.ldo = 256;
+    t.out = out; t.bias_out = bias_out;
+    return launch_wgrad_f16(&t, 1, (const unsigned short*)planes16, 2, nullptr, 0, m_pad, m_rows, (cudaStream_t)stream);
+}
+extern "C" size_t na_train_workspace_bytes(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray) {
+    const size_t a = na_train_workspace_bytes_mode(desc, n_rays, points_per_ray, NA_PRECISION_FP32);
+    const size_t b = na_train_workspace_bytes_mode(desc, n_rays, points_per_ray, NA_PRECISION_TC);
+    return a > b ? a : b;
 }
 
 static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o, const float* rays_d,
@@ -1334,7 +1362,8 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     if (n <= 0) return NA_OK;
     const int P = cfg->points_per_ray;
     if (P < 2 || n * (int64_t)P > 0x7fffffffLL) return NA_ERR_UNSUPPORTED;
-    const TrainWs w = train_ws(ws_, n, P);
+    const bool tc = bwd_on_tensor_cores(cfg->precision);
+    const TrainWs w = train_ws(ws_, n, P, tc);
     if (ws_bytes < w.total) return NA_ERR_WORKSPACE;
     const PackF32 L = pack_layout_f32(desc->multires_view);
     const PackTrain T = pack_layout_train();
@@ -1350,30 +1379,31 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     else      volsdf_composite_bwd_kernel<<<(int)((n + 127) / 128), 128, 0, stream>>>(a);
     NA_CHECK_LAUNCH();
     const size_t M = (size_t)n * P, mpad = (M + TM - 1) / TM * TM;
-    Stash st; st.mpad = mpad; st.wide = w.stash; st.narrow = w.stash + (size_t)N_WIDE * mpad * 256; st.tiny = st.narrow + 3 * mpad * NLD;
+    Stash st; st.mpad = mpad; st.wide = w.stash; st.narrow = w.stash + (size_t)N_WIDE * mpad * 256; st.tiny = st.narrow + 3 * mpad * NLD;      // fp32 mode only
+    auto backward = [&](const BwdJob& j, long long rows, int ts, int tr) -> int {
+        if (tc) return tc_backward(j, packed, cfg->precision, w, ts, tr, gp, stream);
+        NA_TRY(launch_mlp_bwd(j, pk, L, tp, T, st, w, stream));
+        return launch_wgrad(st, rows, j.has_rad, ts, tr, gp, stream);
+    };
     BwdJob job = {};
     job.rays_o = rays_o; job.rays_d = w.dirs; job.n_rows = (int)n; job.t = d_all; job.t_stride = P;
     job.multires_view = desc->multires_view; job.bound_r = desc->bounding_radius;
     const bool has_eik = cfg->w_eikonal != 0.f;
-    int quad = 0;                                   // set by launch_mlp_bwd: the stash planes of this launch are in the quad layout
     if (!neus) {
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = w.g_rad;
         job.apply_bg = 1; job.has_rad = 1;
-        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, &quad, stream));
-        NA_TRY(launch_wgrad(st, (long long)M, 1, cfg->train_surface, cfg->train_radiance, gp, quad, stream));
+        NA_TRY(backward(job, (long long)M, cfg->train_surface, cfg->train_radiance));
     } else {
         // pass A: the P points of d_all (sdf -> alpha, nabla -> eikonal); pass B: the P-1 midpoints (radiance), neus.py:320-324
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = nullptr;
         job.apply_bg = 0; job.has_rad = 0;
         const char* dbg_pass = getenv("NA_BWD_DEBUG_PASS");                 // diagnostics: "A" / "B" runs only that pass
         if (cfg->train_surface && !(dbg_pass && dbg_pass[0] == 'B')) {
-            NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, &quad, stream));
-            NA_TRY(launch_wgrad(st, (long long)M, 0, 1, 0, gp, quad, stream));
+            NA_TRY(backward(job, (long long)M, 1, 0));
         }
         if (dbg_pass && dbg_pass[0] == 'A') return NA_OK;
         job.P = P - 1; job.midpoints = 1; job.g_sdf = nullptr; job.g_nab = nullptr; job.g_rad = w.g_rad; job.has_rad = 1;
-        NA_TRY(launch_mlp_bwd(job, packed, cfg->precision, pk, L, tp, T, st, w, &quad, stream));
-        NA_TRY(launch_wgrad(st, (long long)n * (P - 1), 1, cfg->train_surface, cfg->train_radiance, gp, quad, stream));
+        NA_TRY(backward(job, (long long)n * (P - 1), cfg->train_surface, cfg->train_radiance));
     }
     return NA_OK;
 }

@@ -227,7 +227,7 @@ class NetEngine:
         P = d_all.shape[-1]
         cfg = NaTrainCfg(int(P), float(w_eikonal), int(eikonal_count), int(bool(white_bkgd)), float(speed_factor),
                          int(bool(train_surface)), int(bool(train_radiance)), PRECISIONS[self.precision])
-        nbytes = L.na_train_workspace_bytes(C.byref(self.desc), n, P)
+        nbytes = L.na_train_workspace_bytes_mode(C.byref(self.desc), n, P, PRECISIONS[self.precision])
         if getattr(self, '_tws', None) is None or self._tws.device != dev or self._tws.numel() < nbytes:
             self._tws = None
             self._tws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)

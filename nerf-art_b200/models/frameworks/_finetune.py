@@ -138,17 +138,27 @@ def finetune_forward(trainer, framework, args, model_input, ground_truth, render
     c2w = model_input['c2w'].to(device)
     H = render_kwargs_train['H']
     W = render_kwargs_train['W']
-    rays_o, rays_d, select_inds = rend_util.get_rays(c2w, intrinsics, H, W, -1)     # fine-tune: all rays, not shuffled
-    target_rgb = torch.gather(ground_truth['rgb'].to(device), 1, torch.stack(3 * [select_inds], -1))
-    use_eik = bool(args.finetune.use_eikonal)
     world, rank = parallel.world_rank()
+    gt_rgb = ground_truth['rgb'].to(device)
+    if world > 1:
+        # one image per step for the whole job: rank 0's camera / target and one RNG stream for the style-loss draws
+        c2w, intrinsics, gt_rgb = [t.contiguous() for t in (c2w.float(), intrinsics.float(), gt_rgb.float())]
+        parallel.sync_step_inputs([c2w, intrinsics, gt_rgb])
+    rays_o, rays_d, select_inds = rend_util.get_rays(c2w, intrinsics, H, W, -1)     # fine-tune: all rays, not shuffled
+    target_rgb = torch.gather(gt_rgb, 1, torch.stack(3 * [select_inds], -1))
+    use_eik = bool(args.finetune.use_eikonal)
     n_rays = rays_o.shape[1]
-    lo, hi, _ = parallel.ray_block(n_rays, rank, world)
-    with torch.no_grad():                                                            # pass 1 (this rank's block of rays)
-        rgb, depth_v, _ = trainer.renderer(rays_o[:, lo:hi], rays_d[:, lo:hi], detailed_output=False,
+    idx = parallel.rank_rays(n_rays, rank, world, H, W, device=device)               # None: contiguous block; else interleaved tiles
+    if idx is None:
+        lo, hi, _ = parallel.ray_block(n_rays, rank, world)
+        ro1, rd1 = rays_o[:, lo:hi], rays_d[:, lo:hi]
+    else:
+        ro1, rd1 = rays_o[:, idx], rays_d[:, idx]
+    with torch.no_grad():                                                            # pass 1 (this rank's share of the rays)
+        rgb, depth_v, _ = trainer.renderer(ro1, rd1, detailed_output=False,
                                            use_view_dirs=args.model.radiance.use_view_dirs,
                                            require_nablas=use_eik or args.model.radiance.use_view_dirs, **render_kwargs_train)
-        rgb = parallel.gather_tiles(rgb[0], n_rays)[None]                            # every rank scores the whole image
+        rgb = parallel.gather_rays(rgb[0], n_rays, idx, H, W)[None]                  # every rank scores the whole image
     rgb = rgb.detach().requires_grad_(True)
     losses = calc_style_loss(trainer, rgb, target_rgb, args, H)
     losses.backward()

@@ -30,6 +30,7 @@ def make_checkout(tmp_path, n_images=3):
     sys.path.insert(0, os.path.join(ROOT, 'scripts'))
     import apply_level1
     apply_level1.apply(dst)
+    os.makedirs(os.path.join(dst, 'debug_tools'), exist_ok=True)      # utils/io_util.py:78 backs up a directory the public tree lacks
     # synthetic scene in the DTU layout the shipped configs point at (data_dir ./data/fangzhou_nature): real camera file of the
     # reference, synthetic 960 x 540 portraits (smooth colour gradients) and full mattes
     scene = os.path.join(dst, 'data', 'fangzhou_nature')

@@ -171,6 +171,30 @@ def test_volsdf_backward_vs_oracle_many_tiles(precision):
     assert np.abs(fwd['rgb'].cpu().numpy() - orgb).max() < (1e-4 if precision == 'fp32' else 1e-3)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_backward_reads_no_uninitialised_workspace(precision):
+    """Ragged patch (333 rays x 48 points = 124.9 tiles) through a workspace poisoned with NaN: the stash rows of the last tile's
+    padding samples are read by the weight-gradient kernels, so every one of them must have been written (with zero gradient)."""
+    m = make_volsdf(0.05, 0.5, device=DEV)
+    m.engine().precision = precision
+    from nerfart_b200.models.frameworks.volsdf import render_patch
+    from nerfart_b200.utils import rend_util
+    c2w, K = fx.tilted_camera(37, 9)
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(DEV), K[None].to(DEV), 37, 9)
+    ro, rd = ro[0].contiguous(), rd[0].contiguous()
+    fwd, _ = render_patch(m, ro, rd, N_samples=32, N_importance=16, max_upsample_steps=6)
+    G = torch.full((ro.shape[0], 3), 0.02, device=DEV)
+    clean, sc = product_grads(m, 'volsdf', ro, rd, fwd, G, 0.1, False)
+    eng = m.engine()
+    eng._tws.view(torch.float32).fill_(float('nan'))
+    dirty, sd = product_grads(m, 'volsdf', ro, rd, fwd, G, 0.1, False)
+    for k in clean:
+        assert np.isfinite(dirty[k]).all(), k
+        assert np.abs(dirty[k] - clean[k]).max() <= 2e-5 * np.abs(clean[k]).max() + 1e-9, k      # atomics: summation order only
+    assert np.isfinite(sd).all()
+
+
 def test_backward_accumulates_over_patches_and_is_deterministic_in_structure():
     """two half patches accumulate to the gradient of the whole patch (same eikonal normaliser): the GradPack is additive"""
     g = golden('train_volsdf_b0.1')
@@ -305,3 +329,32 @@ def test_trainer_forward_finetune_step_neus(monkeypatch, precision):
     print(f'NeuS Trainer.forward [{precision}]: worst relative parameter-gradient error vs oracle', worst)
     assert worst < TOL[precision][0]
     opt.step()
+
+
+@pytest.mark.parametrize('l_bf16,r_bf16', [(0, 0), (1, 1)])          # (tcgen05 kind::f16 rejects an fp16 operand against a bf16 one)
+@pytest.mark.parametrize('m_rows', [64, 128 * 37 + 50, 230400])
+def test_wgrad_f16_kernel_vs_torch(l_bf16, r_bf16, m_rows):
+    """csrc/wgrad_f16.cu alone (TMA-fed MN-major tcgen05 GEMM over sample-major 16-bit planes): out = L^T R and the column sums of L
+    against torch in float64 on the same 16-bit values; fp16 and bf16 operands; ragged and full-patch sample counts."""
+    import ctypes as C
+    import nerfart_b200
+    from nerfart_b200._lib import check
+    lib = nerfart_b200.lib()
+    m_pad = (m_rows + 127) // 128 * 128
+    g = torch.Generator(device=DEV); g.manual_seed(7)
+    dt = [torch.bfloat16 if l_bf16 else torch.float16, torch.bfloat16 if r_bf16 else torch.float16]
+    Lp = (torch.randn(m_pad, 256, device=DEV, generator=g) * torch.rand(m_pad, 1, device=DEV, generator=g)).to(dt[0])
+    Rp = torch.randn(m_pad, 256, device=DEV, generator=g).to(dt[1])
+    Lp[m_rows:] = 0                                                    # padding rows carry zero gradient planes
+    planes = torch.empty(2, m_pad, 256, dtype=torch.int16, device=DEV)
+    planes[0] = Lp.view(torch.int16); planes[1] = Rp.view(torch.int16)
+    out = torch.zeros(256, 256, device=DEV); bias = torch.zeros(256, device=DEV)
+    check(lib.na_debug_wgrad_f16(C.c_void_p(planes.data_ptr()), m_pad, m_rows, l_bf16, r_bf16, C.c_void_p(out.data_ptr()),
+                                 C.c_void_p(bias.data_ptr()), None), 'na_debug_wgrad_f16')
+    torch.cuda.synchronize()
+    ref = Lp[:m_rows].double().t() @ Rp[:m_rows].double()
+    bref = Lp[:m_rows].double().sum(0)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    berr = float((bias.double() - bref).abs().max() / (bref.abs().max() + 1e-30))
+    print(f'wgrad_f16 m={m_rows} fmt=({l_bf16},{r_bf16}): rel err {err:.2e}, bias {berr:.2e}')
+    assert err < 2e-5 and berr < 2e-5                                   # products are exact in fp32; only the summation order differs

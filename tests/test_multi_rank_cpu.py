@@ -126,3 +126,76 @@ def test_training_patches_round_robin_and_gradient_allreduce_gloo():
         assert abs(lnb[0] - G.double().sum().item()) < 1e-4
     assert [c[0] for c in res[0][3]] == [100, 100, 100, 100] and [c[0] for c in res[1][3]] == [100, 100, 100, 30]
     assert all(c[1] == c[0] * 6 for r in res for c in r[3])
+
+
+def _sync_worker(rank, world, port, q):
+    import random
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(100 + rank); random.seed(200 + rank)               # ranks start out of step, as after a DistributedSampler
+    c2w = torch.eye(4)[None] * (rank + 1); gt = torch.full((1, 12, 3), float(rank))
+    parallel.sync_step_inputs([c2w, gt])
+    draws = (random.choice(range(1000)), random.sample(range(1000), 8), torch.randint(0, 1000, (5,)).tolist())
+    q.put((rank, c2w[0, 0, 0].item(), gt.mean().item(), draws))
+    dist.destroy_process_group()
+
+
+def test_finetune_step_inputs_and_rng_are_identical_on_every_rank_gloo():
+    """the multi-rank fine-tune step equals the single-GPU step only if every rank scores the same image with the same
+    random draws: rank 0's camera / target are broadcast and all ranks are seeded from one value."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1] == 1.0 and res[0][2] == res[1][2] == 0.0          # rank 0's tensors everywhere
+    assert res[0][3] == res[1][3]                                                    # identical draws
+
+
+def test_tile_partition_covers_every_ray_once_and_is_balanced():
+    for (H, W, world) in ((480, 270, 8), (960, 540, 8), (64, 64, 3), (37, 9, 2), (5, 5, 4)):
+        order, off = parallel.tile_partition(H, W, world)
+        assert sorted(order.tolist()) == list(range(H * W)) and off[0] == 0 and off[-1] == H * W
+        counts = [off[r + 1] - off[r] for r in range(world)]
+        if H * W >= 64 * 64:
+            assert max(counts) - min(counts) <= 16 * 16 * 2 + 16 * max(H, W) // 4, counts     # within ~2 tiles (+ ragged edge tiles)
+        assert parallel.rank_rays(H * W, 0, world, H, W, mode='block') is None
+        if world > 1:
+            got = parallel.rank_rays(H * W, 1, world, H, W, mode='tiles')
+            assert torch.equal(got, order[off[1]:off[2]])
+            # a rank's rays are spread over the whole image (what balances the sampler load), not one band
+            rows = (got // W).float()
+            if H >= 64:
+                assert rows.min() < H * 0.25 and rows.max() > H * 0.75
+
+
+def _tiles_worker(rank, world, port, H, W, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    n = H * W
+    g = torch.Generator().manual_seed(5)
+    ro = torch.randn(n, 3, generator=g); rd = torch.randn(n, 3, generator=g)
+    idx = parallel.rank_rays(n, rank, world, H, W, mode='tiles')
+    mine = _fake_render(ro[idx], rd[idx])[0]
+    full = parallel.gather_rays(mine, n, idx, H, W)
+    q.put((rank, bool(torch.equal(full, _fake_render(ro, rd)[0]))))
+    dist.destroy_process_group()
+
+
+def test_interleaved_tile_gather_equals_single_rank_gloo():
+    world, H, W = 2, 37, 21
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tiles_worker, args=(r, world, port, H, W, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

@@ -123,7 +123,7 @@ def compare_volsdf(out, G, name, scale=1.0, min_same=0.985):
     conv_g = (G['iter_usage'].reshape(n) >= 0) if 'iter_usage' in G else np.ones(n, dtype=bool)
     # rays the reference itself converged on must follow the same path almost always
     assert (same | ~conv_g).mean() > min_same, 'converged rays took a different sampler path'
-    assert frac_div < 0.75
+    assert frac_div < 0.35, frac_div          # reference vs oracle: 25 %; fp32 kernels 28 %; default tc mode 29.5 % (profiles/r3b_tc_accumulation.md)
     for k, tol_med, tol_max in (('rgb', 3e-6, 3e-3), ('depth_volume', 1e-5, 3e-2), ('mask_volume', 2e-6, 2e-4), ('normals_volume', 3e-5, 3e-2)):
         if k not in out or k not in G:
             continue
