@@ -174,6 +174,64 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def train_probe(dev, precision, n_patches=8):
+    """Short probe of the fine-tune step's pass 2 (BASELINE configs 3 / 5): `n_patches` patches of 1200 rays, forward render with
+    detailed outputs + backward kernels, for the VolSDF frame of this bench and for a NeuS model (configs/neus_fangzhou_vangogh.yaml
+    geometry, 64 + 64 samples).  Event-timed after one warm-up patch; the full step is `bench.py --workload train`."""
+    import nerfart_b200  # noqa: F401
+    from helpers import make_volsdf, make_neus
+    import fixtures as fx
+    from nerfart_b200.models.frameworks import volsdf as pv, neus as pn
+    from nerfart_b200.utils import rend_util
+    F_BWD = 2 * (2 * 265216 + 2 * 524544 + 2 * 459008)
+    out = {}
+    pk, _ = peaks()
+    for fw in ('volsdf', 'neus'):
+        if fw == 'volsdf':
+            m = make_volsdf(0.1, 0.0, device=dev).train()
+            c2w, K = fx.closed_form_camera(H, W)
+            kw = dict(near=0.0, far=6.0, perturb=True, max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
+            patch = lambda ro, rd: pv.render_patch(m, ro, rd, **kw)
+            pts = P
+        else:
+            m = make_neus(0.05, 0.0, device=dev).train()
+            c2w, K = fx.closed_form_camera(H, W)
+            c2w = c2w.clone(); c2w[2, 3] = -0.9                                  # inside NeuS' unit bounding sphere
+            kw = dict(upsample_algo='official_solution', N_upsample_iters=4, N_outside=0, obj_bounding_radius=1.0, perturb=True,
+                      N_samples=64, N_importance=64)
+            patch = lambda ro, rd: pn.render_patch(m, ro, rd, **kw)
+            pts = 128
+        m.engine().precision = precision
+        with torch.no_grad():
+            ro, rd, _ = rend_util.get_rays(c2w[None].to(dev), K[None].to(dev), H, W)
+        eng = m.engine(); eng.grad_zero()
+        G = torch.full((1200, 3), 1e-3, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_f = t_b = 0.0
+        for k in range(n_patches + 1):
+            i = 1200 * (40 + k)
+            rop, rdp = ro[0, i:i + 1200].contiguous(), rd[0, i:i + 1200].contiguous()
+            ev[0].record()
+            fwd, scal = patch(rop, rdp)
+            ev[1].record()
+            eng.render_bwd(rop, rdp, scal, fwd, G, w_eikonal=0.1, eikonal_count=1200 * pts, white_bkgd=False, speed_factor=m.speed_factor,
+                           train_radiance=(fw == 'volsdf'))
+            ev[2].record(); torch.cuda.synchronize()
+            if k > 0:
+                t_f += ev[0].elapsed_time(ev[1]); t_b += ev[1].elapsed_time(ev[2])
+        eng.unpack_grads(True, fw == 'volsdf')
+        torch.cuda.synchronize()
+        out[fw] = {'patches': n_patches, 'rays_per_patch': 1200, 'points_per_ray': pts, 'patch_forward_ms': t_f / n_patches,
+                   'patch_backward_ms': t_b / n_patches, 'samples_per_s': 1200 * pts * n_patches / ((t_f + t_b) * 1e-3)}
+        if fw == 'volsdf':
+            ach = 1200 * pts * F_BWD / (t_b / n_patches * 1e-3) / 1e12
+            out[fw]['backward_roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops'],
+                                            'flop_per_sample': F_BWD}
+        del m, eng
+        torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(args, extra=None):
     c = {'workload': f'VolSDF fangzhou_nature-shaped synthetic render {H}x{W} ({H*W} rays), N_samples={N_SAMPLES}, N_importance={N_IMPORTANCE}, '
                      'd_init=512, seed-0 sphere init beta=0.1, radiance gains x3, closed-form camera',
@@ -325,6 +383,9 @@ def main():
                 'frame_flop': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL),
                 'frame_frac_of_peak': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL) / (t_dev / args.steps) / 1e12 / peak / world}
         del x, v
+    probe = None
+    if rank == 0 and not light and world == 1:
+        probe = train_probe(dev, args.precision)
     cpu = None
     ref_gpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -362,7 +423,7 @@ def main():
                 'all_evals_per_s': n_rays * (4 * N_SAMPLES + P) * args.steps / t_dev,
                 'e2e': {'value': samples / t_e2e, 'unit': 'samples/s', 'ms_per_step': 1e3 * t_e2e / args.steps,
                         'h2d_bytes_per_step': 2 * 16 * 4, 'd2h_bytes_per_step': n_rays * 3 * 4},
-                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu}
+                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'train_probe': probe}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -413,10 +413,9 @@ extern "C" int na_clip_vitb32_encode_bwd(const NaClipWeights* Wt, const float* g
     cudaStream_t s = (cudaStream_t)stream_;
     float* ws = (float*)ws_;
     const int T = B * TOK;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_done[64] = {false};
+    if (first_on_device(attr_done)) {
         NA_TRY(check_cuda(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_BWD_SMEM)));
-        attr_set = true;
     }
     const Packed P = packed_layout();
     const Gemm gemm{Wt->precision == NA_CLIP_TF32 ? (const unsigned char*)Wt->packed : nullptr, s};

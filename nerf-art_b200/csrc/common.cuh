@@ -27,6 +27,14 @@ inline int check_cuda(cudaError_t e) {
 #define NA_PRELOAD(k) do { cudaFuncAttributes _a; NA_TRY(na::check_cuda(cudaFuncGetAttributes(&_a, k))); } while (0)
 
 int num_sms();
+// true the first time it is called for (flag array, current device): cudaFuncSetAttribute is per device, not per thread
+inline bool first_on_device(bool (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Stall diagnostics.  Every mbarrier wait of the tcgen05 kernels is bounded (SPIN_LIMIT_NS of wall clock, %globaltimer): a wait

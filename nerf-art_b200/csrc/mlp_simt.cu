@@ -287,11 +287,10 @@ size_t mlp_simt_scratch_bytes(int grid) { return (size_t)grid * 9 * 256 * TM * s
 
 int launch_mlp_simt(const EvalJob& job, const float* packed, const PackF32& L, float* scratch, size_t scratch_bytes,
                     cudaStream_t stream) {
-    static thread_local bool attr_set = false;
+    static bool attr_done[64] = {false};
     const size_t smem = sizeof(MlpSmem);
-    if (!attr_set) {
+    if (first_on_device(attr_done)) {
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        attr_set = true;
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;

@@ -740,15 +740,14 @@ long long* g_tc_dbg = nullptr;
 int launch_mlp_tc(const EvalJob& job_, const unsigned char* packed_base, size_t f32_bytes, const PackF32& L, float* scratch,
                   size_t scratch_bytes, cudaStream_t stream) {
     EvalJob job = job_; job.dbg = g_tc_dbg;
-    static thread_local bool attr_set = false;
+    static bool attr_done[64] = {false};
     static const bool two = []{ const char* e = getenv("NA_TC_TWO_ACC"); return e ? atoi(e) != 0 : (NA_TC_TWO_ACC != 0); }();
     const size_t smem = sizeof(TcSmem) + 1024;
-    if (!attr_set) {
+    if (first_on_device(attr_done)) {
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        attr_set = true;
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;

@@ -203,6 +203,7 @@ struct EpiCtx {
     unsigned st_stg;                // ST: this warp's two 1 KB staging buffers in shared memory
     int st_row0;                    // ST: first sample (row of the plane) of this warp's 32 lanes in the current tile
     mutable unsigned st_cnt;        // ST: TMA stores issued by this warp so far (buffer parity)
+    unsigned long long st_policy;   // ST: L2 evict-first cache policy of the stash stores
     // BW: per-row power-of-two scale of the upstream gradient (the backward is linear in it and rows are independent, so every
     // backward quantity of the row is carried x rs in the fp16 operands and stored x irs) and the row's total d L / d nabla (x rs)
     float rs, irs, nbar[3];
@@ -312,8 +313,9 @@ __device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (c.lane == 0) {
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                     :: "l"(c.st_map), "r"(col0), "r"((int)((size_t)plane * (c.st_plane >> 8)) + c.st_row0), "r"(buf) : "memory");
+        // L2 evict-first: the planes stream out to HBM and must not displace the per-CTA scratch (read back three times per tile)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                     :: "l"(c.st_map), "r"(col0), "r"((int)((size_t)plane * (c.st_plane >> 8)) + c.st_row0), "r"(buf), "l"(c.st_policy) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     ++c.st_cnt;
@@ -351,39 +353,21 @@ __device__ __forceinline__ void qstore16(uint4* base, int plane, int col0, int r
         p[(size_t)j8 * TM] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
-__device__ __forceinline__ void qload16(const uint4* base, int plane, int col0, int r, float (&v)[16]) {
-    const uint4* p = base + (size_t)(plane * 32 + (col0 >> 3)) * TM + r;
+// decode of the prefetched rows: parked fp16 terms (x 2^-8), bf16 stash rows
+__device__ __forceinline__ void qdecode16(const uint4 (&q)[2], float (&v)[16]) {
 #pragma unroll
     for (int j8 = 0; j8 < 2; ++j8) {
-        const uint4 q = p[(size_t)j8 * TM];
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        const unsigned w[4] = {q[j8].x, q[j8].y, q[j8].z, q[j8].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x * 256.f; v[8 * j8 + 2 * i + 1] = f.y * 256.f; }
     }
 }
-// BW: 16 consecutive columns of this thread's row from a stash plane this warp stored earlier in the tile (after stash_flush);
-// L1-bypassing loads: the plane was written by the TMA engine
-__device__ __forceinline__ void stash_load16(const EpiCtx& c, int plane, int col0, float (&v)[16]) {
-    const uint4* p = reinterpret_cast<const uint4*>(c.st_row + (size_t)plane * c.st_plane + col0);
+__device__ __forceinline__ void bf16x16_to_float(const uint4 (&q)[2], float (&v)[16]) {
 #pragma unroll
     for (int j8 = 0; j8 < 2; ++j8) {
-        const uint4 q = __ldcg(p + j8);
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        const unsigned w[4] = {q[j8].x, q[j8].y, q[j8].z, q[j8].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-            v[8 * j8 + 2 * i] = f.x; v[8 * j8 + 2 * i + 1] = f.y;
-        }
-    }
-}
-// BW: softplus'(z_lyr) of 16 columns from the 16-bit codes the forward epilogue left in the per-CTA scratch
-__device__ __forceinline__ void sload16(const EpiCtx& c, int lyr, int col0, float (&v)[16]) {
-    const uint2* p = c.dh + (size_t)(lyr * 64 + (col0 >> 2)) * TM + c.r;
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-        float d4[4];
-        dh_decode4(p[(size_t)j4 * TM], d4);
-        v[4 * j4] = d4[0]; v[4 * j4 + 1] = d4[1]; v[4 * j4 + 2] = d4[2]; v[4 * j4 + 3] = d4[3];
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i])); v[8 * j8 + 2 * i] = f.x; v[8 * j8 + 2 * i + 1] = f.y; }
     }
 }
 
@@ -419,6 +403,27 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) qn[j4] = dhp[(size_t)(((col0 + 64) >> 2) + j4) * TM];
             }
+        }
+        // BW: the scratch / stash rows this pass needs (softplus' codes, g, parked terms) are requested BEFORE the wait for D, so that
+        // their L2 / DRAM latency runs under the GEMM instead of on the epilogue's critical path
+        constexpr bool PRE_S = KIND == K_SO || KIND == K_SO3 || KIND == K_SO7 || KIND == K_TR;
+        constexpr bool PRE_G = KIND == K_SO || KIND == K_SO3 || KIND == K_SO7;
+        constexpr bool PRE_Q = KIND == K_TR || KIND == K_SO7;
+        uint2 sraw[4]; uint4 graw[2], qraw[2];
+        if (PRE_S) {
+            const uint2* p = c.dh + (size_t)(c.lyr * 64 + (col0 >> 2)) * TM + r;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) sraw[j4] = p[(size_t)j4 * TM];
+        }
+        if (PRE_G) {
+            if (c.lyr == 0 && c16 == 0) stash_flush(c);              // the g planes (TMA-stored during the reverse sweep) are read back from here on
+            const uint4* p = reinterpret_cast<const uint4*>(c.st_row + (size_t)(ST_G + c.lyr) * c.st_plane + col0);
+            graw[0] = __ldcg(p); graw[1] = __ldcg(p + 1);
+        }
+        if (PRE_Q) {
+            const uint4* p = c.qp + (size_t)((KIND == K_TR ? c.lyr : 7) * 32 + (col0 >> 3)) * TM + r;
+            if (KIND == K_TR || c.has_rad) { qraw[0] = p[0]; qraw[1] = p[TM]; }
+            else { qraw[0] = make_uint4(0u, 0u, 0u, 0u); qraw[1] = qraw[0]; }
         }
         {                                                            // pass c16 reads N-quarter c16 of D
             const long long t0 = clock64();
@@ -570,9 +575,9 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             } else if (KIND == K_SO || KIND == K_SO3 || KIND == K_SO7) {
                 // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
                 float sv[16], gv[16], q[16];
-                sload16(c, c.lyr, col0, sv);
-                if (c.lyr == 0 && c16 == 0) stash_flush(c);          // the g planes (stored during the reverse sweep) are read back from here on
-                stash_load16(c, ST_G + c.lyr, col0, gv);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) { float d4[4]; dh_decode4(sraw[j4], d4); sv[4 * j4] = d4[0]; sv[4 * j4 + 1] = d4[1]; sv[4 * j4 + 2] = d4[2]; sv[4 * j4 + 3] = d4[3]; }
+                bf16x16_to_float(graw, gv);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float gb = acc[j] * us;
@@ -587,11 +592,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 if (KIND == K_SO7) {
                     // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]
                     float hb[16];
-                    if (c.has_rad) qload16(c.qp, 7, col0, r, hb);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) hb[j] = 0.f;
-                    }
+                    qdecode16(qraw, hb);
                     const float gs = S.BWV[6 * TM + r];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -610,8 +611,9 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             } else {
                 // trunk, K_TR: z-bar_lyr = h-bar_lyr s_lyr + q_lyr
                 float sv[16], qv[16];
-                sload16(c, c.lyr, col0, sv);
-                qload16(c.qp, c.lyr, col0, r, qv);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) { float d4[4]; dh_decode4(sraw[j4], d4); sv[4 * j4] = d4[0]; sv[4 * j4 + 1] = d4[1]; sv[4 * j4 + 2] = d4[2]; sv[4 * j4 + 3] = d4[3]; }
+                qdecode16(qraw, qv);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j] * us, sv[j], qv[j]);
                 stash16(c, ST_ZB + c.lyr, col0, o, c.irs);
@@ -946,6 +948,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
         c.st_m = 0; c.st_map = &job.st_store_map; c.st_cnt = 0; c.st_row0 = 0;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.st_policy));
         c.st_stg = smem_u32(S.Wst) + (unsigned)(NS - 1) * STAGE_BYTES + (unsigned)(warp - 2) * 2048u;
         c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = job.rad != nullptr;
         c.bw = BW ? 1 : 0;
@@ -1381,15 +1384,14 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
                     unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
     using namespace tm;
     EvalJob job = job_; job.dbg = g_tc_dbg;
-    static thread_local bool attr_set = false;
+    static bool attr_done[64] = {false};
     // NA_TM_PRODS: diagnostics override, a 21-character string of '1'/'3' (products per GEMM of the program)
     static const char* prods_env = getenv("NA_TM_PRODS");
     const size_t smem = sizeof(Smem) + 1024;
-    if (!attr_set) {
+    if (first_on_device(attr_done)) {
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        attr_set = true;
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;

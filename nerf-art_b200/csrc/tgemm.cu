@@ -268,11 +268,10 @@ int tgemm(const float* A, const unsigned char* img, float* C, int M, int N, int 
           const float* R, cudaStream_t stream) {
     using namespace tg;
     if (N % BN || K % BK || M <= 0) return NA_ERR_UNSUPPORTED;
-    static thread_local bool attr_set = false;
+    static bool attr_done[64] = {false};
     const size_t smem = sizeof(Smem) + 1024;
-    if (!attr_set) {
+    if (first_on_device(attr_done)) {
         NA_TRY(check_cuda(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-        attr_set = true;
     }
     const int n_tiles = N / BN, m_tiles = (M + BM - 1) / BM, nkb = K / BK;
     int splits = 1;

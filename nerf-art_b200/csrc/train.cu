@@ -1000,7 +1000,7 @@ unpack_grads_kernel(const NaRawParams raw, const NaRawGrads out, const GradPack 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// compositing backward, one thread per ray
+// compositing backward, one warp per ray
 // ---------------------------------------------------------------------------------------------------------------------
 struct CompBwdArgs {
     const float* d_all;      // [n][P]
@@ -1030,98 +1030,158 @@ __device__ __forceinline__ void block_accum(double* accum, double v0, double v1)
     if ((threadIdx.x & 31) == 0) { atomicAdd(accum, v0); atomicAdd(accum + 1, v1); }
 }
 
-// VolSDF ray integration (volsdf.py:540-564) differentiated; sigma from sdf_to_sigma (volsdf.py:34-53)
-__global__ void volsdf_composite_bwd_kernel(const CompBwdArgs a) {
-    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+// inclusive suffix sum over the warp (lane l gets sum of lanes >= l)
+__device__ __forceinline__ double warp_suffix_sum(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v += t; }
+    return v;
+}
+// inclusive prefix product over the warp
+__device__ __forceinline__ double warp_prefix_prod(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v *= t; }
+    return v;
+}
+
+// VolSDF ray integration (volsdf.py:540-564) differentiated; sigma from sdf_to_sigma (volsdf.py:34-53).  One WARP per ray: the
+// transmittance is an exclusive product scan over the samples, the "sum over later samples" of cumprod's backward an exclusive suffix
+// sum, both carried across 32-sample chunks in double (like torch's CPU cumprod, which the forward reproduces).
+__global__ void __launch_bounds__(256) volsdf_composite_bwd_kernel(const CompBwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int ray = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     double beta_bar = 0.0, loss = 0.0;
     if (ray < a.n) {
-        const int P = a.P;
+        const int P = a.P, M = P - 1;
         const float alpha = a.scal[0], beta = a.scal[1];
         const float* d = a.d_all + (size_t)ray * P; const float* s = a.sdf + (size_t)ray * P;
         float* gs = a.g_sdf + (size_t)ray * P;
         const float G0 = a.G[ray * 3], G1 = a.G[ray * 3 + 1], G2 = a.G[ray * 3 + 2];
         const float Gsum = a.white ? (G0 + G1 + G2) : 0.f;
-        double T = 1.0;
-        for (int i = 0; i < P - 1; ++i) {                       // T_i = prod_{j<i} p_j, parked in g_sdf
-            gs[i] = (float)T;
-            const float e = 0.5f * expf(-fabsf(s[i]) / beta);
-            const float sigma = alpha * (s[i] >= 0.f ? e : 1.f - e);
-            const float x = sigma * (d[i + 1] - d[i]);
-            T *= (double)expf(-fmaxf(x, 0.f));
+        double carry = 1.0;
+        for (int base = 0; base < M; base += 32) {               // T_i = prod_{j<i} p_j, parked in g_sdf
+            const int i = base + lane;
+            float p = 1.f;
+            if (i < M) {
+                const float e = 0.5f * expf(-fabsf(s[i]) / beta);
+                const float sigma = alpha * (s[i] >= 0.f ? e : 1.f - e);
+                p = expf(-fmaxf(sigma * (d[i + 1] - d[i]), 0.f));
+            }
+            const double incl = warp_prefix_prod((double)p, lane);
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0;
+            if (i < M) gs[i] = (float)(carry * excl);
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
         }
-        double S = 0.0;                                          // sum_{k>i} tau-bar_k tau_k
-        gs[P - 1] = 0.f;
-        for (int c = 0; c < 3; ++c) a.g_rad[((size_t)ray * P + P - 1) * 3 + c] = 0.f;
-        for (int i = P - 2; i >= 0; --i) {
-            const float Ti = gs[i];
-            const float si = s[i];
-            const float e = 0.5f * expf(-fabsf(si) / beta);
-            const float psi = si >= 0.f ? e : 1.f - e;
-            const float delta = d[i + 1] - d[i];
-            const float x = alpha * psi * delta;
-            const float p = expf(-fmaxf(x, 0.f));
-            const float tau = (1.f - p + 1e-10f) * Ti;
-            const size_t ci = ((size_t)ray * P + i) * 3;
-            const float tau_bar = a.rad[ci] * G0 + a.rad[ci + 1] * G1 + a.rad[ci + 2] * G2 - Gsum;
-            a.g_rad[ci] = tau * G0; a.g_rad[ci + 1] = tau * G1; a.g_rad[ci + 2] = tau * G2;
-            const float x_bar = x > 0.f ? (float)((double)tau_bar * Ti * p - S) : 0.f;
-            S += (double)tau_bar * tau;
-            const float sigma_bar = x_bar * delta;
-            gs[i] = si != 0.f ? sigma_bar * (-(alpha / beta) * e) : 0.f;
-            const float dpsi_dbeta = (si >= 0.f ? 1.f : -1.f) * e * fabsf(si) / (beta * beta);
-            beta_bar += (double)(sigma_bar * (psi * (-1.f / (beta * beta)) + alpha * dpsi_dbeta));
+        double S_hi = 0.0;                                       // sum_{k >= base + 32} tau-bar_k tau_k
+        for (int base = ((M - 1) >> 5) << 5; base >= 0; base -= 32) {
+            const int i = base + lane;
+            const bool live = i < M;
+            float Ti = 0.f, si = 0.f, e = 0.f, psi = 0.f, delta = 0.f, x = 0.f, p = 1.f, tau_bar = 0.f;
+            double v = 0.0;
+            size_t ci = 0;
+            if (live) {
+                Ti = gs[i]; si = s[i];
+                e = 0.5f * expf(-fabsf(si) / beta);
+                psi = si >= 0.f ? e : 1.f - e;
+                delta = d[i + 1] - d[i];
+                x = alpha * psi * delta;
+                p = expf(-fmaxf(x, 0.f));
+                const float tau = (1.f - p + 1e-10f) * Ti;
+                ci = ((size_t)ray * P + i) * 3;
+                tau_bar = a.rad[ci] * G0 + a.rad[ci + 1] * G1 + a.rad[ci + 2] * G2 - Gsum;
+                a.g_rad[ci] = tau * G0; a.g_rad[ci + 1] = tau * G1; a.g_rad[ci + 2] = tau * G2;
+                v = (double)tau_bar * tau;
+            }
+            const double suf = warp_suffix_sum(v, lane);
+            const double S = S_hi + (suf - v);                   // sum_{k>i} tau-bar_k tau_k
+            S_hi += __shfl_sync(0xffffffffu, suf, 0);
+            if (live) {
+                const float x_bar = x > 0.f ? (float)((double)tau_bar * Ti * p - S) : 0.f;
+                const float sigma_bar = x_bar * delta;
+                gs[i] = si != 0.f ? sigma_bar * (-(alpha / beta) * e) : 0.f;
+                const float dpsi_dbeta = (si >= 0.f ? 1.f : -1.f) * e * fabsf(si) / (beta * beta);
+                beta_bar += (double)(sigma_bar * (psi * (-1.f / (beta * beta)) + alpha * dpsi_dbeta));
+            }
         }
-        if (a.w_eik != 0.f) for (int i = 0; i < P; ++i) eik_point(a, (size_t)ray * P + i, loss);
+        if (lane == 0) {
+            gs[P - 1] = 0.f;
+            for (int c = 0; c < 3; ++c) a.g_rad[((size_t)ray * P + P - 1) * 3 + c] = 0.f;
+        }
+        if (a.w_eik != 0.f) for (int i = lane; i < P; i += 32) eik_point(a, (size_t)ray * P + i, loss);
         beta_bar *= (double)(a.speed * beta);                    // beta = exp(ln_beta * speed_factor), volsdf.py:337-339
     }
     block_accum(a.accum, beta_bar, loss);
 }
 
-// NeuS ray integration (neus.py:36-43,65-78,373-381) differentiated
-__global__ void neus_composite_bwd_kernel(const CompBwdArgs a) {
-    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+// NeuS ray integration (neus.py:36-43,65-78,373-381) differentiated, one warp per ray.  alpha_i = max((Phi_i - Phi_{i+1}) / (Phi_i +
+// 1e-10), 0) couples sample i to its neighbour: d L / d Phi_{i+1} = A_{i+1} - a-bar_i / (Phi_i + 1e-10), with
+// A_i = a-bar_i (Phi_{i+1} + 1e-10) / (Phi_i + 1e-10)^2 the contribution of alpha_i to its own leading cdf value.
+__global__ void __launch_bounds__(256) neus_composite_bwd_kernel(const CompBwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int ray = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     double s_bar = 0.0, loss = 0.0;
     if (ray < a.n) {
-        const int P = a.P;
+        const int P = a.P, M = P - 1;
         const float sc = a.scal[0];
         const float* sd = a.sdf + (size_t)ray * P;
         float* gs = a.g_sdf + (size_t)ray * P;
         const float G0 = a.G[ray * 3], G1 = a.G[ray * 3 + 1], G2 = a.G[ray * 3 + 2];
         const float Gsum = a.white ? (G0 + G1 + G2) : 0.f;
         auto Phi = [&](int i) { return __fdiv_rn(1.f, 1.f + expf(-sd[i] * sc)); };
-        double T = 1.0;
-        for (int i = 0; i < P - 1; ++i) {
-            gs[i] = (float)T;
-            const float c0 = Phi(i), c1 = Phi(i + 1);
-            const float al = fmaxf((c0 - c1) / (c0 + 1e-10f), 0.f);
-            T *= (double)(1.f - al + 1e-10f);
+        double carry = 1.0;
+        for (int base = 0; base < M; base += 32) {
+            const int i = base + lane;
+            float qf = 1.f;
+            if (i < M) {
+                const float c0 = Phi(i), c1 = Phi(i + 1);
+                qf = 1.f - fmaxf((c0 - c1) / (c0 + 1e-10f), 0.f) + 1e-10f;
+            }
+            const double incl = warp_prefix_prod((double)qf, lane);
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0;
+            if (i < M) gs[i] = (float)(carry * excl);
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
         }
-        double S = 0.0;
-        float carry = 0.f;                                       // contribution of alpha_{i+1} to Phi-bar_{i+1} (as its "previous" cdf)
-        for (int i = P - 2; i >= 0; --i) {
-            const float Ti = gs[i];
-            const float c0 = Phi(i), c1 = Phi(i + 1);
-            const float raw = (c0 - c1) / (c0 + 1e-10f);
-            const float al = fmaxf(raw, 0.f);
-            const float q = 1.f - al + 1e-10f;
-            const float w = al * Ti;
-            const size_t ci = ((size_t)ray * (P - 1) + i) * 3;
-            const float w_bar = a.rad[ci] * G0 + a.rad[ci + 1] * G1 + a.rad[ci + 2] * G2 - Gsum;
-            a.g_rad[ci] = w * G0; a.g_rad[ci + 1] = w * G1; a.g_rad[ci + 2] = w * G2;
-            const float a_bar = raw >= 0.f ? (float)((double)w_bar * Ti - S / (double)q) : 0.f;
-            S += (double)w_bar * w;
-            const float phi_bar_next = carry - a_bar / (c0 + 1e-10f);
-            const float pre = phi_bar_next * c1 * (1.f - c1);
-            gs[i + 1] = pre * sc;
-            s_bar += (double)(pre * sd[i + 1]);
-            carry = a_bar * (c1 + 1e-10f) / ((c0 + 1e-10f) * (c0 + 1e-10f));
-            if (i == 0) {
-                const float pre0 = carry * c0 * (1.f - c0);
-                gs[0] = pre0 * sc;
-                s_bar += (double)(pre0 * sd[0]);
+        double S_hi = 0.0;
+        float A_hi = 0.f;                                        // A of sample base + 32 (0 beyond the last sample)
+        for (int base = ((M - 1) >> 5) << 5; base >= 0; base -= 32) {
+            const int i = base + lane;
+            const bool live = i < M;
+            float Ti = 0.f, c0 = 1.f, c1 = 0.f, raw = 0.f, q = 1.f, w_bar = 0.f;
+            double v = 0.0;
+            if (live) {
+                Ti = gs[i];
+                c0 = Phi(i); c1 = Phi(i + 1);
+                raw = (c0 - c1) / (c0 + 1e-10f);
+                const float al = fmaxf(raw, 0.f);
+                q = 1.f - al + 1e-10f;
+                const float w = al * Ti;
+                const size_t ci = ((size_t)ray * (P - 1) + i) * 3;
+                w_bar = a.rad[ci] * G0 + a.rad[ci + 1] * G1 + a.rad[ci + 2] * G2 - Gsum;
+                a.g_rad[ci] = w * G0; a.g_rad[ci + 1] = w * G1; a.g_rad[ci + 2] = w * G2;
+                v = (double)w_bar * w;
+            }
+            const double suf = warp_suffix_sum(v, lane);
+            const double S = S_hi + (suf - v);
+            S_hi += __shfl_sync(0xffffffffu, suf, 0);
+            const float a_bar = (live && raw >= 0.f) ? (float)((double)w_bar * Ti - S / (double)q) : 0.f;
+            const float A = live ? a_bar * (c1 + 1e-10f) / ((c0 + 1e-10f) * (c0 + 1e-10f)) : 0.f;
+            float A_next = __shfl_down_sync(0xffffffffu, A, 1);
+            if (lane == 31) A_next = A_hi;
+            A_hi = __shfl_sync(0xffffffffu, A, 0);
+            __syncwarp();                                        // every lane has read its T_i before g_sdf[i + 1] is overwritten
+            if (live) {
+                const float pre = (A_next - a_bar / (c0 + 1e-10f)) * c1 * (1.f - c1);
+                gs[i + 1] = pre * sc;
+                s_bar += (double)(pre * sd[i + 1]);
+                if (i == 0) {
+                    const float pre0 = A * c0 * (1.f - c0);
+                    gs[0] = pre0 * sc;
+                    s_bar += (double)(pre0 * sd[0]);
+                }
             }
         }
-        if (a.w_eik != 0.f) for (int i = 0; i < P; ++i) eik_point(a, (size_t)ray * P + i, loss);
+        if (a.w_eik != 0.f) for (int i = lane; i < P; i += 32) eik_point(a, (size_t)ray * P + i, loss);
         s_bar *= (double)(a.speed * sc);                         // s = exp(ln_s * speed_factor), neus.py:116-117
     }
     block_accum(a.accum, s_bar, loss);
@@ -1375,8 +1435,8 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     a.d_all = d_all; a.sdf = sdf; a.rad = rad; a.nab = nab; a.G = grad_rgb; a.scal = scal;
     a.g_sdf = w.g_sdf; a.g_rad = w.g_rad; a.g_nab = w.g_nab; a.accum = accum; a.n = (int)n; a.P = P; a.white = cfg->white_bkgd;
     a.w_eik = cfg->w_eikonal; a.inv_count = cfg->eikonal_count > 0 ? 1.f / (float)cfg->eikonal_count : 0.f; a.speed = cfg->speed_factor;
-    if (neus) neus_composite_bwd_kernel<<<(int)((n + 127) / 128), 128, 0, stream>>>(a);
-    else      volsdf_composite_bwd_kernel<<<(int)((n + 127) / 128), 128, 0, stream>>>(a);
+    if (neus) neus_composite_bwd_kernel<<<(int)((n + 7) / 8), 256, 0, stream>>>(a);          // one warp per ray
+    else      volsdf_composite_bwd_kernel<<<(int)((n + 7) / 8), 256, 0, stream>>>(a);
     NA_CHECK_LAUNCH();
     const size_t M = (size_t)n * P, mpad = (M + TM - 1) / TM * TM;
     Stash st; st.mpad = mpad; st.wide = w.stash; st.narrow = w.stash + (size_t)N_WIDE * mpad * 256; st.tiny = st.narrow + 3 * mpad * NLD;      // fp32 mode only

@@ -229,7 +229,16 @@ wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                 tmem_ld16(tmem_d + ((unsigned)(32 * q) << 16) + (unsigned)(256 * h + 16 * c16), v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (16 * c16 + j < t.n_valid) atomicAdd(orow + 16 * c16 + j, __uint_as_float(v[j]));
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cc = 16 * c16 + 4 * j4;
+                    if (cc + 3 < t.n_valid)            // 16-byte vector atomic (rows are 16-byte aligned: ldo is a multiple of 4)
+                        atomicAdd(reinterpret_cast<float4*>(orow + cc), make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                                                                    __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])));
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (cc + j < t.n_valid) atomicAdd(orow + cc + j, __uint_as_float(v[4 * j4 + j]));
+                    }
+                }
             }
         }
     }
@@ -267,39 +276,64 @@ wgrad_tiny_kernel(const TinyArgs a) {
     float s8[8], r4[3][8], sb = 0.f, rb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s8[j] = 0.f; r4[0][j] = r4[1][j] = r4[2][j] = 0.f; }
-    for (long long m = m0 + warp; m < m1; m += 8) {
-        if (a.in7) {
-            const float g = a.t1[m * 4];
-            float f[8];
-            unpack8(__ldcs(reinterpret_cast<const uint4*>(a.in7 + m * 256) + lane), a.fwd_bf16 != 0, f);
+    constexpr int U = 4;                                   // rows per warp iteration: 12 independent 16-byte loads in flight per lane
+    for (long long mb = m0 + (long long)warp * U; mb < m1; mb += 8 * U) {
+        uint4 qi[U], qv[U], qy[U]; float g[U]; float4 d[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s8[j] = fmaf(g, f[j], s8[j]);
-            unpack8(__ldcs(reinterpret_cast<const uint4*>(a.vb7 + m * 256) + lane), true, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s8[j] += f[j];
-            sb += g;
+        for (int u = 0; u < U; ++u) {
+            const long long m = mb + u < m1 ? mb + u : m1 - 1;      // clamped rows are given zero weight below
+            const bool live = mb + u < m1;
+            if (a.in7) {
+                qi[u] = __ldcs(reinterpret_cast<const uint4*>(a.in7 + m * 256) + lane);
+                qv[u] = __ldcs(reinterpret_cast<const uint4*>(a.vb7 + m * 256) + lane);
+                g[u] = live ? a.t1[m * 4] : 0.f;
+            }
+            if (a.ys3) {
+                qy[u] = __ldcs(reinterpret_cast<const uint4*>(a.ys3 + m * 256) + lane);
+                d[u] = live ? *reinterpret_cast<const float4*>(a.t0 + m * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        if (a.ys3) {
-            const float4 d = *reinterpret_cast<const float4*>(a.t0 + m * 4);
-            float f[8];
-            unpack8(__ldcs(reinterpret_cast<const uint4*>(a.ys3 + m * 256) + lane), a.fwd_bf16 != 0, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { r4[0][j] = fmaf(d.x, f[j], r4[0][j]); r4[1][j] = fmaf(d.y, f[j], r4[1][j]); r4[2][j] = fmaf(d.z, f[j], r4[2][j]); }
-            rb[0] += d.x; rb[1] += d.y; rb[2] += d.z;
+        for (int u = 0; u < U; ++u) {
+            const float live = mb + u < m1 ? 1.f : 0.f;
+            float f[8];
+            if (a.in7) {
+                unpack8(qi[u], a.fwd_bf16 != 0, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s8[j] = fmaf(g[u], f[j], s8[j]);
+                unpack8(qv[u], true, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s8[j] = fmaf(live, f[j], s8[j]);
+                sb += g[u];
+            }
+            if (a.ys3) {
+                unpack8(qy[u], a.fwd_bf16 != 0, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { r4[0][j] = fmaf(d[u].x, f[j], r4[0][j]); r4[1][j] = fmaf(d[u].y, f[j], r4[1][j]); r4[2][j] = fmaf(d[u].z, f[j], r4[2][j]); }
+                rb[0] += d[u].x; rb[1] += d[u].y; rb[2] += d[u].z;
+            }
         }
     }
-    if (m0 >= m1) return;
-    if (a.in7) {
+    // block-level reduction over the 8 warps, then one vector atomic per 4 columns: 256 x 16-byte atomics per block instead of 8192 scalar ones
+    __shared__ float red[8][4][256];
+    __shared__ float redb[8][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(a.w8_sdf + 8 * lane + j, s8[j]);
-        if (lane == 0) atomicAdd(a.b8_sdf, sb);
-    }
-    if (a.ys3) {
+    for (int j = 0; j < 8; ++j) { red[warp][0][8 * lane + j] = s8[j]; red[warp][1][8 * lane + j] = r4[0][j]; red[warp][2][8 * lane + j] = r4[1][j]; red[warp][3][8 * lane + j] = r4[2][j]; }
+    if (lane == 0) { redb[warp][0] = sb; redb[warp][1] = rb[0]; redb[warp][2] = rb[1]; redb[warp][3] = rb[2]; }
+    __syncthreads();
+    {
+        const int row = threadIdx.x >> 6, c4 = (threadIdx.x & 63) * 4;          // 4 output rows x 64 column quads
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int w = 0; w < 8; ++w) { const float4 t = *reinterpret_cast<const float4*>(&red[w][row][c4]); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+        if (row == 0) { if (a.in7) atomicAdd(reinterpret_cast<float4*>(a.w8_sdf + c4), v); }
+        else if (a.ys3) atomicAdd(reinterpret_cast<float4*>(a.rad_w4 + (row - 1) * 256 + c4), v);
+        if (threadIdx.x < 4) {
+            float b = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(a.rad_w4 + c * 256 + 8 * lane + j, r4[c][j]);
-            if (lane == 0) atomicAdd(a.rad_b4 + c, rb[c]);
+            for (int w = 0; w < 8; ++w) b += redb[w][threadIdx.x];
+            if (threadIdx.x == 0) { if (a.in7) atomicAdd(a.b8_sdf, b); }
+            else if (a.ys3) atomicAdd(a.rad_b4 + threadIdx.x - 1, b);
         }
     }
 }
@@ -391,7 +425,7 @@ int launch_wgrad_tiny(const unsigned short* in7, const unsigned short* vb7, cons
     a.m_rows = m_rows; a.fwd_bf16 = fwd_bf16;
     const int blocks = 2 * num_sms();
     a.rows_per_block = (int)((m_rows + blocks - 1) / blocks);
-    a.rows_per_block = (a.rows_per_block + 7) / 8 * 8;
+    a.rows_per_block = (a.rows_per_block + 31) / 32 * 32;
     const int grid = (int)((m_rows + a.rows_per_block - 1) / a.rows_per_block);
     wf::wgrad_tiny_kernel<<<grid, 256, 0, stream>>>(a);
     NA_CHECK_LAUNCH();

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""INTEGRATION.md level 1, as a script: turn three modules of a NeRF-Art checkout into one-line forwards to nerfart_b200.
+"""INTEGRATION.md level 1, as a script: turn four modules of a NeRF-Art checkout into one-line forwards to nerfart_b200.
 
     python scripts/apply_level1.py /path/to/NeRF-Art
 
@@ -22,6 +22,9 @@ FORWARDS = {
         '# forwarded to nerfart_b200 (reference: get_rays 112-165, lin2img 238-248 are used by render.py / train.py;\n'
         '# rot_to_quat / load_K_Rt_from_P by dataio/)\n'
         'from nerfart_b200.utils.rend_util import *                       # noqa: F401,F403\n',
+    'utils/mesh_util.py':
+        '# forwarded to nerfart_b200 (reference: extract_mesh 82-112 is called by train.py:213-222 and tools/extract_surface.py)\n'
+        'from nerfart_b200.utils.mesh_util import *                       # noqa: F401,F403\n',
 }
 
 

@@ -64,3 +64,24 @@ def test_get_model_contract():
     assert kw_test['rayschunk'] == 1024 and kw_test['perturb'] is False and kw_train['perturb'] is True
     assert render_fn is trainer.renderer and hasattr(model, 'implicit_surface') and hasattr(model, 'radiance_net')
     assert args.model.outside_scene == 'builtin' and args.training.beta_init == 0.1   # defaults injected like the reference
+
+
+def test_mesh_grid_points_follow_the_reference_lattice_and_ply_writer_round_trips(tmp_path):
+    """utils/mesh_util.py:87-100 (float divisions included) on a small grid, bit-identical; binary PLY header / payload sizes."""
+    import numpy as np
+    import torch
+    from nerfart_b200.utils import mesh_util as mu
+    for N, s in ((7, 2.0), (16, 2.4)):
+        idx = np.arange(0, N ** 3, 1).astype(np.int64)
+        xyz = np.zeros([N ** 3, 3])
+        xyz[:, 2] = idx % N; xyz[:, 1] = (idx / N) % N; xyz[:, 0] = ((idx / N) / N) % N
+        o = -s / 2.
+        xyz[:, 0] = xyz[:, 0] * (s / (N - 1)) + o; xyz[:, 1] = xyz[:, 1] * (s / (N - 1)) + o; xyz[:, 2] = xyz[:, 2] * (s / (N - 1)) + o
+        assert torch.equal(torch.from_numpy(xyz).float(), mu.grid_points(0, N ** 3, N, s, 'cpu'))
+        assert torch.equal(torch.from_numpy(xyz[5:40]).float(), mu.grid_points(5, 40, N, s, 'cpu'))       # chunks are consistent
+    p = str(tmp_path / 't.ply')
+    mu.write_ply(p, np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float), np.array([[0, 1, 2], [0, 2, 3]]))
+    raw = open(p, 'rb').read()
+    head, body = raw.split(b'end_header\n')
+    assert b'element vertex 4' in head and b'element face 2' in head and b'property list uchar int vertex_indices' in head
+    assert len(body) == 4 * 12 + 2 * 13

@@ -183,3 +183,56 @@ def test_style_losses_match_restated_reference_formulas_and_cache_text(towers):
     for a, b in ((l1, r1), (l2, r2), (l3, r3)):
         assert abs(float(a) - float(b)) <= 2e-4 * max(1.0, abs(float(b)))
     assert rel(pred.grad, pred2.grad) < 1e-3
+
+
+def test_from_openai_state_dict_layout_and_build_loss_dict():
+    """`ClipVisionB32.from_openai` on a model in the UPSTREAM openai/CLIP module / state-dict layout (tests/stubs/clip: the public
+    ViT-B/32 definition in plain PyTorch, seeded weights with non-trivial LayerNorm affines and biases): key mapping, the
+    `visual.proj` orientation ([768, 512], x @ proj), in_proj packing and the conv1 patch order are all exercised -- features and the
+    image gradient must equal the upstream module's autograd.  Then `criteria.build_loss_dict` (what Trainer.__init__ calls,
+    volsdf.py:639-645) is built from the same `clip` module: one shared tower, cached text features, the four losses."""
+    import os
+    import sys
+    stubs = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'stubs')
+    sys.path.append(stubs)
+    try:
+        import clip
+        if not hasattr(clip, 'FakeCLIP'):
+            pytest.skip('a real `clip` package is installed; this test pins the layout against the synthetic one')
+        from nerfart_b200.criteria.clip_vit import ClipVisionB32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        model, _ = clip.load('ViT-B/32', device=DEV)
+        model = model.float().eval()
+        with torch.no_grad():
+            for n, p in model.visual.named_parameters():           # upstream init is tiny: scale the matrices so every block matters
+                if p.dim() >= 2 and 'positional' not in n:
+                    p.mul_(2.0)
+        tower = ClipVisionB32.from_openai(model, DEV, precision='fp32')
+        g = torch.Generator(device='cpu'); g.manual_seed(3)
+        x = torch.randn(3, 3, 224, 224, generator=g).to(DEV)
+        gf = torch.randn(3, 512, generator=g).to(DEV)
+        x1 = x.clone().requires_grad_(True)
+        ref = model.encode_image(x1)
+        (ref * gf).sum().backward()
+        x2 = x.clone().requires_grad_(True)
+        out = tower.encode_image(x2)
+        (out * gf).sum().backward()
+        e_f, e_g = rel(out, ref.detach()), rel(x2.grad, x1.grad)
+        print('from_openai: features', e_f, 'image gradient', e_g)
+        assert e_f < 2e-4 and e_g < 2e-4
+        # the factory Trainer uses, on the same module (VGG16 weights are not available offline: seeded stand-in, criteria/perceptual.py)
+        os.environ['NA_VGG16_WEIGHTS'] = 'random:0'
+        from nerfart_b200.criteria import build_loss_dict
+        ld = build_loss_dict([480, 270], DEV)
+        assert set(ld) == {'clip', 'contrastive', 'patchnce', 'perceptual'} and ld['perceptual'] is not None
+        img = torch.rand(1, 3, 480, 270, device=DEV)
+        pred = (img * 0.9 + 0.05).requires_grad_(True)
+        from criteria_templates import TEMPLATES                     # any template list: the cache is keyed by class string
+        for k in ('clip', 'contrastive', 'patchnce'):
+            ld[k].text.templates = TEMPLATES
+        loss = ld['clip'](img, 'photo', pred, 'painting') + ld['perceptual'](pred, img) + ld['contrastive'](img, 'sketch', pred, 'painting')
+        loss.backward()
+        assert torch.isfinite(loss) and torch.isfinite(pred.grad).all() and float(pred.grad.abs().max()) > 0
+    finally:
+        sys.path.remove(stubs)
+        os.environ.pop('NA_VGG16_WEIGHTS', None)

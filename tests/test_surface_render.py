@@ -98,3 +98,53 @@ def test_cuda_ray_casting_vs_reference(name, framework, rcfg, scfg):
         lim = (3e-3 if tc else 3e-4) * (1 if algo == 'root_finding' else 3)   # hit points move by the depth tolerance; colours / normals follow
         assert rep['rgb'] < lim and rep['normals'] < lim * 3 and rep['nablas'] < lim * 3
         assert (col[0][~ex['mask_surface'][0]] == 0).all()
+
+
+def test_extract_mesh_sdf_grid_matches_pointwise_evaluation():
+    """mesh_util.sdf_grid: the N^3 SDF samples of extract_mesh equal implicit_surface.forward at the reference's
+    lattice points, and the sphere-initialised network gives |x| - r on them."""
+    import numpy as np
+    from nerfart_b200.utils import mesh_util as mu
+    from helpers import make_volsdf
+    m = make_volsdf(0.1, 0.0, device='cuda:0')
+    N, s = 24, 2.0
+    grid = mu.sdf_grid(m.implicit_surface, s, N, chunk=5000)                 # several chunks, the last one short
+    pts = mu.grid_points(0, N ** 3, N, s, 'cuda:0')
+    with torch.no_grad():
+        direct = m.implicit_surface.forward(pts).cpu().numpy().reshape(N, N, N)
+    assert np.array_equal(grid, direct)
+    r = np.linalg.norm(pts.cpu().numpy(), axis=-1).reshape(N, N, N)
+    assert np.abs(grid - (r - 1.0)).max() < 0.05                              # geometric sphere init, radius_init = 1.0
+
+
+def test_frame_sink_writes_the_frames_of_the_synchronous_path(tmp_path):
+    """utils/frame_sink.py: frames rendered through render_views + FrameSink equal `(rgb * 255).astype(uint8)` of a
+    synchronous render of the same views (render.py:508-509,530-536), in order, as 8-bit RGB PNGs."""
+    import cv2
+    import numpy as np
+    from helpers import make_volsdf, fx
+    from nerfart_b200.utils.frame_sink import FrameSink, render_views
+    from nerfart_b200.utils import rend_util
+    from nerfart_b200.models.frameworks.volsdf import volume_render
+    import functools
+    dev = 'cuda:0'
+    m = make_volsdf(0.1, 0.5, device=dev)
+    H, W = 40, 24
+    cams = []
+    for k in range(4):
+        c2w, K = fx.tilted_camera(H, W)
+        c2w = c2w.clone(); c2w[0, 3] += 0.1 * k
+        cams.append(c2w)
+    kw = dict(batched=True, near=0.0, far=6.0, perturb=False, max_upsample_steps=6, N_samples=32, N_importance=16, require_nablas=True,
+              calc_normal=True, detailed_output=False)
+    render_fn = functools.partial(volume_render, model=m)
+    sink = FrameSink(str(tmp_path / 'rgb'), keep_frames=True)
+    assert render_views(render_fn, [c.numpy() for c in cams], K.to(dev), H, W, sink, **kw) == 4
+    sink.close()
+    for k, c2w in enumerate(cams):
+        with torch.no_grad():
+            ro, rd, _ = rend_util.get_rays(c2w[None].to(dev), K[None].to(dev), H, W)
+            rgb, _, _ = volume_render(ro, rd, m, **kw)
+        want = (rgb.data.cpu().reshape(H, W, 3).numpy() * 255.).astype(np.uint8)
+        got = cv2.imread(str(tmp_path / 'rgb' / ('%05d.png' % (k + 1))))[..., ::-1]
+        assert np.array_equal(got, want) and np.array_equal(sink.frames[k + 1], want)
