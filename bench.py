@@ -46,6 +46,10 @@ def traffic_capture():
     except Exception:
         return None
 
+DTYPES = {'fp32': 'f32',
+          'tc': 'f16x2-split operands (22-bit), f32 accumulate',
+          'tc2acc': 'f16x2-split operands (22-bit), f32 accumulate (two accumulators)',
+          'tc_mixed': 'SDF forward (sampler + final): f16x2-split operands (22-bit); feature head, reverse sweep, radiance net: f16 operands (11-bit); f32 accumulate'}
 RENDER_KW = dict(batched=True, near=0.0, far=6.0, obj_bounding_radius=3.0, perturb=False, white_bkgd=False,
                  max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, epsilon=0.1, max_bisection_steps=10,
                  require_nablas=True, calc_normal=True, detailed_output=False)
@@ -164,7 +168,7 @@ def run_reference(args, rank, world):
     value = n_sample * P * args.steps / t
     what = ("the unmodified reference's volume_render (PyTorch fp32, CPU, rayschunk 2048)" if kind == 'reference'
             else 'numpy+BLAS fp32 oracle port of the reference (no staged reference tree)')
-    line = {'impl': 'reference', 'metric': 'MLP samples/sec (VolSDF 480x270x128)', 'value': value, 'unit': 'samples/s',
+    line = {'impl': 'reference', 'metric': f'MLP samples/sec (VolSDF {H}x{W}x{N_SAMPLES})', 'value': value, 'unit': 'samples/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, extra={'sample': f'{n_sample} of {H*W} rays (strided), same 128+64 samples/ray'}),
@@ -234,7 +238,7 @@ def train_probe(dev, precision, n_patches=8):
 
 def workload_config(args, extra=None):
     c = {'workload': f'VolSDF fangzhou_nature-shaped synthetic render {H}x{W} ({H*W} rays), N_samples={N_SAMPLES}, N_importance={N_IMPORTANCE}, '
-                     'd_init=512, seed-0 sphere init beta=0.1, radiance gains x3, closed-form camera',
+                     f'd_init={4 * N_SAMPLES}, seed-0 sphere init beta=0.1, radiance gains x3, closed-form camera',
          'evals_per_ray': {'sdf_only': 4 * N_SAMPLES, 'full': P},
          'parallelism': f'ray-partition x{args.gpus}' + (' + NCCL all-gather of RGB tiles' if args.gpus > 1 else ''),
          'precision_mode': args.precision,
@@ -255,7 +259,14 @@ def main():
     ap.add_argument('--workload', default='render', choices=['render', 'train'],
                     help="'render' (default): BASELINE configs[1]; 'train': the fine-tune step, see bench_train.py")
     ap.add_argument('--style', default='clip', choices=['clip', 'mse'], help='--workload train: style loss (see bench_train.py)')
+    ap.add_argument('--config', type=int, default=2, choices=[2, 4],
+                    help='BASELINE.json configs[] entry: 2 = VolSDF 480x270, 128 samples (the metric, default); 4 = 960x540, 256 samples (8-GPU config)')
     args = ap.parse_args()
+    if args.config == 4:
+        global H, W, N_SAMPLES, P
+        H, W, N_SAMPLES = 960, 540, 256
+        P = N_SAMPLES + N_IMPORTANCE
+        RENDER_KW.update(N_samples=N_SAMPLES); REF_KW.update(N_samples=N_SAMPLES)
     if args.workload == 'train':
         import bench_train
         return bench_train.main(args)
@@ -416,9 +427,9 @@ def main():
         cpu['rgb_linf_vs_oracle'] = float(np.abs(img[torch.as_tensor(sel, device=dev)].cpu().numpy() - ref['rgb']).max())
     if rank == 0:
         samples = n_rays * P * args.steps
-        line = {'metric': 'MLP samples/sec (VolSDF 480x270x128)', 'value': samples / t_dev, 'unit': 'samples/s', 'n_gpus': world,
+        line = {'metric': f'MLP samples/sec (VolSDF {H}x{W}x{N_SAMPLES})', 'value': samples / t_dev, 'unit': 'samples/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True,
-                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'f16x2-split operands (22-bit), f32 accumulate',
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': DTYPES.get(args.precision, args.precision),
                 'data': 'synthetic', 'config': workload_config(args),
                 'all_evals_per_s': n_rays * (4 * N_SAMPLES + P) * args.steps / t_dev,
                 'e2e': {'value': samples / t_e2e, 'unit': 'samples/s', 'ms_per_step': 1e3 * t_e2e / args.steps,

@@ -79,6 +79,10 @@ __device__ __forceinline__ unsigned mbar_try_wait_(unsigned bar, unsigned parity
 }
 // bounded mbarrier wait; `tag` names the wait site in the diagnostics (role << 24 | ...)
 __device__ __forceinline__ void mbar_wait_guarded(unsigned bar, unsigned parity, const SpinCtx& sc, unsigned tag) {
+#ifdef NA_NO_SPIN_GUARD
+    while (!mbar_try_wait_(bar, parity)) {}
+    return;
+#endif
     if (mbar_try_wait_(bar, parity)) return;
     unsigned polls = 0; unsigned long long t0 = 0;
     while (!mbar_try_wait_(bar, parity)) {

@@ -770,7 +770,11 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 // next GEMM, and a second completion before this warp's wait flips the parity back -- the wait would then never
                 // return (mbarrier phase aliasing; this was the intermittent first-step stall, profiles/r3a_stall_root_cause.md).
                 for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);
+#ifdef NA_TM_ORDER0_ONLY
+                const int order = 0;
+#else
                 const int order = prods == 3 ? prog.corr_first : 0;
+#endif
                 const bool corr_first = order != 0;
                 const int n_a = order == 1 ? n_kb : n_kb - 1;          // K-blocks whose corrections / hi*hi go through phases A / B
                 if (corr_first) {
@@ -1031,7 +1035,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
             }
             for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
+#ifndef NA_NO_INPUT_BAR
             epi_bar_sync();                                   // EMBS / X / V / BWV of this tile: written above by other warps, read from GEMM 3 on
+#endif
 
             float sdf_part = 0.f, rgb_part[3] = {0.f, 0.f, 0.f};
             float small_in[36];

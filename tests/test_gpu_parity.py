@@ -122,9 +122,9 @@ def test_get_rays():
 
 # rgb Linf tolerance of the beta=0.1 (BASELINE config) fixtures per arithmetic mode (include/nerfart_b200.h NA_PRECISION_*):
 # fp32 CUDA cores / two TMEM accumulators / TMEM-resident kernel with the accumulate-truncation bias compensated (sdf error 2.9e-6,
-# profiles/r3b_tc_accumulation.md): 1e-4; mixed (TF32-level reverse sweep + radiance net): 4e-3 (< 1/255)
-RGB_TOL = {'fp32': 1e-4, 'tc2acc': 1e-4, 'tc': 1e-4, 'tc_mixed': 4e-3}
-VAL_SCALE = {'fp32': 1.0, 'tc2acc': 1.0, 'tc': 2.0, 'tc_mixed': 500.0}       # widening of compare_volsdf's value tolerances
+# profiles/r3b_tc_accumulation.md): 1e-4; mixed (TF32-level reverse sweep + radiance net; the default render mode): 1e-3, measured 2.5e-4
+RGB_TOL = {'fp32': 1e-4, 'tc2acc': 1e-4, 'tc': 1e-4, 'tc_mixed': 1e-3}
+VAL_SCALE = {'fp32': 1.0, 'tc2acc': 1.0, 'tc': 2.0, 'tc_mixed': 100.0}       # widening of compare_volsdf's value tolerances
 # share of reference-converged rays that must take the reference's sampler path (threshold decisions, beta <= 0.01 fixtures): the
 # same bar for every mode whose SDF forward pass is fp32-equivalent
 MIN_SAME = {'fp32': 0.985, 'tc2acc': 0.985, 'tc': 0.985, 'tc_mixed': 0.985}
