@@ -56,7 +56,8 @@ SpinCtx diag_next(int kernel, int grid);               // host: sequence number 
 
 #if defined(__CUDACC__) && (!defined(__CUDA_ARCH__) || __CUDA_ARCH__ >= 900)
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-static __device__ __noinline__ void spin_timeout(const SpinCtx sc, unsigned tag, unsigned parity, unsigned long long waited) {
+static __device__ __noinline__ void spin_timeout(const SpinCtx* scp, unsigned tag, unsigned parity, unsigned long long waited) {
+    const SpinCtx sc = *scp;
     if (sc.diag && (threadIdx.x & 31) == 0) {
         const unsigned i = atomicAdd_system(&sc.diag->n_rec, 1u);
         if (i < (unsigned)HANG_RECS) {
@@ -77,23 +78,32 @@ __device__ __forceinline__ unsigned mbar_try_wait_(unsigned bar, unsigned parity
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-// bounded mbarrier wait; `tag` names the wait site in the diagnostics (role << 24 | ...)
-__device__ __forceinline__ void mbar_wait_guarded(unsigned bar, unsigned parity, const SpinCtx& sc, unsigned tag) {
+// Bounded mbarrier wait; `tag` names the wait site in the diagnostics (role << 24 | ...).  The context is passed by pointer to the
+// kernel's __grid_constant__ parameter: a constant-bank address that costs no register on the hot path (carrying the context by
+// value through the 96-register epilogue cost 4.6 % of the SDF-only tile, profiles/r3c_render.md).  try_wait suspends the thread in
+// hardware for a system-defined time, so the loop body runs rarely; the wall clock is read every 8192nd failed attempt.
+__device__ __forceinline__ void mbar_wait_guarded(unsigned bar, unsigned parity, const SpinCtx* sc, unsigned tag) {
 #ifdef NA_NO_SPIN_GUARD
     while (!mbar_try_wait_(bar, parity)) {}
     return;
 #endif
+    // inline on purpose: an out-of-line wait loop makes every contended wait spill the caller's live registers around the call
+    // (measured: +6 % on the SDF-only tile); only the time-out itself is a call
     if (mbar_try_wait_(bar, parity)) return;
     unsigned polls = 0; unsigned long long t0 = 0;
     while (!mbar_try_wait_(bar, parity)) {
-        if ((++polls & 0x3ffu) == 0) {
+        if (++polls == 8192u) {
+            polls = 0;
             const unsigned long long t = global_ns();
             if (t0 == 0) t0 = t;
             else if (t - t0 > SPIN_LIMIT_NS) spin_timeout(sc, tag, parity, t - t0);
         }
     }
 }
-__device__ __forceinline__ void diag_count(const SpinCtx& sc, int which) {       // 0 started, 1 ready (TMEM allocated), 2 finished
+// plain wait for the throughput-critical, register-starved epilogue warps: any deadlock also blocks the CTA's producer and MMA warps,
+// whose waits are the bounded ones (the bounded loop in the 16 epilogue warps cost 3 % of the SDF-only tile)
+__device__ __forceinline__ void mbar_wait_plain(unsigned bar, unsigned parity) { while (!mbar_try_wait_(bar, parity)) {} }
+__device__ __forceinline__ void diag_count(const SpinCtx& sc, int which) {   // (once per CTA phase: the by-value read is fine here)       // 0 started, 1 ready (TMEM allocated), 2 finished
     if (sc.diag && threadIdx.x == 0) {
         HangSlot& s = sc.diag->slot[sc.seq % HANG_SLOTS];
         atomicAdd_system(which == 0 ? &s.started : (which == 1 ? &s.ready : &s.finished), 1u);

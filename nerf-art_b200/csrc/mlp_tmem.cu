@@ -212,7 +212,6 @@ struct EpiCtx {
     uint4* qp;                      // BW: per-CTA fp16 scratch planes
     int bw;
     unsigned d_phase; long long* t_wait; long long* trace;
-    SpinCtx sc;
 };
 
 // this warp's part of K-block kb of the next A operand is in TMEM (and its part of D columns [64kb, 64kb+64) is consumed)
@@ -222,13 +221,20 @@ __device__ __forceinline__ void signal_kb(unsigned kb_bar, int kb, int lane) {
     if (lane == 0) mbar_arrive(kb_bar + 8u * (unsigned)kb);
 }
 
+// two floats -> packed fp16x2 (low half = a), round to nearest, saturating to the largest finite fp16 (F2FP.SATFINITE: the clamp is
+// part of the conversion instruction)
+__device__ __forceinline__ unsigned pack_half2_sat(float a, float b) {
+    unsigned r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 // 16 fp32 values (already x ACT_SCALE) -> 8 packed hi words + 8 packed lo words, stored over the 16 columns at taddr
 // (need_lo == 0: the consumer GEMM uses the hi*hi product only, the lo words are neither computed nor stored)
 __device__ __forceinline__ void store_a16(unsigned taddr, const float (&o)[16], int need_lo) {
     unsigned hi[8];
     __half2 h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]); hi[i] = *reinterpret_cast<const unsigned*>(&h[i]); }
+    for (int i = 0; i < 8; ++i) { hi[i] = pack_half2_sat(o[2 * i], o[2 * i + 1]); h[i] = *reinterpret_cast<const __half2*>(&hi[i]); }
     tmem_st8(taddr, hi);
     if (need_lo) {
         unsigned lo[8];
@@ -345,10 +351,8 @@ __device__ __forceinline__ void qstore16(uint4* base, int plane, int col0, int r
         unsigned w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            // x 2^-8: the parked terms reach 1e4 (100 g-bar g); the clamp keeps an outlier finite instead of turning the patch into NaN
-            const __half2 h = __floats2half2_rn(fminf(fmaxf(v[8 * j8 + 2 * i] * 0.00390625f, -65000.f), 65000.f),
-                                                fminf(fmaxf(v[8 * j8 + 2 * i + 1] * 0.00390625f, -65000.f), 65000.f));
-            w[i] = *reinterpret_cast<const unsigned*>(&h);
+            // x 2^-8: the parked terms reach 1e4 (100 g-bar g); the saturating conversion keeps an outlier finite instead of turning the patch into NaN
+            w[i] = pack_half2_sat(v[8 * j8 + 2 * i] * 0.00390625f, v[8 * j8 + 2 * i + 1] * 0.00390625f);
         }
         p[(size_t)j8 * TM] = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -427,11 +431,11 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         {                                                            // pass c16 reads N-quarter c16 of D
             const long long t0 = clock64();
-            mbar_wait_guarded(c.d_bar + 8u * (unsigned)c16, c.d_phase, c.sc, 0x45000000u | ((unsigned)c.g << 8) | (unsigned)c16);
+            mbar_wait_plain(c.d_bar + 8u * (unsigned)c16, c.d_phase);
             if (N_PASS < 4) {
                 // a GEMM whose epilogue reads fewer than four N-quarters (the 64-wide reverse GEMM 0: its four d_ready commits are
                 // issued together): consume the other phases here, before anything is signalled to the MMA warp
-                for (int k = N_PASS; k < 4; ++k) mbar_wait_guarded(c.d_bar + 8u * (unsigned)k, c.d_phase, c.sc, 0x45800000u | ((unsigned)c.g << 8) | (unsigned)k);
+                for (int k = N_PASS; k < 4; ++k) mbar_wait_plain(c.d_bar + 8u * (unsigned)k, c.d_phase);
             }
             *c.t_wait += clock64() - t0;
             tc_fence_after();
@@ -620,9 +624,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
             }
-            // single-product fp16 operands: keep an outlier finite (|x rs| > 4e3 would round to inf)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = fminf(fmaxf(o[j], -65000.f), 65000.f);
+            // (single-product fp16 operands: an outlier |x rs| > 4e3 saturates in store_a16's conversion instead of rounding to inf)
         } else {
             // radiance hidden layers: relu(16 z)
 #pragma unroll
@@ -687,7 +689,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 template <bool FULL, bool ST, bool BW>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
-                const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch, const SpinCtx sc) {
+                const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch, const __grid_constant__ SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -697,6 +699,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
     const long long total = explicit_pts ? job.m
                           : (long long)(job.n_rows_dev ? min(*job.n_rows_dev, job.n_rows) : job.n_rows) * job.P;
     const long long n_tiles = (total + TM - 1) / TM;
+    // nothing for this CTA (an upsampling iteration whose device-side work list is empty launches the full grid: at beta = 0.1 twelve
+    // of the fourteen sampler rounds of a chunk): leave before the barrier / TMEM / table set-up
+    if ((long long)blockIdx.x >= n_tiles) { diag_count(sc, 0); diag_count(sc, 1); diag_count(sc, 2); return; }
 
     if (tid == 0) {
         for (int s = 0; s < (int)NSK; ++s) { mbar_init(smem_u32(&S.full_bar[s]), 1); mbar_init(smem_u32(&S.empty_bar[s]), 1); }
@@ -735,7 +740,11 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     const unsigned sb = prog.g[g].stage_bytes;
                     const int n_kb = prog.g[g].n_kb, n_sp = prog.g[g].prods == 3 ? 2 : 1;
                     // stage sequence: [hi(kb) | lo(kb)] per K-block; with corr_first the hi stages of a three-product GEMM follow once more
+#ifndef NA_TM_ORDERS
+                    const int order = 0;
+#else
                     const int order = n_sp == 2 ? prog.corr_first : 0;
+#endif
                     const int n_seq = order == 0 ? n_kb * n_sp : (order == 1 ? 3 * n_kb : 3 * n_kb - 1);
                     for (int q = 0; q < n_seq; ++q, ++it) {
                         // stage index in the image: 2 kb + {0 hi, 1 lo}
@@ -744,7 +753,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         else if (order == 1) st = q < 2 * n_kb ? q : 2 * (q - 2 * n_kb);
                         else { const int na = 2 * (n_kb - 1); st = q < na ? q : (q < na + n_kb - 1 ? 2 * (q - na) : 2 * (n_kb - 1) + (q - na - (n_kb - 1))); }
                         const unsigned slot = it % NSK, ph = (it / NSK) & 1;
-                        mbar_wait_guarded(smem_u32(&S.empty_bar[slot]), ph ^ 1, sc, 0x50000000u | ((unsigned)g << 8) | slot);
+                        mbar_wait_guarded(smem_u32(&S.empty_bar[slot]), ph ^ 1, &sc, 0x50000000u | ((unsigned)g << 8) | slot);
                         mbar_expect_tx(smem_u32(&S.full_bar[slot]), sb);
                         bulk_g2s(smem_u32(S.Wst + slot * STAGE_BYTES), src + (size_t)st * sb, sb, smem_u32(&S.full_bar[slot]));
                     }
@@ -769,9 +778,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 // BEFORE this GEMM's MMAs are issued: once D is committed the epilogue starts signalling the same barriers for the
                 // next GEMM, and a second completion before this warp's wait flips the parity back -- the wait would then never
                 // return (mbarrier phase aliasing; this was the intermittent first-step stall, profiles/r3a_stall_root_cause.md).
-                for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);
-#ifdef NA_TM_ORDER0_ONLY
-                const int order = 0;
+                for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);
+#ifndef NA_TM_ORDERS
+                const int order = 0;          // orders 1 / 2 are a build option (-DNA_TM_ORDERS): their code costs 2.4 % of the SDF-only tile even unused
 #else
                 const int order = prods == 3 ? prog.corr_first : 0;
 #endif
@@ -783,10 +792,10 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1, slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
                         const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                         { const long long t0 = clock64();
-                          mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
-                          mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
+                          mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
+                          mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, &sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
                           t_full += clock64() - t0; }
-                        { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                        { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
                         tc_fence_after();
                         NA_TRACE_M(tr, g, kb, 0);
                         if (elect_one()) {
@@ -807,7 +816,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1;
                         const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                         { const long long t0 = clock64();
-                          mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d050000u | ((unsigned)g << 8) | (unsigned)kb);
+                          mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d050000u | ((unsigned)g << 8) | (unsigned)kb);
                           t_full += clock64() - t0; }
                         tc_fence_after();
                         if (elect_one()) {
@@ -839,10 +848,10 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1, slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
                     const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                     { const long long t0 = clock64();
-                      mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
-                      mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
+                      mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
+                      mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, &sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
                       t_full += clock64() - t0; }
-                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
                     tc_fence_after();
                     NA_TRACE_M(tr, g, kb, 0);
                     if (elect_one()) {
@@ -879,10 +888,10 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     // the weights first (the ring runs K-blocks ahead, so these return at once), then the A operand: the MMAs go out
                     // right behind the epilogue's signal
                     { const long long t0 = clock64();
-                      mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
-                      if (prods == 3) mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
+                      mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
+                      if (prods == 3) mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, &sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
                       t_full += clock64() - t0; }
-                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
                     tc_fence_after();
                     NA_TRACE_M(tr, g, kb, 0);
                     if (elect_one()) {
@@ -948,7 +957,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
         c.sdim = small_dim(job.multires_view);
         c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4); c.radw_s = smem_u32(S.RADW);
         c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
-        c.d_phase = 0; c.sc = sc;
+        c.d_phase = 0;
         long long t_d = 0, t_e0 = clock64();
         c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
         c.st_m = 0; c.st_map = &job.st_store_map; c.st_cnt = 0; c.st_row0 = 0;
@@ -1412,7 +1421,11 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     // calibrations of profiles/r3b_tc_accumulation.md for each order; 0 switches the compensation off
     static const char* order_env = getenv("NA_TM_ORDER");
     static const char* debias_env = getenv("NA_TM_DEBIAS");
+#ifdef NA_TM_ORDERS
     prog.corr_first = order_env ? (order_env[0] == '0' ? 0 : (order_env[0] == '1' ? 1 : 2)) : 0;
+#else
+    (void)order_env; prog.corr_first = 0;
+#endif
     static const float debias_default[3] = {14.f, 4.f, 8.f};      // (1 + x 2^-24 is representable in steps of 2)
     const float debias_x = debias_env ? (float)atof(debias_env) : debias_default[prog.corr_first];
     const int last = !job.want_full ? (job.feat ? 8 : 7) : (job.rad ? 20 : 16);

@@ -104,7 +104,7 @@ struct __align__(1024) Smem {
 
 __global__ void __launch_bounds__(THREADS, 1)
 tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg, float* __restrict__ C, int M, int N, int K,
-             const float* __restrict__ bias, float* __restrict__ C_raw, int act, const float* __restrict__ R, int kb_per_split, const SpinCtx sc) {
+             const float* __restrict__ bias, float* __restrict__ C_raw, int act, const float* __restrict__ R, int kb_per_split, const __grid_constant__ SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,7 +132,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
             const unsigned char* src = Bimg + ((size_t)n_tile * nkb_total + kb0) * B_BYTES;
             for (int i = 0; i < nkb; ++i) {
                 const unsigned slot = i % NST, ph = (i / NST) & 1;
-                mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, sc, 0x50000000u | (unsigned)i);
+                mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, &sc, 0x50000000u | (unsigned)i);
                 mbar_expect_tx(smem_u32(&S.full[slot]), B_BYTES);
                 bulk_g2s(smem_u32(S.B[slot]), src + (size_t)i * B_BYTES, B_BYTES, smem_u32(&S.full[slot]));
             }
@@ -141,7 +141,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
         // ---- MMA issuer
         for (int i = 0; i < nkb; ++i) {
             const unsigned slot = i % NST, ph = (i / NST) & 1;
-            mbar_wait_guarded(smem_u32(&S.full[slot]), ph, sc, 0x4d000000u | (unsigned)i);
+            mbar_wait_guarded(smem_u32(&S.full[slot]), ph, &sc, 0x4d000000u | (unsigned)i);
             tc_fence_after();
             if (elect_one()) {
                 const unsigned long long ad = umma_desc(smem_u32(S.A[slot])), bd = umma_desc(smem_u32(S.B[slot]));
@@ -163,7 +163,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
         for (int i = 0; i < nkb + AHEAD; ++i) {
             if (i < nkb) {
                 const unsigned slot = i % NST, ph = (i / NST) & 1;
-                mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, sc, 0x4c000000u | (unsigned)i);
+                mbar_wait_plain(smem_u32(&S.empty[slot]), ph ^ 1);
                 const unsigned dst = smem_u32(S.A[slot]) + dst_row;
                 if (live) {
 #pragma unroll
@@ -180,7 +180,7 @@ tgemm_kernel(const float* __restrict__ A, const unsigned char* __restrict__ Bimg
                 mbar_arrive(smem_u32(&S.full[(i - AHEAD) % NST]));
             }
         }
-        mbar_wait_guarded(smem_u32(&S.acc_ready), 0, sc, 0x45000000u);
+        mbar_wait_plain(smem_u32(&S.acc_ready), 0);
         tc_fence_after();
         const unsigned t_lane = tmem_d + ((unsigned)(32 * q) << 16);
         const bool split = gridDim.z > 1, lead = blockIdx.z == 0;

@@ -107,7 +107,7 @@ constexpr int MAX_TASKS = 16;
 struct Table { Task t[MAX_TASKS]; int n; long long mpad; long long n_blk; };      // n_blk: KS-sample blocks that hold samples
 
 __global__ void __launch_bounds__(THREADS, 1)
-wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_n, const Table tab, const SpinCtx sc) {
+wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_n, const Table tab, const __grid_constant__ SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,7 +143,7 @@ wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                 for (int i = 0; i < n_stage; ++i) {
                     const int pr = i / nblk, b = i - pr * nblk;
                     const unsigned slot = i % NST, ph = (i / NST) & 1;
-                    mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, sc, 0x50000000u | (unsigned)(i & 0xffffff));
+                    mbar_wait_guarded(smem_u32(&S.empty[slot]), ph ^ 1, &sc, 0x50000000u | (unsigned)(i & 0xffffff));
                     const unsigned bar = smem_u32(&S.full[slot]), base = smem_u32(S.st[slot]);
                     mbar_expect_tx(bar, L_BYTES + r_bytes);
                     const long long m0 = (blk0 + b) * KS;
@@ -162,7 +162,7 @@ wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
             for (int i = 0; i < n_stage; ++i) {
                 const int pr = i / nblk;
                 const unsigned slot = i % NST, ph = (i / NST) & 1;
-                mbar_wait_guarded(smem_u32(&S.full[slot]), ph, sc, 0x4d000000u | (unsigned)(i & 0xffffff));
+                mbar_wait_guarded(smem_u32(&S.full[slot]), ph, &sc, 0x4d000000u | (unsigned)(i & 0xffffff));
                 tc_fence_after();
                 if (elect_one()) {
                     const unsigned base = smem_u32(S.st[slot]);
@@ -191,7 +191,7 @@ wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                 const unsigned slot = i % NST, ph = (i / NST) & 1;
                 // (every warp waits for the stage even when it has nothing to sum: its arrival on `empty` must not run ahead of the
                 //  stage, or it would be counted into the previous use of the slot)
-                mbar_wait_guarded(smem_u32(&S.full[slot]), ph, sc, 0x42000000u | (unsigned)(i & 0xffffff));
+                mbar_wait_plain(smem_u32(&S.full[slot]), ph);
                 if (t.bias_out && i < nblk) {
                     const unsigned base = smem_u32(S.st[slot]) + (unsigned)(lane >> 3) * ATOM_BYTES;
 #pragma unroll
@@ -218,7 +218,7 @@ wgrad_f16_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                 for (int j = 0; j < 8; ++j) atomicAdd(t.bias_out + 8 * lane + j, bs[j]);
             }
             // ---- epilogue: warp w reads TMEM lanes 32 * (w % 4) .. of accumulator (w - 2) / 4
-            mbar_wait_guarded(smem_u32(&S.acc_ready), 0, sc, 0x45000000u);
+            mbar_wait_plain(smem_u32(&S.acc_ready), 0);
             tc_fence_after();
             const int q = warp & 3, h = (warp - 2) >> 2;
             const int l = 128 * h + 32 * q + lane;

@@ -100,6 +100,7 @@ def test_cuda_ray_casting_vs_reference(name, framework, rcfg, scfg):
         assert (col[0][~ex['mask_surface'][0]] == 0).all()
 
 
+@pytest.mark.gpu
 def test_extract_mesh_sdf_grid_matches_pointwise_evaluation():
     """mesh_util.sdf_grid: the N^3 SDF samples of extract_mesh equal implicit_surface.forward at the reference's
     lattice points, and the sphere-initialised network gives |x| - r on them."""
@@ -117,6 +118,7 @@ def test_extract_mesh_sdf_grid_matches_pointwise_evaluation():
     assert np.abs(grid - (r - 1.0)).max() < 0.05                              # geometric sphere init, radius_init = 1.0
 
 
+@pytest.mark.gpu
 def test_frame_sink_writes_the_frames_of_the_synchronous_path(tmp_path):
     """utils/frame_sink.py: frames rendered through render_views + FrameSink equal `(rgb * 255).astype(uint8)` of a
     synchronous render of the same views (render.py:508-509,530-536), in order, as 8-bit RGB PNGs."""
