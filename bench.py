@@ -302,6 +302,9 @@ def main():
     n_rays = H * W
     from nerfart_b200 import parallel
     lo, hi, per = parallel.ray_block(n_rays, rank, world)
+    emu = int(os.environ.get('NA_BENCH_EMULATE_WORLD', '0'))     # diagnostics: time rank 0's share of an `emu`-GPU job on ONE GPU (what of a
+    if emu > 1 and world == 1:                                   # frame does not shrink with N, apart from chip-to-chip clock spread)
+        lo, hi, per = parallel.ray_block(n_rays, 0, emu)
     rgb_host = torch.empty(n_rays, 3, dtype=torch.float32).pin_memory()
 
     def step(e2e):

@@ -189,8 +189,19 @@ class PatchNCELoss(_ClipLossBase):
         source_feature_list = [self.get_text_features(s, norm=True) for s in source_classes]
         target_feature = self.get_text_features(target_class, norm=True)
         enc = self.get_image_features(batch)                                 # [12*B, 512]
+        return self.crop_losses(enc, source_feature_list, target_feature, B)
+
+    def crop_losses(self, enc, source_feature_list, target_feature, B):
+        """sum over the crops of mean(-log(pos / (pos + sum_s exp(cos(e, T_s) / tau))))  (patchnce_loss.py:146-160 per crop)"""
+        if B == 1:
+            # the same arithmetic for all crops, classes and templates at once (the reference's loop is 12 x 9 cosine / exp / add
+            # launches forward and twice that backward; the step is host-bound there): cos [12, 8, T], near [12, T]
+            sf = torch.stack([f.detach() for f in source_feature_list])      # [8, T, 512]
+            neg = torch.exp(F.cosine_similarity(enc[:, None, None, :], sf[None], dim=-1) / self.temperature).sum(1)
+            pos = torch.exp(F.cosine_similarity(enc[:, None, :], target_feature.detach()[None], dim=-1) / self.temperature)
+            return torch.mean(-torch.log(pos / (pos + neg)), dim=-1).sum()
         total = 0
-        for c in range(len(crops)):
+        for c in range(enc.shape[0] // B):
             e = enc[c * B:(c + 1) * B]
             near = self.cos(e, target_feature.detach())
             neg = 0

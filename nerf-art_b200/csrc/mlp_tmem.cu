@@ -48,11 +48,11 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 //   26..33 second-order sweep g-bar_i = v-bar_i W_i^T (images 0..7) | 34..40 trunk h-bar_{i-1} = z-bar_i W_i, i = 7..1 (images 9..15)
 
 // NA_TM_TRACE (diagnostic build): CTA 0 records clock64() stamps of its second tile into job.dbg[16..]:
-//   MMA lane:      slot (g*4+kb)*2 + {0: K-block of A ready, 1: its MMAs issued}
-//   epilogue lane: slot 192 + (g*4+pass)*3 + {0: D quarter ready, 1: tcgen05.ld done, 2: A stored}
+//   MMA lane:      slot (g*4+kb)*2 + {0: K-block of A ready, 1: its MMAs issued}                      (44 GEMMs: 352 slots)
+//   epilogue lane: slot 352 + (g*4+pass)*3 + {0: D quarter ready, 1: tcgen05.ld done, 2: A stored}    (528 slots; buffer >= 16 + 880 int64)
 #ifdef NA_TM_TRACE
 #define NA_TRACE_M(tr, g, kb, w) do { if (tr) (tr)[((g) * 4 + (kb)) * 2 + (w)] = clock64(); } while (0)
-#define NA_TRACE_E(tr, g, ps, w) do { if (tr) (tr)[192 + ((g) * 4 + (ps)) * 3 + (w)] = clock64(); } while (0)
+#define NA_TRACE_E(tr, g, ps, w) do { if (tr) (tr)[352 + ((g) * 4 + (ps)) * 3 + (w)] = clock64(); } while (0)
 #else
 #define NA_TRACE_M(tr, g, kb, w) do { } while (0)
 #define NA_TRACE_E(tr, g, ps, w) do { } while (0)
@@ -211,6 +211,8 @@ struct EpiCtx {
     unsigned long long* mk;         // BW: this thread's ReLU-mask slots: mk[l * EPI_THREADS], l = radiance hidden layer (64 columns each)
     uint4* qp;                      // BW: per-CTA fp16 scratch planes
     int bw;
+    unsigned nx;                    // FULL: scratch planes the NEXT GEMM's epilogue reads, for the prefetch: softplus' plane | parked-term plane << 8 |
+                                    // g plane << 16 | (feature rows) << 24; 0xff = none
     unsigned d_phase; long long* t_wait; long long* trace;
 };
 
@@ -375,6 +377,34 @@ __device__ __forceinline__ void bf16x16_to_float(const uint4 (&q)[2], float (&v)
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// The per-CTA scratch (1.2 MB x 148 CTAs in the training program) and the g planes of the stash do not stay in L2 between their
+// producer and their consumers: 78 % of the epilogue's scratch sectors came from DRAM and their latency was 37 % of all stall samples
+// (profiles/r3d_bw_program.md).  A pass therefore requests, one whole GEMM ahead (~10 us), the sectors the same pass of the NEXT GEMM
+// will load: softplus' codes (uint2 per row and column quad: 4-row sectors, lane l takes quad l & 3), parked fp16 terms (uint4 per
+// row and 8 columns: 2-row sectors, lane l takes half l & 1), the thread's own 32-byte piece of the g plane.  No register is held:
+// prefetch.global.L2 has no destination.
+template <bool ST>
+__device__ __forceinline__ void prefetch_next_gemm(const EpiCtx& c, int col0) {
+    const unsigned dh_plane = c.nx & 0xffu, q_plane = (c.nx >> 8) & 0xffu, g_plane = (c.nx >> 16) & 0xffu;
+    if (dh_plane != 0xffu) prefetch_l2(c.dh + (size_t)(dh_plane * 64 + (col0 >> 2) + (c.lane & 3)) * TM + c.r);
+    if (ST && q_plane != 0xffu) prefetch_l2(c.qp + (size_t)(q_plane * 32 + (col0 >> 3) + (c.lane & 1)) * TM + c.r);
+    if (ST && g_plane != 0xffu && c.st_row) prefetch_l2(c.st_row + (size_t)(ST_G + g_plane) * c.st_plane + col0);
+    if (c.nx >> 24) {
+        // geometry feature rows read by the tail of GEMM 16 (float4 per row and column quad: 2-row sectors)
+        const float4* f = c.featp + (size_t)((col0 >> 2) + (c.lane & 3)) * TM;
+        prefetch_l2(f + c.r); prefetch_l2(f + (c.r ^ 2));
+    }
+}
+// planes word of GEMM (op, lyr, program index g); see EpiCtx::nx
+__device__ __forceinline__ unsigned scratch_planes_of(int op, int lyr, int g, int has_rad) {
+    unsigned dh = 0xffu, q = 0xffu, gp = 0xffu, ft = 0u;
+    if (op == OP_FWD) { if (g >= 8 && g <= 15) dh = (unsigned)(15 - g); if (g == 16 && has_rad) ft = 1u; }
+    else if (op == OP_SO) { dh = (unsigned)lyr; gp = (unsigned)lyr; if (lyr == 7 && has_rad) q = 7u; }
+    else if (op == OP_TR) { dh = (unsigned)lyr; q = (unsigned)lyr; }
+    return dh | (q << 8) | (gp << 16) | (ft << 24);
+}
+
 // one GEMM's epilogue for this thread's row and its 64 columns (4 passes of 16)
 template <int KIND, bool FULL, bool ST>
 __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, float& sdf_part, float (&rgb_part)[3], const float (&small_in)[36]) {
@@ -399,6 +429,10 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         // thread = (row, column quarter cq): in pass c16 it owns columns 64*c16 + 16*cq .. +16, i.e. every pass completes one
         // 64-wide K-block of the next layer's A operand across the 16 epilogue warps
         const int col0 = c16 * 64 + c.cq * 16;
+#ifndef NA_TM_NO_PREFETCH
+        // (training program only: in the render kernel, whose 0.7 MB scratch per CTA mostly stays in L2, the extra requests cost 3 %)
+        if (FULL && ST) prefetch_next_gemm<ST>(c, col0);
+#endif
         uint2 q[4];
         if (USES_DH) {
 #pragma unroll
@@ -1074,6 +1108,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 c.lyr = prog.g[g].lyr;
                 c.signal = g + 1 < prog.n_gemm;
                 c.need_lo = c.signal ? (prog.g[g + 1].prods == 3) : 0;
+                c.nx = (FULL && ST && c.signal) ? scratch_planes_of(BW ? (int)prog.g[g + 1].op : (int)OP_FWD, (int)prog.g[g + 1].lyr, g + 1, c.has_rad) : 0x00ffffffu;
                 if (BW && (op == OP_HB || (op == OP_FWD && g == 20))) c.signal = 0;     // the next A operand is written by the tail below
                 const unsigned t_dd = c.t_lane + (unsigned)((g + 1) & 1) * 256u;       // D of this GEMM == A of the next
                 // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance

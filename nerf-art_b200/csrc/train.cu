@@ -1290,7 +1290,12 @@ static int tc_backward(const BwdJob& job, const void* packed, int precision, con
     e.st_t0 = w.tiny; e.st_t1 = w.tiny + mpad * 4;
     e.bw = 1; e.bw_bg_mask = job.apply_bg;
     e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
-    const int fwd_precision = (precision == NA_PRECISION_TC_MIXED || precision == NA_PRECISION_TC2ACC) ? NA_PRECISION_TC : precision;   // softplus' needs the 3-product forward
+    // the forward re-evaluation runs in the render's own mode: in tc_mixed the SDF forward pass (what softplus' and the activations come
+    // from) keeps its three-product operands, the feature head / reverse sweep / radiance layers use single products exactly as in the
+    // patch's forward render (NA_BW_FWD=tc: three products everywhere, the round-2 behaviour)
+    static const char* bw_fwd_env = getenv("NA_BW_FWD");
+    const bool force_tc = bw_fwd_env && bw_fwd_env[0] == 't' && bw_fwd_env[1] == 'c' && bw_fwd_env[2] == 0;
+    const int fwd_precision = precision == NA_PRECISION_TC2ACC ? NA_PRECISION_TC : ((precision == NA_PRECISION_TC_MIXED && force_tc) ? NA_PRECISION_TC : precision);
     NA_TRY(launch_mlp(e, packed, fwd_precision, w.fwd_scratch, w.fwd_scratch_bytes, stream));
 
     const GradPack G = grad_layout();

@@ -94,6 +94,28 @@ def _assign_grads(model, engine, scalar_param, train_surface, train_radiance):
     return scal
 
 
+def patch_groups(starts, n, batch_size, group=None):
+    """Patches of one rank -> launch groups.  The reference back-propagates patch by patch (volsdf.py:754-783); the parameter gradient is
+    the SUM over patches and every per-sample term (the eikonal mean's 1/N included, N = rays of ONE patch x samples) is independent of
+    the other patches, so full-size patches can share a launch: 1200 rays x 192 samples are 1800 tiles = 12.2 waves of 148 CTAs (13 run:
+    7 % idle), six patches are 72.97 waves.  NA_PATCH_GROUP (default 6; 1 = the reference's launch structure) bounds the group; groups are
+    sized evenly; a short last patch (its eikonal normaliser differs) stays alone."""
+    import os
+    group = int(os.environ.get('NA_PATCH_GROUP', '6')) if group is None else group
+    full = [i for i in starts if i + batch_size <= n]
+    part = [i for i in starts if i + batch_size > n]
+    out = []
+    if full:
+        n_groups = -(-len(full) // max(group, 1))
+        base, extra = divmod(len(full), n_groups)
+        k = 0
+        for gi in range(n_groups):
+            sz = base + (1 if gi < extra else 0)
+            out.append(full[k:k + sz]); k += sz
+    out += [[i] for i in part]
+    return out
+
+
 def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *, w_eikonal, white_bkgd, batch_size=None):
     """Pass 2.  rays [1,N,3], gradient [1,N,3]; `render_patch(ro, rd)` = the flat detailed forward outputs of one patch
     (NetEngine.volsdf_render / neus_render).  Returns the mean eikonal loss over patches (what the reference prints)."""
@@ -111,16 +133,24 @@ def backward_patches(model, framework, rays_o, rays_d, gradient, render_patch, *
     # (replaces DDP's bucketed all-reduce, train.py:155)
     world, rank = parallel.world_rank()
     # (NetEngine.pack() re-folds the weights only when a parameter changed: once per step, not once per patch)
-    for pi, i in enumerate(range(0, n, batch_size)):
-        if pi % world != rank:
-            continue
-        rop, rdp = ro[i:i + batch_size].contiguous(), rd[i:i + batch_size].contiguous()
+    mine = [i for pi, i in enumerate(range(0, n, batch_size)) if pi % world == rank]
+    for starts in patch_groups(mine, n, batch_size):
+        if len(starts) == 1:
+            i = starts[0]
+            rop, rdp, gp = ro[i:i + batch_size].contiguous(), rd[i:i + batch_size].contiguous(), g[i:i + batch_size]
+        elif all(b - a == batch_size for a, b in zip(starts, starts[1:])):
+            i, j = starts[0], starts[-1] + batch_size
+            rop, rdp, gp = ro[i:j].contiguous(), rd[i:j].contiguous(), g[i:j]
+        else:
+            rop = torch.cat([ro[i:i + batch_size] for i in starts]); rdp = torch.cat([rd[i:i + batch_size] for i in starts])
+            gp = torch.cat([g[i:i + batch_size] for i in starts])
         fwd, scal = render_patch(rop, rdp)
         P = (fwd['d_vals'] if framework == 'volsdf' else fwd['d_all']).shape[-1]
-        eng.render_bwd(rop, rdp, scal, fwd, g[i:i + batch_size], w_eikonal=w_eikonal, eikonal_count=rop.shape[0] * P,
+        # the eikonal term is a mean over ONE patch's samples (volsdf.py:775-777): the normaliser stays batch_size * P for a group
+        eng.render_bwd(rop, rdp, scal, fwd, gp, w_eikonal=w_eikonal, eikonal_count=min(batch_size, rop.shape[0]) * P,
                        white_bkgd=white_bkgd, speed_factor=model.speed_factor, train_surface=train_surface,
                        train_radiance=train_radiance)
-        n_patches += 1
+        n_patches += len(starts)
     parallel.allreduce_sum(eng._gpack, eng._gscal)
     scalar_param = model.ln_beta if framework == 'volsdf' else model.ln_s
     scal = _assign_grads(model, eng, scalar_param, train_surface, train_radiance)

@@ -38,7 +38,7 @@ x = torch.rand(n, 3, device=dev, generator=g) * 4 - 2
 v = torch.nn.functional.normalize(torch.randn(n // 4, 3, device=dev, generator=g), dim=-1)
 F_SDF = 2 * (39 * 256 + 256 * 256 * 2 + 256 * 217 + 256 * 256 * 4 + 256); F_FULL = 2 * (524544 + 459008 + 265216)
 import ctypes as C
-dbg = torch.zeros(512, dtype=torch.int64, device=dev)
+dbg = torch.zeros(1024, dtype=torch.int64, device=dev)
 trace_dir = os.environ.get('NA_TRACE_DIR')
 for prec in ('fp32',) + TC_MODES:
     m.engine().precision = prec

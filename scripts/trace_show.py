@@ -2,7 +2,7 @@
 import sys, numpy as np
 d = np.load(sys.argv[1]).astype(np.int64)[16:]
 n_g = int(sys.argv[2]) if len(sys.argv) > 2 else 21
-M = d[:192].reshape(24, 4, 2); E = d[192:192 + 24 * 12].reshape(24, 4, 3)
+M = d[:352].reshape(44, 4, 2); E = d[352:352 + 44 * 12].reshape(44, 4, 3)          # (buffer of >= 896 int64, see csrc/mlp_tmem.cu)
 t0 = min(x for x in list(M[:n_g].ravel()) + list(E[:n_g].ravel()) if x > 0)
 f = lambda x: f'{x - t0:7d}' if x > 0 else '      -'
 print('g | MMA: kb ready / issued x4 | EPI: D ready / ld done / A stored x4')

@@ -101,3 +101,62 @@ def test_perceptual_loss_equals_the_reference_module_on_the_same_weights(monkeyp
     lr = R(a, b); gr, = torch.autograd.grad(lr, a)
     lm = M(a, b); gm, = torch.autograd.grad(lm, a)
     assert float(lr.detach()) == float(lm.detach()) and torch.equal(gr, gm) and float(gr.abs().max()) > 0
+
+
+def test_patchnce_batched_arithmetic_equals_the_reference_loop():
+    """PatchNCELoss.forward evaluates all crops / classes / templates at once when B == 1; value and image gradient must equal the
+    reference's per-crop loop (patchnce_loss.py:146-160,196-220), here restated literally on a stand-in image tower."""
+    g = torch.Generator().manual_seed(3)
+    P = torch.randn(3 * 8 * 8, 512, generator=g) * 0.1
+
+    class Tower:
+        def encode_image(self, x):                       # [B,3,224,224] -> [B,512]: a fixed linear map of the 8x8 average-pooled image
+            return torch.nn.functional.adaptive_avg_pool2d(x, 8).flatten(1) @ P
+    feats = {}
+
+    def text(s, norm=True):
+        if s not in feats:
+            gg = torch.Generator().manual_seed(len(feats) + 10)
+            f = torch.randn(7, 512, generator=gg)
+            feats[s] = f / f.norm(dim=-1, keepdim=True)
+        return feats[s]
+    loss = PatchNCELoss(Tower(), text, [96, 54])
+    negs = [f'neg {i}' for i in range(8)]
+    img = torch.rand(1, 3, 96, 54, generator=g)
+    img.requires_grad_(True)
+    loss.ZeroPad = torch.nn.ZeroPad2d((54, 54, 96, 96))
+    loss.sample_crops = lambda H, W, th, tw, full: [(3 * k, 2 * k) for k in range(12)]
+    import nerfart_b200.criteria.losses as LM
+
+    def run(fn):
+        if img.grad is not None:
+            img.grad = None
+        v = fn(); v.backward()
+        return float(v), img.grad.clone()
+    # (a 96x54 frame cannot hold the reference's 112-pixel crops: shrink them for this arithmetic check)
+    orig_forward = LM.PatchNCELoss.forward
+
+    def small_crops(self, source_classes, target_img, target_class, is_full_res, batched=True):
+        target_img = self.ZeroPad(target_img)
+        target_img = torch.nn.functional.interpolate(target_img, size=tuple(self.target_hw), mode='bicubic', align_corners=False)
+        crops = [torch.nn.functional.interpolate(target_img[..., i:i + 40, j:j + 30], size=(224, 224), mode='bicubic', align_corners=False)
+                 for i, j in self.sample_crops(96, 54, 40, 30, False)]
+        enc = self.get_image_features(torch.cat(crops, 0))
+        sfl = [self.get_text_features(s, norm=True) for s in source_classes]
+        tf = self.get_text_features(target_class, norm=True)
+        if batched:
+            return self.crop_losses(enc, sfl, tf, 1)
+        total = 0
+        for c in range(12):                              # the reference's loop, one crop at a time
+            e = enc[c:c + 1]
+            near = self.cos(e, tf.detach())
+            neg = 0
+            for sf in sfl:
+                neg = neg + torch.exp(self.cos(e, sf.detach()) / self.temperature)
+            pos = torch.exp(near / self.temperature)
+            total = total + torch.mean(-torch.log(pos / (pos + neg)))
+        return total
+    va, ga = run(lambda: small_crops(loss, negs, img, 'painting', False, True))
+    vb, gb = run(lambda: small_crops(loss, negs, img, 'painting', False, False))
+    assert abs(va - vb) < 1e-5 * abs(vb) and (ga - gb).abs().max() < 1e-5 * gb.abs().max()
+    assert orig_forward is LM.PatchNCELoss.forward

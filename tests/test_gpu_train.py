@@ -229,7 +229,8 @@ def test_trainer_forward_finetune_step_volsdf(monkeypatch, precision):
     (loss already back-propagated, .grad populated, optimizer.zero_grad() called inside), gradients equal to the oracle's.
     fp32 mode, 'tc' and the DEFAULT mode 'tc_mixed' (renders in tc_mixed; the backward program always re-evaluates the forward with tc operands)."""
     from nerfart_b200.models.frameworks import volsdf as pv, _finetune
-    monkeypatch.setattr(_finetune, 'BATCH_SIZE', 500)
+    PB = 200                                                         # 576 rays: two full patches (ONE launch group) + a short one
+    monkeypatch.setattr(_finetune, 'BATCH_SIZE', PB)
     m = make_volsdf(0.1, 0.5, device=DEV).train()
     m.engine().precision = precision
     H = W = 24
@@ -266,10 +267,10 @@ def test_trainer_forward_finetune_step_volsdf(monkeypatch, precision):
     G = rgb.grad[0]
     net = ot.TrainNet(state(m), 'volsdf')
     total = None
-    for i in range(0, H * W, 500):
-        fwd, _ = pv.render_patch(m, ro[0, i:i + 500].contiguous(), rd[0, i:i + 500].contiguous(), **kw)
-        og, _, _ = ot.volsdf_backward(net, ro[0, i:i + 500].cpu().numpy(), rd[0, i:i + 500].cpu().numpy(), fwd['d_vals'].cpu().numpy(),
-                                      G[i:i + 500].cpu().numpy(), 0.1, False)
+    for i in range(0, H * W, PB):                                    # the oracle goes patch by patch, like the reference
+        fwd, _ = pv.render_patch(m, ro[0, i:i + PB].contiguous(), rd[0, i:i + PB].contiguous(), **kw)
+        og, _, _ = ot.volsdf_backward(net, ro[0, i:i + PB].cpu().numpy(), rd[0, i:i + PB].cpu().numpy(), fwd['d_vals'].cpu().numpy(),
+                                      G[i:i + PB].cpu().numpy(), 0.1, False)
         total = og if total is None else OrderedDict((k, total[k] + og[k]) for k in og)
     worst = 0.0
     for k, p in m.named_parameters():

@@ -75,7 +75,8 @@ class _FakeEngine:
     def render_bwd(self, ro, rd, scal, fwd, g, **kw):
         self.calls.append((int(ro.shape[0]), kw['eikonal_count']))
         self._gpack += torch.stack([ro.double().sum(), rd.double().sum(), (g.double() * ro.double()).sum(), torch.tensor(float(ro.shape[0]), dtype=torch.float64)])
-        self._gscal += torch.tensor([g.double().sum(), 1.0], dtype=torch.float64)
+        # second scalar: the number of reference patches this launch stands for (rays x samples / the per-patch eikonal normaliser)
+        self._gscal += torch.tensor([g.double().sum(), ro.shape[0] * fwd['d_vals'].shape[-1] / kw['eikonal_count']], dtype=torch.float64)
 
     def unpack_grads(self, ts, tr):
         return [], self._gscal
@@ -123,9 +124,23 @@ def test_training_patches_round_robin_and_gradient_allreduce_gloo():
     for rank, gpack, scal, calls, lnb in res:
         assert all(abs(a - b) < 1e-9 for a, b in zip(gpack, want)), (gpack, want)
         assert abs(scal[0] - G.double().sum().item()) < 1e-9 and scal[1] == 8.0
+        # launch groups (default NA_PATCH_GROUP = 6): rank 0 holds four full patches -> one launch; rank 1 three full + the short one
+        assert calls == ([(400, 600)] if rank == 0 else [(300, 600), (30, 180)]), calls
         assert abs(lnb[0] - G.double().sum().item()) < 1e-4
-    assert [c[0] for c in res[0][3]] == [100, 100, 100, 100] and [c[0] for c in res[1][3]] == [100, 100, 100, 30]
-    assert all(c[1] == c[0] * 6 for r in res for c in r[3])
+
+
+def test_patch_groups():
+    """_finetune.patch_groups: even groups of at most NA_PATCH_GROUP full patches, a short last patch alone, group 1 = the
+    reference's launch structure (volsdf.py:754-783)."""
+    from nerfart_b200.models.frameworks._finetune import patch_groups
+    starts = list(range(0, 129600, 1200))
+    g6 = patch_groups(starts, 129600, 1200, group=6)
+    assert len(g6) == 18 and all(len(g) == 6 for g in g6) and sum(g6, []) == starts
+    assert patch_groups(starts, 129600, 1200, group=1) == [[i] for i in starts]
+    assert [len(g) for g in patch_groups(starts[3::8], 129600, 1200, group=6)] == [5, 5, 4]      # rank 3 of 8: 14 patches
+    assert [len(g) for g in patch_groups(starts[4::8], 129600, 1200, group=6)] == [5, 4, 4]      # rank 4 of 8: 13 patches
+    assert patch_groups([0, 100, 200], 250, 100, group=6) == [[0, 100], [200]]
+    assert patch_groups([], 250, 100, group=6) == []
 
 
 def _sync_worker(rank, world, port, q):

@@ -103,7 +103,7 @@ def test_cuda_ray_casting_vs_reference(name, framework, rcfg, scfg):
 @pytest.mark.gpu
 def test_extract_mesh_sdf_grid_matches_pointwise_evaluation():
     """mesh_util.sdf_grid: the N^3 SDF samples of extract_mesh equal implicit_surface.forward at the reference's
-    lattice points, and the sphere-initialised network gives |x| - r on them."""
+    lattice points, and the oracle's SDF network on the same points."""
     import numpy as np
     from nerfart_b200.utils import mesh_util as mu
     from helpers import make_volsdf
@@ -114,8 +114,8 @@ def test_extract_mesh_sdf_grid_matches_pointwise_evaluation():
     with torch.no_grad():
         direct = m.implicit_surface.forward(pts).cpu().numpy().reshape(N, N, N)
     assert np.array_equal(grid, direct)
-    r = np.linalg.norm(pts.cpu().numpy(), axis=-1).reshape(N, N, N)
-    assert np.abs(grid - (r - 1.0)).max() < 0.05                              # geometric sphere init, radius_init = 1.0
+    ref = np.asarray(orc.sdf_net(oracle_net(m, 'volsdf'), pts.cpu().numpy())[0]).reshape(N, N, N)      # numpy restatement of base.py:217-262
+    assert np.abs(grid - ref).max() < 1e-4
 
 
 @pytest.mark.gpu
