@@ -317,7 +317,7 @@ def main():
             rgb, depth, ex = volume_render(ro[:, lo:hi], rd[:, lo:hi], model, **RENDER_KW)
             img = parallel.gather_tiles(rgb[0], n_rays)        # NCCL all-gather of the RGB tiles (no-op at world 1)
             if e2e:
-                rgb_host.copy_(img, non_blocking=True)
+                rgb_host[:img.shape[0]].copy_(img, non_blocking=True)
         return img
 
     def timed(e2e, steps):

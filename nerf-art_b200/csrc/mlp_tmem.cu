@@ -53,9 +53,11 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 #ifdef NA_TM_TRACE
 #define NA_TRACE_M(tr, g, kb, w) do { if (tr) (tr)[((g) * 4 + (kb)) * 2 + (w)] = clock64(); } while (0)
 #define NA_TRACE_E(tr, g, ps, w) do { if (tr) (tr)[352 + ((g) * 4 + (ps)) * 3 + (w)] = clock64(); } while (0)
+#define NA_TRACE_X(tr, i) do { if (tr) (tr)[880 + (i)] = clock64(); } while (0)      // free-form stamps (trace_show.py prints them raw)
 #else
 #define NA_TRACE_M(tr, g, kb, w) do { } while (0)
 #define NA_TRACE_E(tr, g, ps, w) do { } while (0)
+#define NA_TRACE_X(tr, i) do { } while (0)
 #endif
 
 enum BwOp { OP_FWD = 0, OP_DR, OP_FB, OP_HB, OP_SO, OP_TR };      // OP_FWD: forward program, dispatched on the program index
@@ -189,7 +191,11 @@ constexpr size_t MK_BYTES = (size_t)4 * EPI_THREADS * 8;
 constexpr size_t SCRATCH_BYTES = DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES + MK_BYTES;
 
 enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_RAD, K_RAD3,
-               K_DR, K_DR0, K_FB, K_HB, K_SO, K_SO3, K_SO7, K_TR };      // BW program only
+               K_DR, K_FB, K_HB, K_SO, K_TR,                              // BW program only (K_DR: layer 0 too; K_SO: layers 3 and 7 too)
+               // training program: ONE body per group, the layer-specific pieces behind warp-uniform run-time tests.  Its 41 epilogues
+               // were 17.5 k SASS instructions (280 KB) walked once per tile: every kind's first pass paid 2-6 k cycles of instruction
+               // fetch (profiles/r4a_bw_trace.md).  The render kernels keep the specialised kinds.
+               K_FWDX, K_BWDX, K_RADX };
 
 struct EpiCtx {
     Smem* S; uint2* dh; float4* featp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
@@ -337,13 +343,31 @@ __device__ __forceinline__ void stash_flush(const EpiCtx& c) {
 
 // BW: entry k of v-bar_0 = (d emb / d x)^T-contracted total d L / d nabla of row r (x rs): x_c -> n_c, sin(f x_c) -> f cos(f x_c) n_c,
 // cos(f x_c) -> -f sin(f x_c) n_c; sin / cos come from the tile's encoding stash (x ACT_SCALE)
-__device__ __forceinline__ float vbar0_entry(const Smem& S, int k, int r, const float (&nbar)[3]) {
-    if (k < 0 || k >= EMB) return 0.f;
-    if (k < 3) return k == 0 ? nbar[0] : (k == 1 ? nbar[1] : nbar[2]);
-    const int f = (k - 3) / 6, rem = (k - 3) % 6, cc = rem % 3;
-    const float nb = cc == 0 ? nbar[0] : (cc == 1 ? nbar[1] : nbar[2]), fr = (float)(1 << f);
-    return rem < 3 ?  nb * fr * S.EMBS[(k + 3) * TM + r] * (1.f / ACT_SCALE)
-                   : -nb * fr * S.EMBS[(k - 3) * TM + r] * (1.f / ACT_SCALE);
+// entries K_LO .. K_LO + 15 with the index arithmetic done at compile time: straight-line code.  (A run-time-index version,
+// sixteen times in a row, was ~750 branchy instructions that run once per tile, i.e. always from a cold instruction cache: 24-38 k
+// cycles per tile on the clock trace, profiles/r4a_bw_trace.md.)
+template <int K_LO>
+__device__ __forceinline__ void vbar0_range(const Smem& S, int r, const float (&nbar)[3], float (&e)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = K_LO + j;
+        float v = 0.f;
+        if (k >= 0 && k < 3) v = nbar[k < 0 ? 0 : (k > 2 ? 2 : k)];
+        else if (k >= 3 && k < EMB) {
+            const int f = (k - 3) / 6, rem = (k - 3) % 6, cc = rem % 3;
+            const float w = (rem < 3 ? 1.f : -1.f) * (float)(1 << f) * (1.f / ACT_SCALE);
+            v = nbar[cc] * w * S.EMBS[(rem < 3 ? k + 3 : k - 3) * TM + r];
+        }
+        e[j] = v;
+    }
+}
+// the 16 entries of column quarter cq (warp-uniform): first entry 16 cq + BASE, BASE = 0 (v-bar_0 itself) or -25 (skip columns of layer 3)
+template <int BASE>
+__device__ __forceinline__ void vbar0_quarter(const Smem& S, int cq, int r, const float (&nbar)[3], float (&e)[16]) {
+    if (cq == 0) vbar0_range<BASE>(S, r, nbar, e);
+    else if (cq == 1) vbar0_range<BASE + 16>(S, r, nbar, e);
+    else if (cq == 2) vbar0_range<BASE + 32>(S, r, nbar, e);
+    else vbar0_range<BASE + 48>(S, r, nbar, e);
 }
 // BW: 16 consecutive columns of row r in a per-CTA fp16 scratch plane (coalesced: a warp instruction covers 32 rows x 16 B)
 __device__ __forceinline__ void qstore16(uint4* base, int plane, int col0, int r, const float (&v)[16]) {
@@ -411,8 +435,15 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     Smem& S = *c.S;
     const int r = c.r;
     const float us = c.us, us16 = c.us * ACT_SCALE;
-    const unsigned bias = c.bias_s + (unsigned)(KIND == K_FEAT ? 8 : (KIND >= K_RAD0 ? 9 + (c.g - 17) : c.g)) * 1024u;
-    constexpr bool USES_DH = FULL && (KIND == K_FEAT || KIND == K_BWD || KIND == K_BWD4);
+    constexpr bool IS_FWD = KIND == K_FWD || KIND == K_FWD3 || KIND == K_FWD7 || KIND == K_FWDX;
+    constexpr bool IS_BWD = KIND == K_BWD || KIND == K_BWD4 || KIND == K_BWDX;
+    constexpr bool IS_RAD = KIND == K_RAD0 || KIND == K_RAD || KIND == K_RAD3 || KIND == K_RADX;
+    constexpr bool IS_BW = KIND >= K_DR && KIND <= K_TR;
+    const bool fwd3 = KIND == K_FWD3 || (KIND == K_FWDX && c.g == 3), fwd7 = KIND == K_FWD7 || (KIND == K_FWDX && c.g == 7);
+    const bool bwd4 = KIND == K_BWD4 || (KIND == K_BWDX && c.g == 12), rad3 = KIND == K_RAD3 || (KIND == K_RADX && c.g == 20);
+    const bool dr0 = KIND == K_DR && c.lyr == 0, so3 = KIND == K_SO && c.lyr == 3, so7 = KIND == K_SO && c.lyr == 7;
+    const unsigned bias = c.bias_s + (unsigned)(KIND == K_FEAT ? 8 : (IS_RAD ? 9 + (c.g - 17) : c.g)) * 1024u;
+    constexpr bool USES_DH = FULL && (KIND == K_FEAT || IS_BWD);
     constexpr int N_PASS = KIND == K_BWD0 ? 1 : 4;                  // reverse GEMM 0: only 39 useful columns, all in pass 0
     // softplus' plane this epilogue multiplies by: feature head (g = 8) -> layer 7, reverse GEMM g = 9..15 -> layer 15 - g
     const uint2* dhp = c.dh + (size_t)((15 - c.g) * 64) * TM + r;
@@ -444,9 +475,9 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         // BW: the scratch / stash rows this pass needs (softplus' codes, g, parked terms) are requested BEFORE the wait for D, so that
         // their L2 / DRAM latency runs under the GEMM instead of on the epilogue's critical path
-        constexpr bool PRE_S = KIND == K_SO || KIND == K_SO3 || KIND == K_SO7 || KIND == K_TR;
-        constexpr bool PRE_G = KIND == K_SO || KIND == K_SO3 || KIND == K_SO7;
-        constexpr bool PRE_Q = KIND == K_TR || KIND == K_SO7;
+        constexpr bool PRE_S = KIND == K_SO || KIND == K_TR;
+        constexpr bool PRE_G = KIND == K_SO;
+        const bool PRE_Q = KIND == K_TR || so7;
         uint2 sraw[4]; uint4 graw[2], qraw[2];
         if (PRE_S) {
             const uint2* p = c.dh + (size_t)(c.lyr * 64 + (col0 >> 2)) * TM + r;
@@ -454,7 +485,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             for (int j4 = 0; j4 < 4; ++j4) sraw[j4] = p[(size_t)j4 * TM];
         }
         if (PRE_G) {
-            if (c.lyr == 0 && c16 == 0) stash_flush(c);              // the g planes (TMA-stored during the reverse sweep) are read back from here on
+            if (c.lyr == 0 && c16 == 0) { NA_TRACE_X(c.trace, 5); stash_flush(c); NA_TRACE_X(c.trace, 6); }     // the g planes (TMA-stored during the reverse sweep) are read back from here on
             const uint4* p = reinterpret_cast<const uint4*>(c.st_row + (size_t)(ST_G + c.lyr) * c.st_plane + col0);
             graw[0] = __ldcg(p); graw[1] = __ldcg(p + 1);
         }
@@ -485,7 +516,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
         }
         float o[16];
-        if (KIND == K_FWD || KIND == K_FWD3 || KIND == K_FWD7) {
+        if (IS_FWD) {
             // z16 = 16 z ; softplus_100(z) = max(z,0) + ln2/100 * log2(1 + 2^(-|100 z| log2 e)).  Written stage by stage over the 16
             // columns so that 16 independent MUFU.EX2 / MUFU.LG2 are in flight per warp.
             float z16[16], t[16];
@@ -509,12 +540,12 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     for (int i = 0; i < 4; ++i) {
                         const int j = 4 * j4 + i;
                         cd[i] = dh_code(z16[j], t[j]);
-                        if (KIND == K_FWD3 && col0 + j >= SKIP_H) cd[i] = 0u;          // decodes to 0
+                        if (fwd3 && col0 + j >= SKIP_H) cd[i] = 0u;          // decodes to 0
                     }
                     c.dh[(size_t)(c.g * 64 + (col0 >> 2) + j4) * TM + r] = make_uint2(cd[0] | (cd[1] << 16), cd[2] | (cd[3] << 16));
                 }
             }
-            if (KIND == K_FWD3 && c16 == 3 && c.cq >= 1) {
+            if (fwd3 && c16 == 3 && c.cq >= 1) {
                 // skip connection columns (k >= 217): h = emb[k - 217] (x16); this thread's 16 columns are encoding entries
                 // 16 cq - 25 .. + 16
                 const int e0 = 16 * c.cq - 25;
@@ -535,7 +566,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             if (ST) {
                 stash16(c, ST_IN + c.g, col0, o, 1.f / ACT_SCALE);
             }
-            if (KIND == K_FWD7) {
+            if (fwd7) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
@@ -564,7 +595,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             }
             if (ST) stash16(c, ST_FEAT, col0, fst, 1.f);
             if (ST && FULL) { stash16(c, ST_G + 7, col0, o, 1.f / ACT_SCALE); }
-        } else if (KIND == K_BWD || KIND == K_BWD4) {
+        } else if (IS_BWD) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 float dd[4];
@@ -572,7 +603,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int k = col0 + 4 * j4 + i;
-                    if (KIND == K_BWD4 && k >= SKIP_H) c.misc[(k - SKIP_H) * TM + r] = acc[4 * j4 + i] * us;      // embedding branch of the skip
+                    if (bwd4 && k >= SKIP_H) c.misc[(k - SKIP_H) * TM + r] = acc[4 * j4 + i] * us;      // embedding branch of the skip
                     o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
                 }
             }
@@ -580,15 +611,15 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         } else if (KIND == K_BWD0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[k * TM + r] += acc[j] * us; }
-        } else if (KIND >= K_DR) {
+        } else if (IS_BW) {
             // ---- backward program (BW): every value is carried x rs in the operands; stash planes receive x irs ----------------
-            if (KIND == K_DR || KIND == K_DR0) {
+            if (KIND == K_DR) {
                 // delta_lyr = (delta_{lyr+1} R_{lyr+1}) * [ys_{lyr+1} > 0]   (radiance hidden layers, lyr = 2, 1, 0)
                 const unsigned long long m64 = c.mk[(size_t)c.lyr * EPI_THREADS] >> (16 * c16);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = ((m64 >> j) & 1ull) ? acc[j] * us16 : 0.f;
                 stash16(c, ST_D + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
-                if (KIND == K_DR0) {
+                if (dr0) {
                     // d L / d nabla through radiance layer 0: delta_0 . W0[:, nabla columns]  (partial over this thread's columns)
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc)
@@ -610,7 +641,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = acc[j] * us;
                 qstore16(c.qp, 7, col0, r, o);
-            } else if (KIND == K_SO || KIND == K_SO3 || KIND == K_SO7) {
+            } else if (KIND == K_SO) {
                 // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
                 float sv[16], gv[16], q[16];
 #pragma unroll
@@ -622,12 +653,15 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     q[j] = 100.f * gb * gv[j] * (1.f - sv[j]);
                     o[j] = gb * sv[j];
                 }
-                if (KIND == K_SO3 && col0 + 15 >= SKIP_H) {
+                if (so3 && c16 == 3 && c.cq >= 1) {
+                    // skip connection: columns k >= SKIP_H = 217 of v-bar_4 are v-bar_0 entries k - 217 (this thread: 16 cq - 25 ..)
+                    float e[16];
+                    vbar0_quarter<-25>(S, c.cq, r, c.nbar, e);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (col0 + j >= SKIP_H) o[j] = vbar0_entry(S, col0 + j - SKIP_H, r, c.nbar);      // skip connection
+                    for (int j = 0; j < 16; ++j) if (16 * c.cq - 25 + j >= 0) o[j] = e[j];
                 }
                 stash16(c, ST_VB + c.lyr, col0, o, c.irs);
-                if (KIND == K_SO7) {
+                if (so7) {
                     // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]
                     float hb[16];
                     qdecode16(qraw, hb);
@@ -696,7 +730,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 unsigned long long* slot = c.mk + (size_t)(c.g - 17) * EPI_THREADS;
                 *slot = (c16 == 0 ? 0ull : *slot) | (m16 << (16 * c16));
             }
-            if (KIND == K_RAD3) {
+            if (rad3) {
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
@@ -707,8 +741,8 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     }
             }
         }
-        const bool store = !(KIND == K_BWD0 || KIND == K_RAD3 || KIND == K_HB || (KIND == K_FWD7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL) ||
-                             (KIND >= K_DR && !c.signal));
+        const bool store = !(KIND == K_BWD0 || rad3 || KIND == K_HB || (fwd7 && !FULL && !c.job->feat) || (KIND == K_FEAT && !FULL) ||
+                             (IS_BW && !c.signal));
         if (store) store_a16(t_d + col0, o, c.need_lo);
         NA_TRACE_E(c.trace, c.g, c16, 2);
         if (USES_DH && (c.lane & 15) == 0 && !(ST && c.bw)) {
@@ -812,7 +846,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 // BEFORE this GEMM's MMAs are issued: once D is committed the epilogue starts signalling the same barriers for the
                 // next GEMM, and a second completion before this warp's wait flips the parity back -- the wait would then never
                 // return (mbarrier phase aliasing; this was the intermittent first-step stall, profiles/r3a_stall_root_cause.md).
+                if (g == 26) NA_TRACE_X(tr, 8);
                 for (int kb = n_kb; kb < 4; ++kb) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d040000u | ((unsigned)g << 8) | (unsigned)kb);
+                if (g == 26) NA_TRACE_X(tr, 9);
 #ifndef NA_TM_ORDERS
                 const int order = 0;          // orders 1 / 2 are a build option (-DNA_TM_ORDERS): their code costs 2.4 % of the SDF-only tile even unused
 #else
@@ -1088,8 +1124,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
             // previous D; also the narrow v-bar_0 stash plane
             auto write_vbar0 = [&](unsigned t_region) {
                 float e[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) e[j] = vbar0_entry(S, 16 * cq + j, r, c.nbar);
+                NA_TRACE_X(c.trace, 0);
+                vbar0_quarter<0>(S, cq, r, c.nbar, e);
+                NA_TRACE_X(c.trace, 1);
                 if (c.st_row && job.st_vb0) {
                     uint4 lo, hi;
                     pack16(e, c.irs, lo, hi);
@@ -1098,8 +1135,11 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) e[j] *= ACT_SCALE;
+                NA_TRACE_X(c.trace, 2);
                 store_a16(t_region + (unsigned)(16 * cq), e, 0);
+                NA_TRACE_X(c.trace, 3);
                 for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
+                NA_TRACE_X(c.trace, 4);
             };
             for (int g = 0; g < prog.n_gemm; ++g) {
                 const int op = BW ? (int)prog.g[g].op : (int)OP_FWD;
@@ -1114,28 +1154,27 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
                 if (BW && op != OP_FWD) {
                     if (op == OP_DR) {
-                        if (c.lyr == 0) epi_gemm<K_DR0, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
-                        else epi_gemm<K_DR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        epi_gemm<K_DR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (op == OP_FB) {
                         epi_gemm<K_FB, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (op == OP_HB) {
                         epi_gemm<K_HB, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (op == OP_SO) {
-                        if (c.lyr == 3) epi_gemm<K_SO3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
-                        else if (c.lyr == 7) epi_gemm<K_SO7, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
-                        else epi_gemm<K_SO, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        epi_gemm<K_SO, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else {
                         epi_gemm<K_TR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     }
                 } else if (g < 8) {
-                    if (g == 3) epi_gemm<K_FWD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    if (ST) epi_gemm<K_FWDX, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    else if (g == 3) epi_gemm<K_FWD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     else if (g == 7) epi_gemm<K_FWD7, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     else epi_gemm<K_FWD, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                 } else if (g == 8) {
                     epi_gemm<K_FEAT, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                 } else if (FULL) {
                     if (g <= 15) {
-                        if (g == 12) epi_gemm<K_BWD4, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        if (ST) epi_gemm<K_BWDX, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                        else if (g == 12) epi_gemm<K_BWD4, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                         else epi_gemm<K_BWD, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 16) {
                         epi_bar_sync();                                   // embedding-branch gradients (written at g == 12 by other threads)
@@ -1174,6 +1213,8 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                             __stcs(srow, lo); __stcs(srow + 1, hi);
                         }
                         epi_gemm<K_RAD0, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
+                    } else if (ST) {
+                        epi_gemm<K_RADX, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (g == 20) {
                         epi_gemm<K_RAD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else {

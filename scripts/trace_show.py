@@ -18,3 +18,6 @@ for g in range(n_g):
     gap2 = M[g, 0, 0] - E[g - 1, 0, 2] if g > 0 and E[g - 1, 0, 2] > 0 else -1
     per = E[g, 0, 0] - E[g - 1, 0, 0] if g > 0 else -1
     print(f'{g:2d} | passes {durs} ld {ld} | D-wait {gap:6d} | kb0 ready after pass0 store {gap2:6d} | period {per}')
+x = d[880:896]
+if (x > 0).any():
+    print('free-form stamps:', ' '.join(f'X{i}={int(v - t0)}' for i, v in enumerate(x) if v > 0))
