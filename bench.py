@@ -236,6 +236,58 @@ def train_probe(dev, precision, n_patches=8):
     return out
 
 
+def small_beta_probe(dev, precision, step=8):
+    """Informational line beside the headline: the same frame with beta = 0.01, where the error-bound sampler runs
+    its upsampling iterations on most rays (trained checkpoints live there; BASELINE.md section 3 quotes ~1385 evaluations per ray).
+    Reports ms / frame, SDF evaluations per ray, and -- on every `step`-th ray -- the share of rays whose rgb differs by more than 1e-3
+    from the UNMODIFIED reference rendered on this GPU, for the default mode and for the fp32 CUDA-core mode (the sampler is
+    discontinuous: two fp32-correct evaluations already disagree on ~12 % of the rays of the 400-ray beta = 0.01 fixture)."""
+    import nerfart_b200  # noqa: F401
+    import ref_runner
+    import fixtures as fx
+    from helpers import make_volsdf
+    from nerfart_b200.models.frameworks.volsdf import volume_render
+    from nerfart_b200.utils import rend_util
+    beta = 0.01
+    m = make_volsdf(beta, 0.0, device=dev)
+    m.engine().precision = precision
+    c2w, K = make_inputs()
+    out = {'beta': beta}
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(dev), K[None].to(dev), H, W)
+        volume_render(ro, rd, m, **RENDER_KW)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            volume_render(ro, rd, m, **RENDER_KW)
+        e1.record(); torch.cuda.synchronize()
+        out['ms_per_frame'] = e0.elapsed_time(e1) / 2
+        sel = torch.arange(0, H * W, step, device=dev)
+        kw = dict(RENDER_KW, detailed_output=True)
+        rgb, _, ex = volume_render(ro[:, sel], rd[:, sel], m, **kw)
+        usage = ex['iter_usage'].reshape(-1)
+        iters = torch.where(usage < 0, torch.full_like(usage, float(RENDER_KW.get('max_upsample_steps', 6))), usage)
+        out['sdf_evals_per_ray'] = float((4 * N_SAMPLES * (1 + iters)).mean()) + P
+        out['rays_not_converged_frac'] = float((usage < 0).float().mean())
+        out['samples_per_s'] = H * W * P / (out['ms_per_frame'] * 1e-3)
+        if ref_runner.reference_root() is not None:
+            rm = ref_runner.build_model('volsdf', make_volsdf(beta, 0.0).state_dict(), fx.volsdf_kwargs(beta), device=str(dev))
+            rr = ref_runner.load()['rend_util']
+            rro, rrd, _ = rr.get_rays(c2w[None].to(dev), K[None].to(dev), H, W, -1)
+            ref_rgb, _, _, dt = ref_runner.volume_render('volsdf', rm, rro[:, sel], rrd[:, sel], **REF_KW)
+            out['reference_gpu_s'] = dt
+            d_def = (rgb[0] - ref_rgb[0]).abs().amax(-1)
+            m.engine().precision = 'fp32'
+            rgb32, _, _ = volume_render(ro[:, sel], rd[:, sel], m, **RENDER_KW)
+            d_32 = (rgb32[0] - ref_rgb[0]).abs().amax(-1)
+            out['vs_reference_gpu'] = {'rays': int(sel.numel()),
+                                       precision: {'rgb_diff_gt_1e-3_frac': float((d_def > 1e-3).float().mean()), 'rgb_diff_median': float(d_def.median())},
+                                       'fp32': {'rgb_diff_gt_1e-3_frac': float((d_32 > 1e-3).float().mean()), 'rgb_diff_median': float(d_32.median())}}
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(args, extra=None):
     c = {'workload': f'VolSDF fangzhou_nature-shaped synthetic render {H}x{W} ({H*W} rays), N_samples={N_SAMPLES}, N_importance={N_IMPORTANCE}, '
                      f'd_init={4 * N_SAMPLES}, seed-0 sphere init beta=0.1, radiance gains x3, closed-form camera',
@@ -398,8 +450,11 @@ def main():
                 'frame_frac_of_peak': n_rays * (4 * N_SAMPLES * F_SDF + P * F_FULL) / (t_dev / args.steps) / 1e12 / peak / world}
         del x, v
     probe = None
+    beta_probe = None
     if rank == 0 and not light and world == 1:
         probe = train_probe(dev, args.precision)
+        if args.config == 2:
+            beta_probe = small_beta_probe(dev, args.precision)
     cpu = None
     ref_gpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -437,7 +492,7 @@ def main():
                 'all_evals_per_s': n_rays * (4 * N_SAMPLES + P) * args.steps / t_dev,
                 'e2e': {'value': samples / t_e2e, 'unit': 'samples/s', 'ms_per_step': 1e3 * t_e2e / args.steps,
                         'h2d_bytes_per_step': 2 * 16 * 4, 'd2h_bytes_per_step': n_rays * 3 * 4},
-                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'train_probe': probe}
+                'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'train_probe': probe, 'small_beta_probe': beta_probe}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

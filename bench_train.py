@@ -206,6 +206,7 @@ def main(args):
                 'phases_ms': {'pass1_render': 1e3 * t_p1, 'pass2_patch_forward': 1e3 * t_pfwd, 'pass2_backward': 1e3 * t_bwd,
                               'style_loss_forward': 1e3 * t_style,
                               'other (style backward, unpack, Adam, host)': 1e3 * (t / args.steps - t_p1 - t_pfwd - t_bwd - t_style)},
+                'style_ms_per_step': [round(a.elapsed_time(b), 2) for a, b, _ in phases['style']],
                 'e2e': {'value': n_rays * P * args.steps / t, 'unit': 'samples/s', 'ms_per_step': 1e3 * t / args.steps,
                         'h2d_bytes_per_step': 2 * 64 + n_rays * 12, 'd2h_bytes_per_step': 4,
                         'note': 'the step is timed through Trainer.forward with pinned-host camera / target image in and the loss out'},

@@ -50,6 +50,17 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 // NA_TM_TRACE (diagnostic build): CTA 0 records clock64() stamps of its second tile into job.dbg[16..]:
 //   MMA lane:      slot (g*4+kb)*2 + {0: K-block of A ready, 1: its MMAs issued}                      (44 GEMMs: 352 slots)
 //   epilogue lane: slot 352 + (g*4+pass)*3 + {0: D quarter ready, 1: tcgen05.ld done, 2: A stored}    (528 slots; buffer >= 16 + 880 int64)
+// NA_TM_CYCLES (diagnostic build, implied by NA_TM_TRACE): CTA 0 accumulates the cycles its MMA lane / one epilogue lane spend in their
+// waits into job.dbg[0..4] (scripts/tc_check.py prints them).  Not in the default build: two clock reads and a 64-bit accumulate around
+// every wait are ~3 % of an SDF-only epilogue pass.
+#if defined(NA_TM_TRACE) && !defined(NA_TM_CYCLES)
+#define NA_TM_CYCLES
+#endif
+#ifdef NA_TM_CYCLES
+#define NA_CYC(...) __VA_ARGS__
+#else
+#define NA_CYC(...)
+#endif
 #ifdef NA_TM_TRACE
 #define NA_TRACE_M(tr, g, kb, w) do { if (tr) (tr)[((g) * 4 + (kb)) * 2 + (w)] = clock64(); } while (0)
 #define NA_TRACE_E(tr, g, ps, w) do { if (tr) (tr)[352 + ((g) * 4 + (ps)) * 3 + (w)] = clock64(); } while (0)
@@ -204,6 +215,7 @@ struct EpiCtx {
     int signal, need_lo, lane;
     unsigned short* st_row;         // ST: this thread's row in plane 0 of the 16-bit stash (st_wide + m * 256), nullptr beyond the allocation
     size_t st_plane;                // ST: elements per plane
+    int st_mpad;                    // ST: rows per plane (the TMA row coordinate of plane p, sample m is p * st_mpad + m: below 2^31)
     long long st_m;                 // ST: flat sample index of the row
     const TmaMap* st_map;           // ST: tensor map of the wide planes (store boxes: 16 columns x 32 samples)
     unsigned st_stg;                // ST: this warp's two 1 KB staging buffers in shared memory
@@ -329,7 +341,7 @@ __device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, co
     if (c.lane == 0) {
         // L2 evict-first: the planes stream out to HBM and must not displace the per-CTA scratch (read back three times per tile)
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
-                     :: "l"(c.st_map), "r"(col0), "r"((int)((size_t)plane * (c.st_plane >> 8)) + c.st_row0), "r"(buf), "l"(c.st_policy) : "memory");
+                     :: "l"(c.st_map), "r"(col0), "r"(plane * c.st_mpad + c.st_row0), "r"(buf), "l"(c.st_policy) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     ++c.st_cnt;
@@ -370,26 +382,29 @@ __device__ __forceinline__ void vbar0_quarter(const Smem& S, int cq, int r, cons
     else vbar0_range<BASE + 48>(S, r, nbar, e);
 }
 // BW: 16 consecutive columns of row r in a per-CTA fp16 scratch plane (coalesced: a warp instruction covers 32 rows x 16 B)
+// The planes hold value x 2^-8 (QP_SCALE): the parked terms reach 1e4 (100 g-bar g); the saturating conversion keeps an outlier finite
+// instead of turning the patch into NaN.  PRESCALED: `v` already carries the factor (folded into the caller's constants).
+constexpr float QP_SCALE = 0.00390625f, QP_UNSCALE = 256.f;
+template <bool PRESCALED>
 __device__ __forceinline__ void qstore16(uint4* base, int plane, int col0, int r, const float (&v)[16]) {
     uint4* p = base + (size_t)(plane * 32 + (col0 >> 3)) * TM + r;
 #pragma unroll
     for (int j8 = 0; j8 < 2; ++j8) {
         unsigned w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // x 2^-8: the parked terms reach 1e4 (100 g-bar g); the saturating conversion keeps an outlier finite instead of turning the patch into NaN
-            w[i] = pack_half2_sat(v[8 * j8 + 2 * i] * 0.00390625f, v[8 * j8 + 2 * i + 1] * 0.00390625f);
-        }
+        for (int i = 0; i < 4; ++i)
+            w[i] = PRESCALED ? pack_half2_sat(v[8 * j8 + 2 * i], v[8 * j8 + 2 * i + 1])
+                             : pack_half2_sat(v[8 * j8 + 2 * i] * QP_SCALE, v[8 * j8 + 2 * i + 1] * QP_SCALE);
         p[(size_t)j8 * TM] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 // decode of the prefetched rows: parked fp16 terms (x 2^-8), bf16 stash rows
-__device__ __forceinline__ void qdecode16(const uint4 (&q)[2], float (&v)[16]) {
+__device__ __forceinline__ void qdecode16(const uint4 (&q)[2], float (&v)[16], float scale = QP_UNSCALE) {       // scale: QP_UNSCALE x the caller's unit
 #pragma unroll
     for (int j8 = 0; j8 < 2; ++j8) {
         const unsigned w[4] = {q[j8].x, q[j8].y, q[j8].z, q[j8].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x * 256.f; v[8 * j8 + 2 * i + 1] = f.y * 256.f; }
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[8 * j8 + 2 * i] = f.x * scale; v[8 * j8 + 2 * i + 1] = f.y * scale; }
     }
 }
 __device__ __forceinline__ void bf16x16_to_float(const uint4 (&q)[2], float (&v)[16]) {
@@ -430,6 +445,8 @@ __device__ __forceinline__ unsigned scratch_planes_of(int op, int lyr, int g, in
 }
 
 // one GEMM's epilogue for this thread's row and its 64 columns (4 passes of 16)
+// trace build: stamps inside pass 1 of the second-order sweep's third GEMM (program index 28)
+#define NA_TRACE_XS(i) do { if (KIND == K_SO && c.g == 28 && c16 == 1) NA_TRACE_X(c.trace, i); } while (0)
 template <int KIND, bool FULL, bool ST>
 __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, float& sdf_part, float (&rgb_part)[3], const float (&small_in)[36]) {
     Smem& S = *c.S;
@@ -460,6 +477,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         // thread = (row, column quarter cq): in pass c16 it owns columns 64*c16 + 16*cq .. +16, i.e. every pass completes one
         // 64-wide K-block of the next layer's A operand across the 16 epilogue warps
         const int col0 = c16 * 64 + c.cq * 16;
+        NA_TRACE_XS(7);
 #ifndef NA_TM_NO_PREFETCH
         // (training program only: in the render kernel, whose 0.7 MB scratch per CTA mostly stays in L2, the extra requests cost 3 %)
         if (FULL && ST) prefetch_next_gemm<ST>(c, col0);
@@ -495,14 +513,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             else { qraw[0] = make_uint4(0u, 0u, 0u, 0u); qraw[1] = qraw[0]; }
         }
         {                                                            // pass c16 reads N-quarter c16 of D
-            const long long t0 = clock64();
+            NA_CYC(const long long t0 = clock64();)
             mbar_wait_plain(c.d_bar + 8u * (unsigned)c16, c.d_phase);
             if (N_PASS < 4) {
                 // a GEMM whose epilogue reads fewer than four N-quarters (the 64-wide reverse GEMM 0: its four d_ready commits are
                 // issued together): consume the other phases here, before anything is signalled to the MMA warp
                 for (int k = N_PASS; k < 4; ++k) mbar_wait_plain(c.d_bar + 8u * (unsigned)k, c.d_phase);
             }
-            *c.t_wait += clock64() - t0;
+            NA_CYC(*c.t_wait += clock64() - t0;)
             tc_fence_after();
             NA_TRACE_E(c.trace, c.g, c16, 0);
         }
@@ -512,6 +530,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             tmem_ld16(t_d + col0, v);
             tmem_wait_ld();
             NA_TRACE_E(c.trace, c.g, c16, 1);
+            NA_TRACE_XS(10);
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
         }
@@ -640,32 +659,37 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 // feature part of h-bar_7, parked (x rs) in scratch plane 7 until the second-order sweep reaches layer 7
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = acc[j] * us;
-                qstore16(c.qp, 7, col0, r, o);
+                qstore16<false>(c.qp, 7, col0, r, o);
             } else if (KIND == K_SO) {
-                // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr
+                // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr.
+                // Units are folded into the constants: o is carried x ACT_SCALE (the A operand's unit; the stash scale undoes it), q is
+                // produced x QP_SCALE (the parked plane's unit): t = 16 g-bar, q' = (t g) ((1 - s) 100 / 16 / 256).
                 float sv[16], gv[16], q[16];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) { float d4[4]; dh_decode4(sraw[j4], d4); sv[4 * j4] = d4[0]; sv[4 * j4 + 1] = d4[1]; sv[4 * j4 + 2] = d4[2]; sv[4 * j4 + 3] = d4[3]; }
                 bf16x16_to_float(graw, gv);
+                constexpr float QK = 100.f / ACT_SCALE * QP_SCALE;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float gb = acc[j] * us;
-                    q[j] = 100.f * gb * gv[j] * (1.f - sv[j]);
-                    o[j] = gb * sv[j];
+                    const float t = acc[j] * us16;
+                    q[j] = (t * gv[j]) * fmaf(sv[j], -QK, QK);
+                    o[j] = t * sv[j];
                 }
                 if (so3 && c16 == 3 && c.cq >= 1) {
                     // skip connection: columns k >= SKIP_H = 217 of v-bar_4 are v-bar_0 entries k - 217 (this thread: 16 cq - 25 ..)
                     float e[16];
                     vbar0_quarter<-25>(S, c.cq, r, c.nbar, e);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (16 * c.cq - 25 + j >= 0) o[j] = e[j];
+                    for (int j = 0; j < 16; ++j) if (16 * c.cq - 25 + j >= 0) o[j] = e[j] * ACT_SCALE;
                 }
-                stash16(c, ST_VB + c.lyr, col0, o, c.irs);
+                NA_TRACE_XS(11);
+                stash16(c, ST_VB + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
+                NA_TRACE_XS(12);
                 if (so7) {
-                    // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]
+                    // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]   (x ACT_SCALE)
                     float hb[16];
-                    qdecode16(qraw, hb);
-                    const float gs = S.BWV[6 * TM + r];
+                    qdecode16(qraw, hb, QP_UNSCALE * ACT_SCALE);
+                    const float gs = S.BWV[6 * TM + r] * ACT_SCALE;
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
@@ -673,24 +697,21 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                         hb[4 * j4 + 2] = fmaf(gs, w4.z, hb[4 * j4 + 2]); hb[4 * j4 + 3] = fmaf(gs, w4.w, hb[4 * j4 + 3]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = fmaf(hb[j], sv[j], q[j]);
-                    stash16(c, ST_ZB + 7, col0, o, c.irs);
+                    for (int j = 0; j < 16; ++j) o[j] = fmaf(hb[j], sv[j], q[j] * (QP_UNSCALE * ACT_SCALE));
+                    stash16(c, ST_ZB + 7, col0, o, c.irs * (1.f / ACT_SCALE));
                 } else {
-                    qstore16(c.qp, c.lyr, col0, r, q);                                   // parked (x rs) until the trunk reaches this layer
+                    qstore16<true>(c.qp, c.lyr, col0, r, q);                             // parked (x rs) until the trunk reaches this layer
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
+                NA_TRACE_XS(13);
             } else {
-                // trunk, K_TR: z-bar_lyr = h-bar_lyr s_lyr + q_lyr
+                // trunk, K_TR: z-bar_lyr = h-bar_lyr s_lyr + q_lyr   (carried x ACT_SCALE, see K_SO)
                 float sv[16], qv[16];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) { float d4[4]; dh_decode4(sraw[j4], d4); sv[4 * j4] = d4[0]; sv[4 * j4 + 1] = d4[1]; sv[4 * j4 + 2] = d4[2]; sv[4 * j4 + 3] = d4[3]; }
-                qdecode16(qraw, qv);
+                qdecode16(qraw, qv, QP_UNSCALE * ACT_SCALE);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j] * us, sv[j], qv[j]);
-                stash16(c, ST_ZB + c.lyr, col0, o, c.irs);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] *= ACT_SCALE;
+                for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j] * us16, sv[j], qv[j]);
+                stash16(c, ST_ZB + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
             }
             // (single-product fp16 operands: an outlier |x rs| > 4e3 saturates in store_a16's conversion instead of rounding to inf)
         } else {
@@ -745,6 +766,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                              (IS_BW && !c.signal));
         if (store) store_a16(t_d + col0, o, c.need_lo);
         NA_TRACE_E(c.trace, c.g, c16, 2);
+        NA_TRACE_XS(14);
         if (USES_DH && (c.lane & 15) == 0 && !(ST && c.bw)) {
             // the 16 lanes' codes of this pass share one line per column quad; they are dead now: keep them out of DRAM
 #pragma unroll
@@ -831,7 +853,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
         // ================= MMA issuer =================
         // the whole warp walks the program (converged control flow, waits included); one elected lane issues tcgen05.mma / commit
         unsigned it = 0, a_phase = 0;
-        long long t_a = 0, t_full = 0, t_tot0 = clock64();
+        NA_CYC(long long t_a = 0; long long t_full = 0; const long long t_tot0 = clock64();)
         const unsigned wst = smem_u32(S.Wst);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int g = 0; g < prog.n_gemm; ++g) {
@@ -861,11 +883,11 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     for (int kb = 0; kb < n_a; ++kb) {
                         const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1, slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
                         const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
-                        { const long long t0 = clock64();
+                        { NA_CYC(const long long t0 = clock64();)
                           mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
                           mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, &sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
-                          t_full += clock64() - t0; }
-                        { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                          NA_CYC(t_full += clock64() - t0;) }
+                        { NA_CYC(const long long t0 = clock64();) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); NA_CYC(t_a += clock64() - t0;) }
                         tc_fence_after();
                         NA_TRACE_M(tr, g, kb, 0);
                         if (elect_one()) {
@@ -885,9 +907,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     for (int kb = 0; kb < n_a; ++kb) {
                         const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1;
                         const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
-                        { const long long t0 = clock64();
+                        { NA_CYC(const long long t0 = clock64();)
                           mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d050000u | ((unsigned)g << 8) | (unsigned)kb);
-                          t_full += clock64() - t0; }
+                          NA_CYC(t_full += clock64() - t0;) }
                         tc_fence_after();
                         if (elect_one()) {
                             const unsigned long long bd0 = umma_desc(wst + slot0 * STAGE_BYTES);
@@ -917,11 +939,11 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     const int kb = n_kb - 1;
                     const unsigned slot0 = it % NSK, ph0 = (it / NSK) & 1, slot1 = (it + 1) % NSK, ph1 = ((it + 1) / NSK) & 1;
                     const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
-                    { const long long t0 = clock64();
+                    { NA_CYC(const long long t0 = clock64();)
                       mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
                       mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, &sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
-                      t_full += clock64() - t0; }
-                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                      NA_CYC(t_full += clock64() - t0;) }
+                    { NA_CYC(const long long t0 = clock64();) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); NA_CYC(t_a += clock64() - t0;) }
                     tc_fence_after();
                     NA_TRACE_M(tr, g, kb, 0);
                     if (elect_one()) {
@@ -957,11 +979,11 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     const unsigned a_hi = t_in + (unsigned)(kb * 4) * 16u;
                     // the weights first (the ring runs K-blocks ahead, so these return at once), then the A operand: the MMAs go out
                     // right behind the epilogue's signal
-                    { const long long t0 = clock64();
+                    { NA_CYC(const long long t0 = clock64();)
                       mbar_wait_guarded(smem_u32(&S.full_bar[slot0]), ph0, &sc, 0x4d010000u | ((unsigned)g << 8) | (unsigned)kb);
                       if (prods == 3) mbar_wait_guarded(smem_u32(&S.full_bar[slot1]), ph1, &sc, 0x4d020000u | ((unsigned)g << 8) | (unsigned)kb);
-                      t_full += clock64() - t0; }
-                    { const long long t0 = clock64(); mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); t_a += clock64() - t0; }
+                      NA_CYC(t_full += clock64() - t0;) }
+                    { NA_CYC(const long long t0 = clock64();) mbar_wait_guarded(smem_u32(&S.kb_ready[kb]), a_phase, &sc, 0x4d030000u | ((unsigned)g << 8) | (unsigned)kb); NA_CYC(t_a += clock64() - t0;) }
                     tc_fence_after();
                     NA_TRACE_M(tr, g, kb, 0);
                     if (elect_one()) {
@@ -1014,7 +1036,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     __syncwarp();
                 }
             }
-        if (job.dbg && blockIdx.x == 0 && lane == 0) { job.dbg[0] = clock64() - t_tot0; job.dbg[1] = t_a; job.dbg[2] = t_full; }
+        NA_CYC(if (job.dbg && blockIdx.x == 0 && lane == 0) { job.dbg[0] = clock64() - t_tot0; job.dbg[1] = t_a; job.dbg[2] = t_full; })
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3, cq = (warp - 2) >> 2;
@@ -1028,8 +1050,8 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
         c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4); c.radw_s = smem_u32(S.RADW);
         c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
         c.d_phase = 0;
-        long long t_d = 0, t_e0 = clock64();
-        c.t_wait = &t_d; c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256;
+        NA_CYC(long long t_d = 0; const long long t_e0 = clock64(); c.t_wait = &t_d;)
+        c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256; c.st_mpad = (int)job.st_mpad;
         c.st_m = 0; c.st_map = &job.st_store_map; c.st_cnt = 0; c.st_row0 = 0;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.st_policy));
         c.st_stg = smem_u32(S.Wst) + (unsigned)(NS - 1) * STAGE_BYTES + (unsigned)(warp - 2) * 2048u;
@@ -1368,7 +1390,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
             }
         }
         if (ST) stash_flush(c);
-        if (job.dbg && blockIdx.x == 0 && tid == 64) { job.dbg[3] = clock64() - t_e0; job.dbg[4] = t_d; }
+        NA_CYC(if (job.dbg && blockIdx.x == 0 && tid == 64) { job.dbg[3] = clock64() - t_e0; job.dbg[4] = t_d; })
     }
     tc_fence_before();
     __syncthreads();

@@ -52,5 +52,5 @@ for prec in ('fp32',) + TC_MODES:
         print(f'{prec:9s} {name:9s} {cnt/t/1e6:9.2f} Msamples/s  {cnt*fl/t/1e12:8.2f} TFLOP/s (algorithmic)  {t*1e3:8.2f} ms')
         if prec != 'fp32':
             if trace_dir: np.save(os.path.join(trace_dir, f'trace_{prec}_{name}.npy'), dbg.cpu().numpy())
-            d = dbg.cpu().tolist(); ntile = (cnt + 127) // 128 / 148
-            print(f'      CTA0 cycles/tile: mma-thread total {d[0]/ntile:9.0f}  wait a_ready {d[1]/ntile:9.0f}  wait weights {d[2]/ntile:9.0f} | epilogue total {d[3]/ntile:9.0f}  wait d_ready {d[4]/ntile:9.0f}')
+            d = dbg.cpu().tolist(); ntile = (cnt + 127) // 128 / 148          # (cycle counters: -DNA_TM_CYCLES builds only)
+            if d[0] > 0: print(f'      CTA0 cycles/tile: mma-thread total {d[0]/ntile:9.0f}  wait a_ready {d[1]/ntile:9.0f}  wait weights {d[2]/ntile:9.0f} | epilogue total {d[3]/ntile:9.0f}  wait d_ready {d[4]/ntile:9.0f}')
