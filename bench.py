@@ -194,7 +194,8 @@ def train_probe(dev, precision, n_patches=8):
         if fw == 'volsdf':
             m = make_volsdf(0.1, 0.0, device=dev).train()
             c2w, K = fx.closed_form_camera(H, W)
-            kw = dict(near=0.0, far=6.0, perturb=True, max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
+            kw = dict(near=0.0, far=6.0, perturb=True, max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE,
+                      train_stash=precision in ('tc', 'tc_mixed'))       # split training program, as Trainer.forward runs it
             patch = lambda ro, rd: pv.render_patch(m, ro, rd, **kw)
             pts = P
         else:

@@ -135,12 +135,15 @@ def main(args):
     eng.volsdf_render = timed_call('patch_fwd', orig_fwd)
     from nerfart_b200.models.frameworks import _finetune
     phases['style'] = []
+    style_host = []
     orig_style = _finetune.calc_style_loss
 
     def style_timed(*a, **k):                          # forward of the style losses; their backward runs inside losses.backward()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
         e0.record(); r = orig_style(*a, **k); e1.record()
         phases['style'].append((e0, e1, True))
+        style_host.append(1e3 * (time.perf_counter() - h0))
         return r
     _finetune.calc_style_loss = style_timed
 
@@ -207,6 +210,7 @@ def main(args):
                               'style_loss_forward': 1e3 * t_style,
                               'other (style backward, unpack, Adam, host)': 1e3 * (t / args.steps - t_p1 - t_pfwd - t_bwd - t_style)},
                 'style_ms_per_step': [round(a.elapsed_time(b), 2) for a, b, _ in phases['style']],
+                'style_host_ms_per_step': [round(v, 2) for v in style_host[-args.steps:]],
                 'e2e': {'value': n_rays * P * args.steps / t, 'unit': 'samples/s', 'ms_per_step': 1e3 * t / args.steps,
                         'h2d_bytes_per_step': 2 * 64 + n_rays * 12, 'd2h_bytes_per_step': 4,
                         'note': 'the step is timed through Trainer.forward with pinned-host camera / target image in and the loss out'},

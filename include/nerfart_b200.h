@@ -265,6 +265,24 @@ int na_volsdf_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrai
                          const float* nablas, const float* grad_rgb, void* grad_pack, double* scalars, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Split form of the VolSDF fine-tune patch (tensor-core modes; same results as na_volsdf_render_fwd + na_volsdf_render_bwd up to
+ * rounding order).  The reference renders the patch with grad and then back-propagates through the same graph
+ * (volsdf.py:760-783): one network evaluation per sample.  na_volsdf_render_fwd + na_volsdf_render_bwd evaluate the network twice
+ * (the backward launch re-evaluates the forward pass it differentiates).  Here the final full evaluation of the forward render is
+ * itself the forward half of the training program: it leaves the activations the backward needs in `train_workspace`
+ * (na_train_workspace_bytes_mode bytes for the same n_rays / points_per_ray / precision); na_volsdf_render_bwd_stashed, given the
+ * SAME workspace and the detailed outputs of that render, runs the backward half only.  `out` must carry d_vals, sdf, radiance and
+ * nablas.  NA_ERR_UNSUPPORTED for NA_PRECISION_FP32 / NA_PRECISION_TC2ACC.                                               */
+int na_volsdf_render_fwd_train(const NaNetDesc* desc, const void* packed, const NaVolsdfCfg* cfg, const float* rays_o,
+                               const float* rays_d, int64_t n_rays, const float* alpha_beta, const float* t_coarse,
+                               const float* t_init, const float* u_up, const float* u_imp, const float* u_final,
+                               const NaVolsdfOut* out, void* workspace, size_t workspace_bytes, void* train_workspace,
+                               size_t train_workspace_bytes, void* stream);
+int na_volsdf_render_bwd_stashed(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o,
+                                 const float* rays_d, int64_t n_rays, const float* alpha_beta, const float* d_all, const float* sdf,
+                                 const float* radiance, const float* nablas, const float* grad_rgb, void* grad_pack, double* scalars,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* NeuS: s = {forward_s()}; d_all / sdf [n,P], nablas [n,P,3] at the sample points, radiance [n,P-1,3] at the midpoints
  * (extras of neus.py:397-407).  scalars: [0] d loss / d ln_s, [1] eikonal loss.                                      */
 int na_neus_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o, const float* rays_d,

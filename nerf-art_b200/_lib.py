@@ -149,6 +149,9 @@ def lib():
         L.na_volsdf_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaVolsdfCfg), C.c_void_p, C.c_void_p,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(NaVolsdfOut), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.na_volsdf_render_fwd_train.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaVolsdfCfg), C.c_void_p, C.c_void_p,
+                                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.POINTER(NaVolsdfOut), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         if hasattr(L, 'na_neus_render_fwd'):
             L.na_neus_workspace_bytes.restype = C.c_size_t
             L.na_neus_workspace_bytes.argtypes = [C.POINTER(NaNeusCfg), C.c_int64]
@@ -168,7 +171,7 @@ def lib():
         L.na_debug_wgrad_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.na_train_workspace_bytes_mode.restype = C.c_size_t
         L.na_train_workspace_bytes_mode.argtypes = [C.POINTER(NaNetDesc), C.c_int64, C.c_int32, C.c_int32]
-        for fn in (L.na_volsdf_render_bwd, L.na_neus_render_bwd):
+        for fn in (L.na_volsdf_render_bwd, L.na_neus_render_bwd, L.na_volsdf_render_bwd_stashed):
             fn.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaTrainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_size_t, C.c_void_p]

@@ -223,6 +223,12 @@ struct EvalJob {
     const float* bw_gsdf;  const float* bw_gnab;  const float* bw_grad;
     unsigned short* st_emb;  unsigned short* st_vb0; // [st_mpad][64] (39 used): encoding (fwd format), v-bar_0 (bf16)
     float* st_t0;  float* st_t1;                     // [st_mpad][4] fp32: delta of the radiance output layer; masked d L / d sdf
+    // Split training program (csrc/train.cu): 0 = one launch does forward re-evaluation + backward (bw = 1), or a plain render (bw = 0);
+    // 1 = the patch's forward render IS the forward half: program 0..20 with the forward stash planes written, softplus' codes and
+    // ReLU masks persisted per TILE in tile_buf, the sphere-background flag left in st_t1[.][1] (bw = 0);
+    // 2 = backward half: program 21..40 only, reading tile_buf, st_t1 and the forward launch's radiance (`rad` is an INPUT) (bw = 1)
+    int bw_split;
+    unsigned char* tile_buf;                         // [n_tiles][TILE_BUF_BYTES] (csrc/mlp_tmem.cu), modes 1 / 2
 };
 
 // planes of EvalJob::st_wide a forward launch fills (the backward kernels of csrc/train.cu add theirs; see the enum there)

@@ -73,7 +73,7 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 
 enum BwOp { OP_FWD = 0, OP_DR, OP_FB, OP_HB, OP_SO, OP_TR };      // OP_FWD: forward program, dispatched on the program index
 struct Gemm { unsigned w_off; unsigned stage_bytes; unsigned char n_kb, prods, n64, img, op, lyr, pad0, pad1; float debias; };   // img: weight image (unscale index); debias: see launch_mlp_tmem
-struct Program { int n_gemm; int nsplit; int corr_first; Gemm g[MAX_GEMM]; };      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
+struct Program { int n_gemm; int g0; int nsplit; int corr_first; Gemm g[MAX_GEMM]; };      // g0: first GEMM run (21 in the backward-only launch)      // nsplit: N-parts (2 or 4) the last K-block of a GEMM is issued in
 // corr_first (product order of a three-product GEMM; the tensor core's fp32 accumulate truncates toward zero, so the error is a BIAS that
 // grows linearly with the number of accumulator updates made at full magnitude -- profiles/r3b_tc_accumulation.md):
 //   0  K-block-interleaved hi*hi, lo*hi, hi*lo (all 48 updates of a 256-deep layer at full magnitude)
@@ -200,6 +200,7 @@ constexpr size_t QP_BYTES = (size_t)8 * 32 * TM * 16;
 constexpr size_t GP_BYTES = 0;
 constexpr size_t MK_BYTES = (size_t)4 * EPI_THREADS * 8;
 constexpr size_t SCRATCH_BYTES = DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES + MK_BYTES;
+constexpr size_t TILE_BUF_BYTES = DH_BYTES + MK_BYTES;        // split training program: what the backward half needs from the forward half, per tile
 
 enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_RAD, K_RAD3,
                K_DR, K_FB, K_HB, K_SO, K_TR,                              // BW program only (K_DR: layer 0 too; K_SO: layers 3 and 7 too)
@@ -744,7 +745,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 for (int i = 0; i < 4; ++i) o[4 * j4 + i] = fmaxf(z[i], 0.f);
             }
             if (ST) stash16(c, ST_YS + c.g - 17, col0, o, 1.f / ACT_SCALE);
-            if (ST && c.bw) {
+            if (ST) {
                 unsigned long long m16 = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) m16 |= (unsigned long long)(o[j] > 0.f) << j;
@@ -767,7 +768,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         if (store) store_a16(t_d + col0, o, c.need_lo);
         NA_TRACE_E(c.trace, c.g, c16, 2);
         NA_TRACE_XS(14);
-        if (USES_DH && (c.lane & 15) == 0 && !(ST && c.bw)) {
+        if (USES_DH && (c.lane & 15) == 0 && !ST) {
             // the 16 lanes' codes of this pass share one line per column quad; they are dead now: keep them out of DRAM
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) discard_l2(dhp + (size_t)((col0 >> 2) + j4) * TM);
@@ -825,7 +826,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
         if (lane == 0) {
             unsigned it = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int g = 0; g < prog.n_gemm; ++g) {
+                for (int g = prog.g0; g < prog.n_gemm; ++g) {
                     const unsigned char* src = wimg + prog.g[g].w_off;
                     const unsigned sb = prog.g[g].stage_bytes;
                     const int n_kb = prog.g[g].n_kb, n_sp = prog.g[g].prods == 3 ? 2 : 1;
@@ -856,7 +857,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
         NA_CYC(long long t_a = 0; long long t_full = 0; const long long t_tot0 = clock64();)
         const unsigned wst = smem_u32(S.Wst);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int g = 0; g < prog.n_gemm; ++g) {
+            for (int g = prog.g0; g < prog.n_gemm; ++g) {
 #ifdef NA_TM_TRACE
                 long long* const tr = (job.dbg && blockIdx.x == 0 && tile == (long long)gridDim.x && lane == 0) ? job.dbg + 16 : nullptr;
 #endif
@@ -1065,6 +1066,12 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
 #ifdef NA_TM_TRACE
             c.trace = (job.dbg && blockIdx.x == 0 && tile == (long long)gridDim.x && tid == 64) ? job.dbg + 16 : nullptr;
 #endif
+            if (ST && job.bw_split != 0) {
+                // split training program: the softplus' codes and ReLU masks of a tile outlive the forward launch
+                unsigned char* tb = job.tile_buf + (size_t)tile * TILE_BUF_BYTES;
+                c.dh = reinterpret_cast<uint2*>(tb);
+                c.mk = reinterpret_cast<unsigned long long*>(tb + DH_BYTES) + (tid - 64);
+            }
             // ---- tile inputs: point, encoding (x ACT_SCALE, hi/lo) into K-block 0 of region 0 ---------------------
             {
                 const long long w = tile * TM + r;
@@ -1126,16 +1133,16 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         for (int cc = 0; cc < 3; ++cc) { S.BWV[cc * TM + r] = gn[cc] * c.rs; S.BWV[(3 + cc) * TM + r] = gr[cc] * c.rs; }
                         S.BWV[6 * TM + r] = gs;                                          // masked and scaled at the sdf head (g == 7)
                     }
-                    if (c.st_row && job.st_emb) {                                      // 64 columns: zero beyond the 39 entries
-                        uint4 lo, hi;
-                        pack16(e, 1.f / ACT_SCALE, lo, hi);
-                        uint4* erow = reinterpret_cast<uint4*>(job.st_emb + (size_t)w * ST_NLD + 16 * cq);
-                        __stcs(erow, lo); __stcs(erow + 1, hi);
-                    }
                 }
-                store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
+                if (ST && job.bw_split != 2 && c.st_row && job.st_emb) {               // 64 columns: zero beyond the 39 entries
+                    uint4 lo, hi;
+                    pack16(e, 1.f / ACT_SCALE, lo, hi);
+                    uint4* erow = reinterpret_cast<uint4*>(job.st_emb + (size_t)w * ST_NLD + 16 * cq);
+                    __stcs(erow, lo); __stcs(erow + 1, hi);
+                }
+                if (prog.g0 == 0) store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
             }
-            for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
+            if (prog.g0 == 0) { for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane); }
 #ifndef NA_NO_INPUT_BAR
             epi_bar_sync();                                   // EMBS / X / V / BWV of this tile: written above by other warps, read from GEMM 3 on
 #endif
@@ -1163,7 +1170,57 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
                 NA_TRACE_X(c.trace, 4);
             };
-            for (int g = 0; g < prog.n_gemm; ++g) {
+            // BW: A <- delta_3 = (delta_4 W4) * [ys_4 > 0] (K-blocks 0..3 of radiance-backward GEMM 21), over this thread's own (consumed)
+            // columns of D of GEMM 20; delta_4 (x rs) is in BWV[3..5]
+            auto delta3_stage = [&](unsigned t_region) {
+                epi_bar_sync();                                   // delta_4 of every row
+                const float d4[3] = {S.BWV[3 * TM + r], S.BWV[4 * TM + r], S.BWV[5 * TM + r]};
+                const unsigned long long m64 = c.mk[(size_t)3 * EPI_THREADS];
+#pragma unroll 1
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    const int col0 = c16 * 64 + cq * 16;
+                    float o[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 w0 = lds128(c.w4_s + (unsigned)(col0 + 4 * j4) * 4u), w1 = lds128(c.w4_s + (unsigned)(256 + col0 + 4 * j4) * 4u),
+                                     w2 = lds128(c.w4_s + (unsigned)(512 + col0 + 4 * j4) * 4u);
+                        o[4 * j4] = d4[0] * w0.x + d4[1] * w1.x + d4[2] * w2.x; o[4 * j4 + 1] = d4[0] * w0.y + d4[1] * w1.y + d4[2] * w2.y;
+                        o[4 * j4 + 2] = d4[0] * w0.z + d4[1] * w1.z + d4[2] * w2.z; o[4 * j4 + 3] = d4[0] * w0.w + d4[1] * w1.w + d4[2] * w2.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = ((m64 >> (16 * c16 + j)) & 1ull) ? o[j] * ACT_SCALE : 0.f;
+                    stash16(c, ST_D + 3, col0, o, c.irs * (1.f / ACT_SCALE));
+                    store_a16(t_region + col0, o, 0);               // GEMM 21 is a single-product GEMM: no lo words
+                    signal_kb(c.kb_bar, c16, lane);
+                }
+            };
+            if (BW && prog.g0 > 0) {
+                // ---- backward half of the split program: what the tails of GEMMs 7 and 20 do in the one-launch program, from the
+                // forward launch's outputs: the masked d L / d sdf (flag in st_t1[.][1]) and delta_4 = d L / d radiance * rgb (1 - rgb)
+                if (cq == 0) {
+                    const bool live = c.st_row != nullptr && S.OIDX[r] >= 0;
+                    float gs = S.BWV[6 * TM + r];
+                    if (c.st_row && job.st_t1) {
+                        float* t1 = job.st_t1 + (size_t)c.st_m * 4;
+                        if (job.bw_bg_mask && __ldcg(t1 + 1) != 0.f) gs = 0.f;
+                        *reinterpret_cast<float4*>(t1) = make_float4(gs, 0.f, 0.f, 0.f);
+                    }
+                    S.BWV[6 * TM + r] = gs * c.rs;
+                    if (live) {
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            const float rgb = __ldcg(job.rad + S.OIDX[r] * 3 + cc);
+                            S.BWV[(3 + cc) * TM + r] *= rgb * (1.f - rgb);
+                        }
+                    }
+                    if (c.st_row && job.st_t0)
+                        *reinterpret_cast<float4*>(job.st_t0 + (size_t)c.st_m * 4) =
+                            live ? make_float4(S.BWV[3 * TM + r] * c.irs, S.BWV[4 * TM + r] * c.irs, S.BWV[5 * TM + r] * c.irs, 0.f)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                delta3_stage(c.t_lane + (unsigned)(prog.g0 & 1) * 256u);         // (its leading barrier also publishes BWV[6])
+            }
+            for (int g = prog.g0; g < prog.n_gemm; ++g) {
                 const int op = BW ? (int)prog.g[g].op : (int)OP_FWD;
                 c.g = g; c.us = unscale[prog.g[g].img];          // us = 2^-(weight shift) / ACT_SCALE
                 c.us *= prog.g[g].debias;
@@ -1251,6 +1308,13 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     epi_bar_sync();
                     if (cq == 0) {
                         float sdf = S.PART[r] + S.PART[TM + r] + S.PART[2 * TM + r] + S.PART[3 * TM + r] + __ldg(pk + L.b8_sdf);
+                        if (ST && !BW && job.bw_split == 1 && c.st_row && job.st_t1) {
+                            // forward half of the split program: leave the sphere-background flag (volsdf.py:349-357: where
+                            // R - |x| < sdf the network's sdf is not the output) for the backward half, next to its d L / d sdf slot
+                            const float x0 = S.X[r], x1 = S.X[TM + r], x2 = S.X[2 * TM + r];
+                            const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+                            *reinterpret_cast<float4*>(job.st_t1 + (size_t)c.st_m * 4) = make_float4(0.f, (job.bound_r - nrm < sdf) ? 1.f : 0.f, 0.f, 0.f);
+                        }
                         if (job.apply_bg) {
                             const float x0 = S.X[r], x1 = S.X[TM + r], x2 = S.X[2 * TM + r];
                             const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
@@ -1359,29 +1423,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         // padding row of the last tile: the weight-gradient kernels read whole tiles, its delta_4 is zero
                         *reinterpret_cast<float4*>(job.st_t0 + (size_t)c.st_m * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    if (BW && g + 1 < prog.n_gemm) {
-                        epi_bar_sync();                                   // delta_4 of every row
-                        // A <- delta_3 = (delta_4 W4) * [ys_4 > 0], over this thread's own (consumed) columns of D of GEMM 20
-                        const float d4[3] = {S.BWV[3 * TM + r], S.BWV[4 * TM + r], S.BWV[5 * TM + r]};
-                        const unsigned long long m64 = c.mk[(size_t)3 * EPI_THREADS];
-#pragma unroll 1
-                        for (int c16 = 0; c16 < 4; ++c16) {
-                            const int col0 = c16 * 64 + cq * 16;
-                            float o[16];
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 w0 = lds128(c.w4_s + (unsigned)(col0 + 4 * j4) * 4u), w1 = lds128(c.w4_s + (unsigned)(256 + col0 + 4 * j4) * 4u),
-                                             w2 = lds128(c.w4_s + (unsigned)(512 + col0 + 4 * j4) * 4u);
-                                o[4 * j4] = d4[0] * w0.x + d4[1] * w1.x + d4[2] * w2.x; o[4 * j4 + 1] = d4[0] * w0.y + d4[1] * w1.y + d4[2] * w2.y;
-                                o[4 * j4 + 2] = d4[0] * w0.z + d4[1] * w1.z + d4[2] * w2.z; o[4 * j4 + 3] = d4[0] * w0.w + d4[1] * w1.w + d4[2] * w2.w;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] = ((m64 >> (16 * c16 + j)) & 1ull) ? o[j] * ACT_SCALE : 0.f;
-                            stash16(c, ST_D + 3, col0, o, c.irs * (1.f / ACT_SCALE));
-                            store_a16(t_dd + col0, o, c.need_lo);
-                            signal_kb(c.kb_bar, c16, lane);
-                        }
-                    }
+                    if (BW && g + 1 < prog.n_gemm) delta3_stage(t_dd);
                 }
                 if (g + 1 >= prog.n_gemm) {
                     tc_fence_before();
@@ -1489,6 +1531,7 @@ int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, cons
 }
 
 size_t mlp_tmem_scratch_bytes(int grid) { return (size_t)grid * tm::SCRATCH_BYTES; }
+size_t mlp_tmem_tile_buf_bytes(long long n_samples) { return (size_t)((n_samples + tm::TM - 1) / tm::TM) * tm::TILE_BUF_BYTES; }
 
 extern long long* g_tc_dbg;
 
@@ -1505,11 +1548,12 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;
     const ImageLayout T = image_layout();
-    Program prog; prog.n_gemm = 0;
+    Program prog; prog.n_gemm = 0; prog.g0 = 0;
     static const char* nsplit_env = getenv("NA_TM_NSPLIT");                   // diagnostics: "2" = N-halves (the r1n scheme), default quarters
     prog.nsplit = (nsplit_env && nsplit_env[0] == '2') ? 2 : 4;
     // NA_TM_ORDER=0: K-block-interleaved products (the r2 scheme).  NA_TM_DEBIAS=<x>: experimental multiplicative compensation of the
@@ -1549,6 +1593,13 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
         }
         for (int l = 0; l < 8; ++l) add(l, OP_SO, l);                     // second-order sweep
         for (int l = 6; l >= 0; --l) add(15 - l, OP_TR, l);               // trunk: z-bar_l from z-bar_{l+1} W_{l+1}
+        if (job.bw_split == 2) {
+            // backward half of the split program: the forward launch (bw_split == 1) left the stash planes, tile_buf and rad
+            if (!job.rad || !job.tile_buf || !job.st_t1) return NA_ERR_BAD_ARG;
+            prog.g0 = 21;
+        } else if (job.bw_split != 0) return NA_ERR_BAD_ARG;
+    } else if (job.bw_split != 0) {
+        if (job.bw_split != 1 || !job.st_wide || !job.tile_buf || !job.want_full || !job.rad || !STASH) return NA_ERR_BAD_ARG;
     }
     long long tiles = (total + TM - 1) / TM;
     int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
@@ -1557,7 +1608,9 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     if (job.st_wide && !job.want_full) return NA_ERR_BAD_ARG;
     const SpinCtx sc = diag_next(DK_MLP_TMEM, grid);
     if (job.bw)             mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
-    else if (job.st_wide)   return NA_ERR_UNSUPPORTED;               // the stash is written by the BW program only
+    else if (job.st_wide && job.bw_split == 1)
+                            mlp_tmem_kernel<true, true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else if (job.st_wide)   return NA_ERR_UNSUPPORTED;               // the stash is written by the training programs only
     else if (job.want_full) mlp_tmem_kernel<true, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     else                    mlp_tmem_kernel<false, false, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     NA_CHECK_LAUNCH();
@@ -1568,6 +1621,7 @@ int preload_mlp_tmem() {
     NA_PRELOAD((tm::mlp_tmem_kernel<false, false, false>));
     NA_PRELOAD((tm::mlp_tmem_kernel<true, false, false>));
     NA_PRELOAD((tm::mlp_tmem_kernel<true, true, true>));
+    NA_PRELOAD((tm::mlp_tmem_kernel<true, true, false>));
     NA_PRELOAD(tm::pack_kernel);
     NA_PRELOAD(tm::absmax_kernel);
     return NA_OK;

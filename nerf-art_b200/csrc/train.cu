@@ -1191,8 +1191,11 @@ __global__ void normalize_dirs_train_kernel(const float* __restrict__ d, float* 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float a = d[i * 3], b = d[i * 3 + 1], c = d[i * 3 + 2];
-    const float nrm = fmaxf(sqrtf(a * a + b * b + c * c), 1e-12f);               // F.normalize, volsdf.py:442
-    out[i * 3] = a / nrm; out[i * 3 + 1] = b / nrm; out[i * 3 + 2] = c / nrm;
+    // F.normalize, volsdf.py:442 -- the same un-fused operations as the forward render's normalize_dirs_kernel (csrc/volsdf_render.cu):
+    // the re-evaluated sample positions are then bit-identical to the render's (a contracted a*a + b*b + c*c differs in the last bit,
+    // which moves ReLU / softplus' decisions of a few samples)
+    const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c))), 1e-12f);
+    out[i * 3] = __fdiv_rn(a, nrm); out[i * 3 + 1] = __fdiv_rn(b, nrm); out[i * 3 + 2] = __fdiv_rn(c, nrm);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1207,8 +1210,10 @@ struct TrainWs {
     float* stash; float* scratch;                                                   // fp32 mode
     unsigned short* wide16; unsigned short* narrow16; float* tiny; size_t mpad;     // tensor-core modes
     float* f_sdf; float* f_rad; float* fwd_scratch; size_t fwd_scratch_bytes;
+    unsigned char* tile_buf;                                                        // split program: per-tile softplus' codes + ReLU masks
     size_t total;
 };
+size_t mlp_tmem_tile_buf_bytes(long long n_samples);                                // csrc/mlp_tmem.cu
 size_t mlp_scratch_bytes();                                                         // csrc/api.cu
 int launch_wgrad_f16(const WgF16Task* tasks, int n_tasks, const unsigned short* wide, int n_wide_planes, const unsigned short* narrow,
                      int n_narrow_planes, long long mpad, long long m_rows, cudaStream_t stream);       // csrc/wgrad_f16.cu
@@ -1235,6 +1240,7 @@ static TrainWs train_ws(void* base, long long n_rays, int P, bool tc) {
         w.tiny = take((size_t)2 * mpad * 4 * 4);
         w.f_sdf = take(M * 4); w.f_rad = take(M * 12);
         w.fwd_scratch_bytes = mlp_scratch_bytes(); w.fwd_scratch = take(w.fwd_scratch_bytes);
+        w.tile_buf = (unsigned char*)take(mlp_tmem_tile_buf_bytes((long long)M));
     } else {
         w.stash = take(stash_floats(mpad) * 4);
         w.scratch = take((size_t)num_sms() * 16 * 256 * TM * 4);
@@ -1269,8 +1275,36 @@ static int launch_mlp_bwd(const BwdJob& job, const float* pk, const PackF32& L, 
 // Tensor-core modes: ONE tcgen05 launch per patch (BW program of csrc/mlp_tmem.cu: forward re-evaluation with three-product operands,
 // then the 20 backward-data GEMMs), which leaves every (delta, input) pair in the bf16 stash; then the weight gradients
 // (csrc/wgrad_f16.cu).
+// stash planes / tables of the training workspace -> the fields of an EvalJob
+static int attach_stash(EvalJob& e, const TrainWs& w) {
+    const size_t mpad = w.mpad;
+    unsigned short* nar = w.narrow16;
+    e.st_wide = w.wide16; e.st_mpad = mpad;
+    NA_TRY(make_stash_store_map(&e.st_store_map, w.wide16, N_WIDE, (long long)mpad));
+    e.st_emb = nar + (size_t)NP_EMB * mpad * ST_NLD; e.st_vb0 = nar + (size_t)NP_VB0 * mpad * ST_NLD; e.st_small = nar + (size_t)NP_SMALL * mpad * ST_NLD;
+    e.st_t0 = w.tiny; e.st_t1 = w.tiny + mpad * 4;
+    e.tile_buf = w.tile_buf;
+    return NA_OK;
+}
+
+// Forward half of the split training program: the final full evaluation of the patch's forward render (csrc/volsdf_render.cu), run
+// as program 0..20 with the forward stash planes written and the softplus' codes / ReLU masks persisted per tile.  `fj` is the
+// render's own job (its sdf / radiance / nabla outputs, apply_bg); the backward half is na_volsdf_render_bwd_stashed.
+int train_forward_stash(const EvalJob& fj, const void* packed, int precision, void* train_workspace, size_t train_ws_bytes,
+                        float* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    if (precision != NA_PRECISION_TC && precision != NA_PRECISION_TC_MIXED) return NA_ERR_UNSUPPORTED;
+    if (!train_workspace || fj.x || !fj.rad || !fj.want_full || fj.row_ids || fj.n_rows_dev) return NA_ERR_BAD_ARG;
+    const TrainWs w = train_ws(train_workspace, fj.n_rows, fj.P, true);
+    if (train_ws_bytes < w.total) return NA_ERR_WORKSPACE;
+    EvalJob e = fj;
+    NA_TRY(attach_stash(e, w));
+    e.bw = 0; e.bw_split = 1;
+    return launch_mlp(e, packed, precision, scratch, scratch_bytes, stream);
+}
+
+// split != 0: the forward half already ran (train_forward_stash); job.f_rad = its radiance output
 static int tc_backward(const BwdJob& job, const void* packed, int precision, const TrainWs& w, int train_surface, int train_radiance,
-                       float* gp, cudaStream_t stream) {
+                       float* gp, cudaStream_t stream, int split = 0) {
     const int fwd_bf16 = 1;
     const long long M = (long long)job.n_rows * job.P;
     if (M <= 0) return NA_OK;
@@ -1281,14 +1315,13 @@ static int tc_backward(const BwdJob& job, const void* packed, int precision, con
     e.rays_o = job.rays_o; e.rays_d = job.rays_d; e.n_rows = job.n_rows; e.P = job.P;
     e.t = job.t; e.t_stride = job.t_stride; e.t_off = 0; e.midpoints = job.midpoints;
     e.o_stride = job.P; e.o_off = 0;
-    e.sdf = w.f_sdf; e.rad = job.has_rad ? w.f_rad : nullptr;
+    e.sdf = split ? nullptr : w.f_sdf;
+    e.rad = split ? const_cast<float*>(job.f_rad) : (job.has_rad ? w.f_rad : nullptr);        // split: the forward launch's radiance, an input
     e.apply_bg = 0;                                   // raw network sdf: the background mask compares it with R - |x| itself
     e.bound_r = job.bound_r; e.want_full = 1; e.multires_view = job.multires_view;
-    e.st_wide = w.wide16; e.st_mpad = mpad;
-    NA_TRY(make_stash_store_map(&e.st_store_map, w.wide16, N_WIDE, (long long)mpad));
-    e.st_emb = nar + (size_t)NP_EMB * mpad * ST_NLD; e.st_vb0 = nar + (size_t)NP_VB0 * mpad * ST_NLD; e.st_small = nar + (size_t)NP_SMALL * mpad * ST_NLD;
-    e.st_t0 = w.tiny; e.st_t1 = w.tiny + mpad * 4;
-    e.bw = 1; e.bw_bg_mask = job.apply_bg;
+    NA_TRY(attach_stash(e, w));
+    e.bw = 1; e.bw_bg_mask = job.apply_bg; e.bw_split = split ? 2 : 0;
+    if (split && (!job.has_rad || !job.f_rad)) return NA_ERR_BAD_ARG;
     e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
     // the forward re-evaluation runs in the render's own mode: in tc_mixed the SDF forward pass (what softplus' and the activations come
     // from) keeps its three-product operands, the feature head / reverse sweep / radiance layers use single products exactly as in the
@@ -1421,13 +1454,15 @@ extern "C" size_t na_train_workspace_bytes(const NaNetDesc* desc, int64_t n_rays
 
 static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o, const float* rays_d,
                       int64_t n, const float* scal, const float* d_all, const float* sdf, const float* rad, const float* nab,
-                      const float* grad_rgb, float* gp, double* accum, void* ws_, size_t ws_bytes, cudaStream_t stream, bool neus) {
+                      const float* grad_rgb, float* gp, double* accum, void* ws_, size_t ws_bytes, cudaStream_t stream, bool neus,
+                      bool stashed = false) {
     if (!desc || !packed || !cfg || !rays_o || !rays_d || !scal || !d_all || !sdf || !rad || !nab || !grad_rgb || !gp || !accum || !ws_)
         return NA_ERR_BAD_ARG;
     if (n <= 0) return NA_OK;
     const int P = cfg->points_per_ray;
     if (P < 2 || n * (int64_t)P > 0x7fffffffLL) return NA_ERR_UNSUPPORTED;
     const bool tc = bwd_on_tensor_cores(cfg->precision);
+    if (stashed && (!tc || neus || (cfg->precision != NA_PRECISION_TC && cfg->precision != NA_PRECISION_TC_MIXED))) return NA_ERR_UNSUPPORTED;
     const TrainWs w = train_ws(ws_, n, P, tc);
     if (ws_bytes < w.total) return NA_ERR_WORKSPACE;
     const PackF32 L = pack_layout_f32(desc->multires_view);
@@ -1446,7 +1481,7 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     const size_t M = (size_t)n * P, mpad = (M + TM - 1) / TM * TM;
     Stash st; st.mpad = mpad; st.wide = w.stash; st.narrow = w.stash + (size_t)N_WIDE * mpad * 256; st.tiny = st.narrow + 3 * mpad * NLD;      // fp32 mode only
     auto backward = [&](const BwdJob& j, long long rows, int ts, int tr) -> int {
-        if (tc) return tc_backward(j, packed, cfg->precision, w, ts, tr, gp, stream);
+        if (tc) return tc_backward(j, packed, cfg->precision, w, ts, tr, gp, stream, stashed ? 1 : 0);
         NA_TRY(launch_mlp_bwd(j, pk, L, tp, T, st, w, stream));
         return launch_wgrad(st, rows, j.has_rad, ts, tr, gp, stream);
     };
@@ -1456,7 +1491,7 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     const bool has_eik = cfg->w_eikonal != 0.f;
     if (!neus) {
         job.P = P; job.midpoints = 0; job.g_sdf = w.g_sdf; job.g_nab = has_eik ? w.g_nab : nullptr; job.g_rad = w.g_rad;
-        job.apply_bg = 1; job.has_rad = 1;
+        job.apply_bg = 1; job.has_rad = 1; job.f_rad = rad;
         NA_TRY(backward(job, (long long)M, cfg->train_surface, cfg->train_radiance));
     } else {
         // pass A: the P points of d_all (sdf -> alpha, nabla -> eikonal); pass B: the P-1 midpoints (radiance), neus.py:320-324
@@ -1480,6 +1515,17 @@ extern "C" int na_volsdf_render_bwd(const NaNetDesc* desc, const void* packed, c
     if (desc && desc->framework != NA_FRAMEWORK_VOLSDF) return NA_ERR_BAD_ARG;
     return render_bwd(desc, packed, cfg, rays_o, rays_d, n_rays, alpha_beta, d_all, sdf, radiance, nablas, grad_rgb, (float*)grad_pack,
                       scalars, workspace, workspace_bytes, (cudaStream_t)stream, false);
+}
+
+// Backward half of the split training program: `workspace` is the training workspace the forward render of the SAME rays filled
+// (na_volsdf_render_fwd_train); sdf / radiance / nablas / d_all are that render's detailed outputs.
+extern "C" int na_volsdf_render_bwd_stashed(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o,
+                                            const float* rays_d, int64_t n_rays, const float* alpha_beta, const float* d_all, const float* sdf,
+                                            const float* radiance, const float* nablas, const float* grad_rgb, void* grad_pack,
+                                            double* scalars, void* workspace, size_t workspace_bytes, void* stream) {
+    if (desc && desc->framework != NA_FRAMEWORK_VOLSDF) return NA_ERR_BAD_ARG;
+    return render_bwd(desc, packed, cfg, rays_o, rays_d, n_rays, alpha_beta, d_all, sdf, radiance, nablas, grad_rgb, (float*)grad_pack,
+                      scalars, workspace, workspace_bytes, (cudaStream_t)stream, false, true);
 }
 
 extern "C" int na_neus_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o,

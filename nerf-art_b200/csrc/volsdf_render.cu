@@ -293,10 +293,18 @@ extern "C" size_t na_volsdf_workspace_bytes(const NaVolsdfCfg* cfg, int64_t n_ra
     return volsdf_ws_layout(*cfg, n_rays).total;
 }
 
-extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, const NaVolsdfCfg* cfg,
-                                    const float* rays_o, const float* rays_d, int64_t n_rays, const float* alpha_beta,
-                                    const float* t_coarse, const float* t_init, const float* u_up, const float* u_imp,
-                                    const float* u_final, const NaVolsdfOut* out, void* workspace, size_t ws_bytes, void* stream_) {
+namespace na {
+int train_forward_stash(const EvalJob& fj, const void* packed, int precision, void* train_workspace, size_t train_ws_bytes,
+                        float* scratch, size_t scratch_bytes, cudaStream_t stream);                     // csrc/train.cu
+}
+
+// train_ws != nullptr: the final full evaluation is the forward half of the split training program (it also fills the training
+// workspace with the forward stash; csrc/train.cu)
+static int volsdf_render_fwd(const NaNetDesc* desc, const void* packed, const NaVolsdfCfg* cfg,
+                             const float* rays_o, const float* rays_d, int64_t n_rays, const float* alpha_beta,
+                             const float* t_coarse, const float* t_init, const float* u_up, const float* u_imp,
+                             const float* u_final, const NaVolsdfOut* out, void* workspace, size_t ws_bytes, void* train_ws,
+                             size_t train_ws_bytes, void* stream_) {
     if (!desc || !packed || !cfg || !rays_o || !rays_d || !alpha_beta || !t_coarse || !t_init || !u_up || !u_imp || !out || !workspace)
         return NA_ERR_BAD_ARG;
     if (n_rays <= 0) return NA_ERR_BAD_ARG;
@@ -375,7 +383,8 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
         fj.rays_o = rays_o; fj.rays_d = dirs; fj.n_rows = (int)n_rays; fj.P = P; fj.t = d_all; fj.t_stride = P; fj.t_off = 0;
         fj.o_stride = P; fj.o_off = 0; fj.sdf = sdf_f; fj.rad = rad_f; fj.nab = nab_f;
         fj.apply_bg = 1; fj.bound_r = desc->bounding_radius; fj.want_full = 1; fj.multires_view = desc->multires_view;
-        NA_TRY(launch_mlp(fj, packed, cfg->precision, scratch, scratch_bytes, stream));
+        if (train_ws) NA_TRY(train_forward_stash(fj, packed, cfg->precision, train_ws, train_ws_bytes, scratch, scratch_bytes, stream));
+        else          NA_TRY(launch_mlp(fj, packed, cfg->precision, scratch, scratch_bytes, stream));
         CompositeArgs ca = {};
         ca.d_all = d_all; ca.sdf = sdf_f; ca.rad = rad_f; ca.nab = out->normals ? nab_f : nullptr; ca.alpha_beta = alpha_beta;
         ca.P = P; ca.white_bkgd = cfg->white_bkgd; ca.n_rays = n_rays;
@@ -386,4 +395,22 @@ extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, c
         NA_CHECK_LAUNCH();
     }
     return NA_OK;
+}
+
+extern "C" int na_volsdf_render_fwd(const NaNetDesc* desc, const void* packed, const NaVolsdfCfg* cfg,
+                                    const float* rays_o, const float* rays_d, int64_t n_rays, const float* alpha_beta,
+                                    const float* t_coarse, const float* t_init, const float* u_up, const float* u_imp,
+                                    const float* u_final, const NaVolsdfOut* out, void* workspace, size_t ws_bytes, void* stream_) {
+    return volsdf_render_fwd(desc, packed, cfg, rays_o, rays_d, n_rays, alpha_beta, t_coarse, t_init, u_up, u_imp, u_final, out, workspace,
+                             ws_bytes, nullptr, 0, stream_);
+}
+
+extern "C" int na_volsdf_render_fwd_train(const NaNetDesc* desc, const void* packed, const NaVolsdfCfg* cfg,
+                                          const float* rays_o, const float* rays_d, int64_t n_rays, const float* alpha_beta,
+                                          const float* t_coarse, const float* t_init, const float* u_up, const float* u_imp,
+                                          const float* u_final, const NaVolsdfOut* out, void* workspace, size_t ws_bytes,
+                                          void* train_workspace, size_t train_ws_bytes, void* stream_) {
+    if (!train_workspace || !out || !out->d_vals || !out->sdf || !out->radiance || !out->nablas) return NA_ERR_BAD_ARG;   // detailed outputs: the backward reads them
+    return volsdf_render_fwd(desc, packed, cfg, rays_o, rays_d, n_rays, alpha_beta, t_coarse, t_init, u_up, u_imp, u_final, out, workspace,
+                             ws_bytes, train_workspace, train_ws_bytes, stream_);
 }

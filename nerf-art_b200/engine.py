@@ -140,8 +140,10 @@ class NetEngine:
 
     # ------------------------------------------------------------------------------------------
     def volsdf_render(self, rays_o, rays_d, alpha_beta, *, near, far, N_samples, N_importance, max_upsample_steps,
-                      max_bisection_steps, epsilon, white_bkgd, perturb, calc_normal, detailed_output, u_final=None):
-        """rays [N,3] (un-normalised directions) -> dict of flat outputs.  volsdf.volume_render, volsdf.py:389-615."""
+                      max_bisection_steps, epsilon, white_bkgd, perturb, calc_normal, detailed_output, u_final=None, train_stash=False):
+        """rays [N,3] (un-normalised directions) -> dict of flat outputs.  volsdf.volume_render, volsdf.py:389-615.
+        train_stash (tensor-core modes, detailed_output): the final full evaluation also is the forward half of the training program
+        (na_volsdf_render_fwd_train): `render_bwd` on the returned outputs then runs the backward half only."""
         L = _lib.lib()
         dev = rays_o.device
         n = rays_o.shape[0]
@@ -164,12 +166,34 @@ class NetEngine:
         ws = self.workspace(L.na_volsdf_workspace_bytes(C.byref(cfg), n))
         tc, ti = cpu_linspace(N_samples, dev), cpu_linspace(4 * N_samples, dev)
         uu, ui = cpu_linspace(4 * N_samples + 2, dev), cpu_linspace(N_importance, dev)
+        self._stash_key = None
+        if train_stash:
+            if not detailed_output or self.precision not in ('tc', 'tc_mixed'):
+                raise RuntimeError("train_stash needs detailed_output and precision 'tc' / 'tc_mixed'")
+            tws = self._train_workspace(n, P, dev)
         with torch.cuda.device(dev):
-            check(L.na_volsdf_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
-                                         ptr(alpha_beta), ptr(tc), ptr(ti), ptr(uu), ptr(ui),
-                                         ptr(u_final.contiguous()) if u_final is not None else None,
-                                         C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_volsdf_render_fwd')
+            if train_stash:
+                check(L.na_volsdf_render_fwd_train(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
+                                                   ptr(alpha_beta), ptr(tc), ptr(ti), ptr(uu), ptr(ui),
+                                                   ptr(u_final.contiguous()) if u_final is not None else None,
+                                                   C.byref(out), ptr(ws), ws.numel(), ptr(tws), tws.numel(), stream_ptr(dev)),
+                      'na_volsdf_render_fwd_train')
+                # what the stash belongs to: the backward half is only valid for these outputs, these weights and this precision
+                self._stash_key = (n, P, o['d_vals'].data_ptr(), o['radiance'].data_ptr(), self.precision, self._pack_key)
+            else:
+                check(L.na_volsdf_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
+                                             ptr(alpha_beta), ptr(tc), ptr(ti), ptr(uu), ptr(ui),
+                                             ptr(u_final.contiguous()) if u_final is not None else None,
+                                             C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_volsdf_render_fwd')
         return o
+
+    def _train_workspace(self, n, P, dev):
+        L = _lib.lib()
+        nbytes = L.na_train_workspace_bytes_mode(C.byref(self.desc), n, P, PRECISIONS[self.precision])
+        if getattr(self, '_tws', None) is None or self._tws.device != dev or self._tws.numel() < nbytes:
+            self._tws = None
+            self._tws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        return self._tws
 
     def neus_render(self, rays_o, rays_d, s_dev, *, obj_bounding_radius, N_samples, N_importance, N_upsample_iters,
                     white_bkgd, perturb, detailed_output, u_rand=None):
@@ -227,12 +251,13 @@ class NetEngine:
         P = d_all.shape[-1]
         cfg = NaTrainCfg(int(P), float(w_eikonal), int(eikonal_count), int(bool(white_bkgd)), float(speed_factor),
                          int(bool(train_surface)), int(bool(train_radiance)), PRECISIONS[self.precision])
-        nbytes = L.na_train_workspace_bytes_mode(C.byref(self.desc), n, P, PRECISIONS[self.precision])
-        if getattr(self, '_tws', None) is None or self._tws.device != dev or self._tws.numel() < nbytes:
-            self._tws = None
-            self._tws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        # the forward render of exactly these outputs left its stash in the workspace (volsdf_render(train_stash=True)): backward half only
+        stashed = (not neus) and getattr(self, '_stash_key', None) is not None and \
+            self._stash_key == (n, P, d_all.data_ptr(), fwd['radiance'].data_ptr(), self.precision, self._pack_key)
+        self._stash_key = None
+        self._train_workspace(n, P, dev)
         g = grad_rgb.reshape(-1, 3).float().contiguous()
-        fn = L.na_neus_render_bwd if neus else L.na_volsdf_render_bwd
+        fn = L.na_neus_render_bwd if neus else (L.na_volsdf_render_bwd_stashed if stashed else L.na_volsdf_render_bwd)
         with torch.cuda.device(dev):
             check(fn(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n, ptr(scal), ptr(d_all),
                      ptr(fwd['sdf']), ptr(fwd['radiance']), ptr(fwd['nablas']), ptr(g), ptr(self._gpack),

@@ -130,15 +130,18 @@ class SingleRenderer(nn.Module):
 
 
 def render_patch(model: VolSDF, ro, rd, near=0.0, far=6.0, perturb=False, white_bkgd=False, max_upsample_steps=5, N_samples=128,
-                 N_importance=64, max_bisection_steps=10, epsilon=0.1, u_final=None, **dummy_kwargs):
+                 N_importance=64, max_bisection_steps=10, epsilon=0.1, u_final=None, train_stash=False, **dummy_kwargs):
     """Forward render of one flat ray patch with the detailed per-sample outputs the backward needs (volume_render's
-    defaults, volsdf.py:389-424).  Returns (flat outputs, {alpha, beta} on the device)."""
+    defaults, volsdf.py:389-424).  Returns (flat outputs, {alpha, beta} on the device).
+    train_stash: this render is the forward half of the training program (NetEngine.volsdf_render): the reference renders the patch
+    with grad and back-propagates through that one evaluation (volsdf.py:760-783); `engine.render_bwd` on these outputs then runs the
+    backward half only instead of re-evaluating the networks."""
     alpha, beta = model.forward_ab()
     ab = torch.cat([alpha.detach().reshape(1), beta.detach().reshape(1)]).float().contiguous()
     o = model.engine().volsdf_render(ro, rd, ab, near=near, far=far, N_samples=N_samples, N_importance=N_importance,
                                      max_upsample_steps=max_upsample_steps, max_bisection_steps=max_bisection_steps,
                                      epsilon=epsilon, white_bkgd=white_bkgd, perturb=perturb, calc_normal=False,
-                                     detailed_output=True, u_final=u_final)
+                                     detailed_output=True, u_final=u_final, train_stash=train_stash)
     return o, ab
 
 

@@ -359,3 +359,50 @@ def test_wgrad_f16_kernel_vs_torch(l_bf16, r_bf16, m_rows):
     berr = float((bias.double() - bref).abs().max() / (bref.abs().max() + 1e-30))
     print(f'wgrad_f16 m={m_rows} fmt=({l_bf16},{r_bf16}): rel err {err:.2e}, bias {berr:.2e}')
     assert err < 2e-5 and berr < 2e-5                                   # products are exact in fp32; only the summation order differs
+
+
+@pytest.mark.parametrize('precision,white,w_eik', [('tc_mixed', False, 0.1), ('tc', True, 0.0), ('tc_mixed', True, 0.1)])
+def test_split_training_program_equals_the_one_launch_program(precision, white, w_eik):
+    """na_volsdf_render_fwd_train + na_volsdf_render_bwd_stashed (the patch's forward render IS the forward half of the training
+    program, the backward launch runs GEMMs 21..40 only) against na_volsdf_render_fwd + na_volsdf_render_bwd (the backward launch
+    re-evaluates the forward pass): same forward outputs bit for bit, same gradients up to the order of the atomic sums.
+    Several tiles, a ragged last tile (523 rays x 48 samples = 196.1 tiles) and the sphere-background override on part of the rays."""
+    from nerfart_b200.models.frameworks.volsdf import render_patch
+    from nerfart_b200.utils import rend_util
+    m = make_volsdf(0.1, 0.5, device=DEV).train()
+    eng = m.engine(); eng.precision = precision
+    H, W = 24, 24
+    c2w, K = fx.tilted_camera(H, W)
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(DEV), K[None].to(DEV), H, W)
+    n = 523
+    ro, rd = ro[0, :n].contiguous(), rd[0, :n].contiguous()
+    g = torch.Generator(device=DEV); g.manual_seed(11)
+    G = 1e-2 * torch.randn(n, 3, device=DEV, generator=g)
+    kw = dict(near=0.0, far=6.0, N_samples=32, N_importance=16, max_upsample_steps=6, perturb=False, white_bkgd=white)
+    res = []
+    for stash in (False, True):
+        fwd, ab = render_patch(m, ro, rd, train_stash=stash, **kw)
+        assert (eng._stash_key is not None) == stash
+        eng.grad_zero()
+        eng.render_bwd(ro, rd, ab, fwd, G, w_eikonal=w_eik, eikonal_count=n * 48, white_bkgd=white, speed_factor=m.speed_factor)
+        assert eng._stash_key is None                                  # a stash is consumed by the backward of ITS render only
+        pairs, scal = eng.unpack_grads()
+        torch.cuda.synchronize()
+        res.append((fwd, [(p, gr.clone()) for p, gr in pairs], scal.clone()))
+    (f0, p0, s0), (f1, p1, s1) = res
+    for k in ('rgb', 'd_vals', 'sdf', 'radiance', 'nablas'):
+        assert torch.equal(f0[k], f1[k]), k
+    names = {id(p): k for k, p in m.named_parameters()}
+    worst = 0.0
+    for (pa, ga), (pb, gb) in zip(p0, p1):
+        assert pa is pb
+        e = float((ga - gb).abs().max() / (ga.abs().max() + 1e-30))
+        worst = max(worst, e)
+        assert e < 2e-3, (names[id(pa)], e)
+    print(f'split vs one-launch training program [{precision}, white={white}, eik={w_eik}]: worst gradient difference {worst:.2e} of the tensor scale')
+    assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-12)
+    # a render without the stash in between invalidates it: the backward falls back to the one-launch program
+    fwd, ab = render_patch(m, ro, rd, train_stash=True, **kw)
+    render_patch(m, ro[:50].contiguous(), rd[:50].contiguous(), **kw)
+    assert eng._stash_key is None
