@@ -473,6 +473,20 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) qn[j4] = dhp[(size_t)(c.cq * 4 + j4) * TM];
     }
+    // BW (second-order sweep, trunk): the softplus' codes run one pass ahead in registers.  In the backward-only launch D is ready
+    // whenever the epilogue asks (the GEMMs are epilogue-bound), so a load issued at the top of its own pass is fully exposed: 55 % of
+    // the kernel's stall samples were long-scoreboard waits on these codes (profiles/r4b_split_program.md).  Pass c+1's codes are
+    // requested right after pass c's tcgen05.ld: kernel 2.26 -> 2.12 ms per patch.  (Carrying pass 0's codes across the GEMM boundary
+    // as well costs eight more live registers through the tails: 400 B of spills and 3.1 ms; the parked terms one pass ahead: no change;
+    // the g-plane rows one pass ahead: spills, 2.63 ms -- all measured (profiles/r4b_split_program.md), none kept.)
+    constexpr bool PRE_S = KIND == K_SO || KIND == K_TR;
+    constexpr bool PRE_G = KIND == K_SO;
+    uint2 sn[4];
+    if (PRE_S) {
+        const uint2* p = c.dh + (size_t)(c.lyr * 64 + c.cq * 4) * TM + r;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) sn[j4] = p[(size_t)j4 * TM];
+    }
 #pragma unroll 1
     for (int c16 = 0; c16 < N_PASS; ++c16) {
         // thread = (row, column quarter cq): in pass c16 it owns columns 64*c16 + 16*cq .. +16, i.e. every pass completes one
@@ -494,14 +508,11 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         // BW: the scratch / stash rows this pass needs (softplus' codes, g, parked terms) are requested BEFORE the wait for D, so that
         // their L2 / DRAM latency runs under the GEMM instead of on the epilogue's critical path
-        constexpr bool PRE_S = KIND == K_SO || KIND == K_TR;
-        constexpr bool PRE_G = KIND == K_SO;
         const bool PRE_Q = KIND == K_TR || so7;
         uint2 sraw[4]; uint4 graw[2], qraw[2];
         if (PRE_S) {
-            const uint2* p = c.dh + (size_t)(c.lyr * 64 + (col0 >> 2)) * TM + r;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) sraw[j4] = p[(size_t)j4 * TM];
+            for (int j4 = 0; j4 < 4; ++j4) sraw[j4] = sn[j4];
         }
         if (PRE_G) {
             if (c.lyr == 0 && c16 == 0) { NA_TRACE_X(c.trace, 5); stash_flush(c); NA_TRACE_X(c.trace, 6); }     // the g planes (TMA-stored during the reverse sweep) are read back from here on
@@ -534,6 +545,11 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             NA_TRACE_XS(10);
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+        }
+        if (PRE_S && c16 + 1 < N_PASS) {
+            const uint2* p = c.dh + (size_t)(c.lyr * 64 + ((col0 + 64) >> 2)) * TM + r;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) sn[j4] = p[(size_t)j4 * TM];
         }
         float o[16];
         if (IS_FWD) {
