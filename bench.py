@@ -190,12 +190,13 @@ def train_probe(dev, precision, n_patches=8):
     F_BWD = 2 * (2 * 265216 + 2 * 524544 + 2 * 459008)
     out = {}
     pk, _ = peaks()
+    split = precision in ('tc', 'tc_mixed') and os.environ.get('NA_BW_SPLIT', '1') != '0'      # split training program, as Trainer.forward runs it
     for fw in ('volsdf', 'neus'):
         if fw == 'volsdf':
             m = make_volsdf(0.1, 0.0, device=dev).train()
             c2w, K = fx.closed_form_camera(H, W)
             kw = dict(near=0.0, far=6.0, perturb=True, max_upsample_steps=6, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE,
-                      train_stash=precision in ('tc', 'tc_mixed'))       # split training program, as Trainer.forward runs it
+                      train_stash=split)
             patch = lambda ro, rd: pv.render_patch(m, ro, rd, **kw)
             pts = P
         else:
@@ -203,7 +204,7 @@ def train_probe(dev, precision, n_patches=8):
             c2w, K = fx.closed_form_camera(H, W)
             c2w = c2w.clone(); c2w[2, 3] = -0.9                                  # inside NeuS' unit bounding sphere
             kw = dict(upsample_algo='official_solution', N_upsample_iters=4, N_outside=0, obj_bounding_radius=1.0, perturb=True,
-                      N_samples=64, N_importance=64)
+                      N_samples=64, N_importance=64, train_stash=split)
             patch = lambda ro, rd: pn.render_patch(m, ro, rd, **kw)
             pts = 128
         m.engine().precision = precision

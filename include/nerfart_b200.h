@@ -283,6 +283,18 @@ int na_volsdf_render_bwd_stashed(const NaNetDesc* desc, const void* packed, cons
                                  const float* radiance, const float* nablas, const float* grad_rgb, void* grad_pack, double* scalars,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* the same split for NeuS (neus.py:520-576): two evaluations per ray sample exist in the reference too (P points for sdf / nabla,
+ * P - 1 midpoints for the radiance, neus.py:320-324); each is evaluated once.  The workspace holds both stashes
+ * (na_train_workspace_bytes_mode with a NeuS desc accounts for it).                                                       */
+int na_neus_render_fwd_train(const NaNetDesc* desc, const void* packed, const NaNeusCfg* cfg, const float* rays_o,
+                             const float* rays_d, int64_t n_rays, const float* s, const float* t_coarse, const float* u_imp,
+                             const float* u_rand, const NaNeusOut* out, void* workspace, size_t workspace_bytes,
+                             void* train_workspace, size_t train_workspace_bytes, void* stream);
+int na_neus_render_bwd_stashed(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o,
+                               const float* rays_d, int64_t n_rays, const float* s, const float* d_all, const float* sdf,
+                               const float* radiance, const float* nablas, const float* grad_rgb, void* grad_pack, double* scalars,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* NeuS: s = {forward_s()}; d_all / sdf [n,P], nablas [n,P,3] at the sample points, radiance [n,P-1,3] at the midpoints
  * (extras of neus.py:397-407).  scalars: [0] d loss / d ln_s, [1] eikonal loss.                                      */
 int na_neus_render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o, const float* rays_d,

@@ -158,6 +158,9 @@ def lib():
             L.na_neus_render_fwd.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaNeusCfg), C.c_void_p, C.c_void_p,
                                              C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(NaNeusOut), C.c_void_p, C.c_size_t, C.c_void_p]
+            L.na_neus_render_fwd_train.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaNeusCfg), C.c_void_p, C.c_void_p,
+                                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.POINTER(NaNeusOut), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         L.na_surface_workspace_bytes.restype = C.c_size_t
         L.na_surface_workspace_bytes.argtypes = [C.POINTER(NaSurfaceCfg), C.c_int64]
         L.na_ray_cast.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaSurfaceCfg), C.c_void_p, C.c_void_p, C.c_int64,
@@ -171,7 +174,7 @@ def lib():
         L.na_debug_wgrad_f16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.na_train_workspace_bytes_mode.restype = C.c_size_t
         L.na_train_workspace_bytes_mode.argtypes = [C.POINTER(NaNetDesc), C.c_int64, C.c_int32, C.c_int32]
-        for fn in (L.na_volsdf_render_bwd, L.na_neus_render_bwd, L.na_volsdf_render_bwd_stashed):
+        for fn in (L.na_volsdf_render_bwd, L.na_neus_render_bwd, L.na_volsdf_render_bwd_stashed, L.na_neus_render_bwd_stashed):
             fn.argtypes = [C.POINTER(NaNetDesc), C.c_void_p, C.POINTER(NaTrainCfg), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_size_t, C.c_void_p]

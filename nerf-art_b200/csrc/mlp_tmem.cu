@@ -1222,19 +1222,27 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         *reinterpret_cast<float4*>(t1) = make_float4(gs, 0.f, 0.f, 0.f);
                     }
                     S.BWV[6 * TM + r] = gs * c.rs;
-                    if (live) {
+                    if (live && has_rad) {
 #pragma unroll
                         for (int cc = 0; cc < 3; ++cc) {
                             const float rgb = __ldcg(job.rad + S.OIDX[r] * 3 + cc);
                             S.BWV[(3 + cc) * TM + r] *= rgb * (1.f - rgb);
                         }
                     }
-                    if (c.st_row && job.st_t0)
+                    if (has_rad && c.st_row && job.st_t0)
                         *reinterpret_cast<float4*>(job.st_t0 + (size_t)c.st_m * 4) =
                             live ? make_float4(S.BWV[3 * TM + r] * c.irs, S.BWV[4 * TM + r] * c.irs, S.BWV[5 * TM + r] * c.irs, 0.f)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                delta3_stage(c.t_lane + (unsigned)(prog.g0 & 1) * 256u);         // (its leading barrier also publishes BWV[6])
+                if (has_rad) {
+                    delta3_stage(c.t_lane + (unsigned)(prog.g0 & 1) * 256u);     // (its leading barrier also publishes BWV[6])
+                } else {
+                    // no radiance part (NeuS pass A): the second-order sweep starts here with the eikonal gradient alone
+                    epi_bar_sync();                                               // BWV[6] of every row
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) c.nbar[cc] = S.BWV[cc * TM + r];
+                    write_vbar0(c.t_lane + (unsigned)(prog.g0 & 1) * 256u);
+                }
             }
             for (int g = prog.g0; g < prog.n_gemm; ++g) {
                 const int op = BW ? (int)prog.g[g].op : (int)OP_FWD;
@@ -1610,12 +1618,13 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
         for (int l = 0; l < 8; ++l) add(l, OP_SO, l);                     // second-order sweep
         for (int l = 6; l >= 0; --l) add(15 - l, OP_TR, l);               // trunk: z-bar_l from z-bar_{l+1} W_{l+1}
         if (job.bw_split == 2) {
-            // backward half of the split program: the forward launch (bw_split == 1) left the stash planes, tile_buf and rad
-            if (!job.rad || !job.tile_buf || !job.st_t1) return NA_ERR_BAD_ARG;
-            prog.g0 = 21;
+            // backward half of the split program: the forward launch (bw_split == 1) left the stash planes, tile_buf and (with the
+            // radiance part) rad; without it (NeuS pass A: sdf + nabla only) the program starts at the second-order sweep
+            if (!job.tile_buf || !job.st_t1) return NA_ERR_BAD_ARG;
+            prog.g0 = last + 1;                                          // 21 | 17
         } else if (job.bw_split != 0) return NA_ERR_BAD_ARG;
     } else if (job.bw_split != 0) {
-        if (job.bw_split != 1 || !job.st_wide || !job.tile_buf || !job.want_full || !job.rad || !STASH) return NA_ERR_BAD_ARG;
+        if (job.bw_split != 1 || !job.st_wide || !job.tile_buf || !job.want_full || !STASH) return NA_ERR_BAD_ARG;
     }
     long long tiles = (total + TM - 1) / TM;
     int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());

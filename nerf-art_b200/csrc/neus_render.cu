@@ -220,10 +220,18 @@ extern "C" size_t na_neus_workspace_bytes(const NaNeusCfg* cfg, int64_t n_rays) 
     return neus_ws_layout(*cfg, n_rays).total;
 }
 
-extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, const NaNeusCfg* cfg,
-                                  const float* rays_o, const float* rays_d, int64_t n_rays, const float* s_dev,
-                                  const float* t_coarse, const float* u_imp, const float* u_rand,
-                                  const NaNeusOut* out, void* workspace, size_t ws_bytes, void* stream_) {
+namespace na {
+int train_forward_stash(const EvalJob& fj, const void* packed, int precision, void* train_workspace, size_t train_ws_bytes,
+                        float* scratch, size_t scratch_bytes, cudaStream_t stream);                     // csrc/train.cu
+size_t train_ws_total(long long n_rays, int P);
+}
+
+// train_ws != nullptr: the two final evaluations (P points: sdf + nabla; P - 1 midpoints: radiance) are the forward halves of the split
+// training program; their stashes lie one behind the other in the training workspace (csrc/train.cu)
+static int neus_render_fwd(const NaNetDesc* desc, const void* packed, const NaNeusCfg* cfg,
+                           const float* rays_o, const float* rays_d, int64_t n_rays, const float* s_dev,
+                           const float* t_coarse, const float* u_imp, const float* u_rand,
+                           const NaNeusOut* out, void* workspace, size_t ws_bytes, void* train_ws, size_t train_ws_bytes, void* stream_) {
     if (!desc || !packed || !cfg || !rays_o || !rays_d || !s_dev || !t_coarse || !u_imp || !out || !workspace || n_rays <= 0) return NA_ERR_BAD_ARG;
     if (!out->rgb || !out->depth || !out->acc) return NA_ERR_BAD_ARG;
     if (cfg->perturb && !u_rand) return NA_ERR_BAD_ARG;
@@ -273,10 +281,15 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     // sdf + nablas at the P depths (neus.py:320), radiance at the P-1 midpoints through a second SDF pass (324, 111-114)
     EvalJob fj = job;
     fj.P = P; fj.t_off = 0; fj.o_off = 0; fj.sdf = sdf_f; fj.nab = nab_f; fj.rad = nullptr; fj.want_full = 1;
-    NA_TRY(launch_mlp(fj, packed, cfg->precision, scratch, scratch_bytes, stream));
+    const size_t ws_a = train_ws ? train_ws_total(n_rays, P) : 0;
+    if (train_ws) {
+        if (train_ws_bytes < ws_a + train_ws_total(n_rays, P - 1)) return NA_ERR_WORKSPACE;
+        NA_TRY(train_forward_stash(fj, packed, cfg->precision, train_ws, ws_a, scratch, scratch_bytes, stream));
+    } else NA_TRY(launch_mlp(fj, packed, cfg->precision, scratch, scratch_bytes, stream));
     EvalJob mj = job;
     mj.P = P - 1; mj.t_off = 0; mj.midpoints = 1; mj.o_stride = P - 1; mj.o_off = 0; mj.sdf = nullptr; mj.nab = nullptr; mj.rad = rad_f; mj.want_full = 1;
-    NA_TRY(launch_mlp(mj, packed, cfg->precision, scratch, scratch_bytes, stream));
+    if (train_ws) NA_TRY(train_forward_stash(mj, packed, cfg->precision, (unsigned char*)train_ws + ws_a, train_ws_bytes - ws_a, scratch, scratch_bytes, stream));
+    else          NA_TRY(launch_mlp(mj, packed, cfg->precision, scratch, scratch_bytes, stream));
     NeusCompositeArgs ca = {};
     ca.d_all = T; ca.sdf = sdf_f; ca.rad = rad_f; ca.nab = nab_f; ca.s_dev = s_dev; ca.P = P; ca.white_bkgd = cfg->white_bkgd; ca.n_rays = n_rays;
     ca.rgb = out->rgb; ca.depth = out->depth; ca.acc = out->acc; ca.normals = out->normals; ca.alpha_out = out->alpha; ca.w_out = out->weights;
@@ -284,4 +297,21 @@ extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, con
     neus_composite_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(ca);
     NA_CHECK_LAUNCH();
     return NA_OK;
+}
+
+extern "C" int na_neus_render_fwd(const NaNetDesc* desc, const void* packed, const NaNeusCfg* cfg,
+                                  const float* rays_o, const float* rays_d, int64_t n_rays, const float* s_dev,
+                                  const float* t_coarse, const float* u_imp, const float* u_rand,
+                                  const NaNeusOut* out, void* workspace, size_t ws_bytes, void* stream_) {
+    return neus_render_fwd(desc, packed, cfg, rays_o, rays_d, n_rays, s_dev, t_coarse, u_imp, u_rand, out, workspace, ws_bytes, nullptr, 0, stream_);
+}
+
+extern "C" int na_neus_render_fwd_train(const NaNetDesc* desc, const void* packed, const NaNeusCfg* cfg,
+                                        const float* rays_o, const float* rays_d, int64_t n_rays, const float* s_dev,
+                                        const float* t_coarse, const float* u_imp, const float* u_rand,
+                                        const NaNeusOut* out, void* workspace, size_t ws_bytes, void* train_workspace,
+                                        size_t train_ws_bytes, void* stream_) {
+    if (!train_workspace || !out || !out->d_all || !out->sdf || !out->radiance || !out->nablas) return NA_ERR_BAD_ARG;     // detailed outputs: the backward reads them
+    return neus_render_fwd(desc, packed, cfg, rays_o, rays_d, n_rays, s_dev, t_coarse, u_imp, u_rand, out, workspace, ws_bytes,
+                           train_workspace, train_ws_bytes, stream_);
 }

@@ -1287,13 +1287,16 @@ static int attach_stash(EvalJob& e, const TrainWs& w) {
     return NA_OK;
 }
 
+// bytes of the tensor-core training workspace of one launch of n_rays x P samples (NeuS keeps two: points and midpoints)
+size_t train_ws_total(long long n_rays, int P) { return train_ws(nullptr, n_rays, P, true).total; }
+
 // Forward half of the split training program: the final full evaluation of the patch's forward render (csrc/volsdf_render.cu), run
 // as program 0..20 with the forward stash planes written and the softplus' codes / ReLU masks persisted per tile.  `fj` is the
 // render's own job (its sdf / radiance / nabla outputs, apply_bg); the backward half is na_volsdf_render_bwd_stashed.
 int train_forward_stash(const EvalJob& fj, const void* packed, int precision, void* train_workspace, size_t train_ws_bytes,
                         float* scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (precision != NA_PRECISION_TC && precision != NA_PRECISION_TC_MIXED) return NA_ERR_UNSUPPORTED;
-    if (!train_workspace || fj.x || !fj.rad || !fj.want_full || fj.row_ids || fj.n_rows_dev) return NA_ERR_BAD_ARG;
+    if (!train_workspace || fj.x || !fj.want_full || fj.row_ids || fj.n_rows_dev) return NA_ERR_BAD_ARG;
     const TrainWs w = train_ws(train_workspace, fj.n_rows, fj.P, true);
     if (train_ws_bytes < w.total) return NA_ERR_WORKSPACE;
     EvalJob e = fj;
@@ -1316,12 +1319,12 @@ static int tc_backward(const BwdJob& job, const void* packed, int precision, con
     e.t = job.t; e.t_stride = job.t_stride; e.t_off = 0; e.midpoints = job.midpoints;
     e.o_stride = job.P; e.o_off = 0;
     e.sdf = split ? nullptr : w.f_sdf;
-    e.rad = split ? const_cast<float*>(job.f_rad) : (job.has_rad ? w.f_rad : nullptr);        // split: the forward launch's radiance, an input
+    e.rad = !job.has_rad ? nullptr : (split ? const_cast<float*>(job.f_rad) : w.f_rad);      // split: the forward launch's radiance, an input
     e.apply_bg = 0;                                   // raw network sdf: the background mask compares it with R - |x| itself
     e.bound_r = job.bound_r; e.want_full = 1; e.multires_view = job.multires_view;
     NA_TRY(attach_stash(e, w));
     e.bw = 1; e.bw_bg_mask = job.apply_bg; e.bw_split = split ? 2 : 0;
-    if (split && (!job.has_rad || !job.f_rad)) return NA_ERR_BAD_ARG;
+    if (split && job.has_rad && !job.f_rad) return NA_ERR_BAD_ARG;
     e.bw_gsdf = job.g_sdf; e.bw_gnab = job.g_nab; e.bw_grad = job.g_rad;
     // the forward re-evaluation runs in the render's own mode: in tc_mixed the SDF forward pass (what softplus' and the activations come
     // from) keeps its three-product operands, the feature head / reverse sweep / radiance layers use single products exactly as in the
@@ -1437,7 +1440,11 @@ extern "C" size_t na_grad_pack_bytes(const NaNetDesc* desc) { (void)desc; return
 extern "C" size_t na_train_workspace_bytes_mode(const NaNetDesc* desc, int64_t n_rays, int32_t points_per_ray, int32_t precision) {
     (void)desc;
     if (n_rays <= 0 || points_per_ray <= 1) return 0;
-    return train_ws(nullptr, n_rays, points_per_ray, bwd_on_tensor_cores(precision)).total;
+    const bool tc = bwd_on_tensor_cores(precision);
+    size_t b = train_ws(nullptr, n_rays, points_per_ray, tc).total;
+    // NeuS, split program: the stash of the P - 1 midpoints (radiance pass) lives behind that of the P points (sdf / nabla pass)
+    if (tc && desc && desc->framework == NA_FRAMEWORK_NEUS && points_per_ray > 2) b += train_ws(nullptr, n_rays, points_per_ray - 1, tc).total;
+    return b;
 }
 extern "C" int na_debug_wgrad_f16(const void* planes16, int64_t m_pad, int64_t m_rows, int l_bf16, int r_bf16, float* out, float* bias_out, void* stream) {
     if (!planes16 || !out || m_pad <= 0 || m_rows <= 0 || m_rows > m_pad) return NA_ERR_BAD_ARG;
@@ -1462,9 +1469,11 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     const int P = cfg->points_per_ray;
     if (P < 2 || n * (int64_t)P > 0x7fffffffLL) return NA_ERR_UNSUPPORTED;
     const bool tc = bwd_on_tensor_cores(cfg->precision);
-    if (stashed && (!tc || neus || (cfg->precision != NA_PRECISION_TC && cfg->precision != NA_PRECISION_TC_MIXED))) return NA_ERR_UNSUPPORTED;
+    if (stashed && (!tc || (cfg->precision != NA_PRECISION_TC && cfg->precision != NA_PRECISION_TC_MIXED))) return NA_ERR_UNSUPPORTED;
     const TrainWs w = train_ws(ws_, n, P, tc);
-    if (ws_bytes < w.total) return NA_ERR_WORKSPACE;
+    // NeuS split program: second workspace (midpoints) behind the first
+    const TrainWs wB = (stashed && neus) ? train_ws((unsigned char*)ws_ + w.total, n, P - 1, tc) : w;
+    if (ws_bytes < w.total + ((stashed && neus) ? wB.total : 0)) return NA_ERR_WORKSPACE;
     const PackF32 L = pack_layout_f32(desc->multires_view);
     const PackTrain T = pack_layout_train();
     const float* pk = (const float*)packed;
@@ -1480,8 +1489,8 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
     NA_CHECK_LAUNCH();
     const size_t M = (size_t)n * P, mpad = (M + TM - 1) / TM * TM;
     Stash st; st.mpad = mpad; st.wide = w.stash; st.narrow = w.stash + (size_t)N_WIDE * mpad * 256; st.tiny = st.narrow + 3 * mpad * NLD;      // fp32 mode only
-    auto backward = [&](const BwdJob& j, long long rows, int ts, int tr) -> int {
-        if (tc) return tc_backward(j, packed, cfg->precision, w, ts, tr, gp, stream, stashed ? 1 : 0);
+    auto backward = [&](const BwdJob& j, long long rows, int ts, int tr, bool second = false) -> int {
+        if (tc) return tc_backward(j, packed, cfg->precision, second ? wB : w, ts, tr, gp, stream, stashed ? 1 : 0);
         NA_TRY(launch_mlp_bwd(j, pk, L, tp, T, st, w, stream));
         return launch_wgrad(st, rows, j.has_rad, ts, tr, gp, stream);
     };
@@ -1502,8 +1511,8 @@ static int render_bwd(const NaNetDesc* desc, const void* packed, const NaTrainCf
             NA_TRY(backward(job, (long long)M, 1, 0));
         }
         if (dbg_pass && dbg_pass[0] == 'A') return NA_OK;
-        job.P = P - 1; job.midpoints = 1; job.g_sdf = nullptr; job.g_nab = nullptr; job.g_rad = w.g_rad; job.has_rad = 1;
-        NA_TRY(backward(job, (long long)n * (P - 1), cfg->train_surface, cfg->train_radiance));
+        job.P = P - 1; job.midpoints = 1; job.g_sdf = nullptr; job.g_nab = nullptr; job.g_rad = w.g_rad; job.has_rad = 1; job.f_rad = rad;
+        NA_TRY(backward(job, (long long)n * (P - 1), cfg->train_surface, cfg->train_radiance, true));
     }
     return NA_OK;
 }
@@ -1535,6 +1544,16 @@ extern "C" int na_neus_render_bwd(const NaNetDesc* desc, const void* packed, con
     if (desc && desc->framework != NA_FRAMEWORK_NEUS) return NA_ERR_BAD_ARG;
     return render_bwd(desc, packed, cfg, rays_o, rays_d, n_rays, s, d_all, sdf, radiance, nablas, grad_rgb, (float*)grad_pack,
                       scalars, workspace, workspace_bytes, (cudaStream_t)stream, true);
+}
+
+// NeuS split program: `workspace` was filled by na_neus_render_fwd_train for the same rays (points stash, then midpoints stash)
+extern "C" int na_neus_render_bwd_stashed(const NaNetDesc* desc, const void* packed, const NaTrainCfg* cfg, const float* rays_o,
+                                          const float* rays_d, int64_t n_rays, const float* s, const float* d_all, const float* sdf,
+                                          const float* radiance, const float* nablas, const float* grad_rgb, void* grad_pack,
+                                          double* scalars, void* workspace, size_t workspace_bytes, void* stream) {
+    if (desc && desc->framework != NA_FRAMEWORK_NEUS) return NA_ERR_BAD_ARG;
+    return render_bwd(desc, packed, cfg, rays_o, rays_d, n_rays, s, d_all, sdf, radiance, nablas, grad_rgb, (float*)grad_pack,
+                      scalars, workspace, workspace_bytes, (cudaStream_t)stream, true, true);
 }
 
 extern "C" int na_unpack_grads(const NaNetDesc* desc, const NaRawParams* raw, const void* grad_pack, const NaRawGrads* out, void* stream) {

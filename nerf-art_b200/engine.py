@@ -196,8 +196,8 @@ class NetEngine:
         return self._tws
 
     def neus_render(self, rays_o, rays_d, s_dev, *, obj_bounding_radius, N_samples, N_importance, N_upsample_iters,
-                    white_bkgd, perturb, detailed_output, u_rand=None):
-        """neus.volume_render ('official_solution', N_outside=0), neus.py:142-424."""
+                    white_bkgd, perturb, detailed_output, u_rand=None, train_stash=False):
+        """neus.volume_render ('official_solution', N_outside=0), neus.py:142-424.  train_stash: see volsdf_render."""
         L = _lib.lib()
         dev = rays_o.device
         n = rays_o.shape[0]
@@ -219,10 +219,22 @@ class NetEngine:
         self.pack()
         ws = self.workspace(L.na_neus_workspace_bytes(C.byref(cfg), n))
         tc, ui = cpu_linspace(N_samples, dev), cpu_linspace(n_new, dev)
+        self._stash_key = None
+        if train_stash:
+            if not detailed_output or self.precision not in ('tc', 'tc_mixed'):
+                raise RuntimeError("train_stash needs detailed_output and precision 'tc' / 'tc_mixed'")
+            tws = self._train_workspace(n, P, dev)
         with torch.cuda.device(dev):
-            check(L.na_neus_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
-                                       ptr(s_dev), ptr(tc), ptr(ui), ptr(u_rand.contiguous()) if u_rand is not None else None,
-                                       C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_neus_render_fwd')
+            if train_stash:
+                check(L.na_neus_render_fwd_train(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
+                                                 ptr(s_dev), ptr(tc), ptr(ui), ptr(u_rand.contiguous()) if u_rand is not None else None,
+                                                 C.byref(out), ptr(ws), ws.numel(), ptr(tws), tws.numel(), stream_ptr(dev)),
+                      'na_neus_render_fwd_train')
+                self._stash_key = (n, P, o['d_all'].data_ptr(), o['radiance'].data_ptr(), self.precision, self._pack_key)
+            else:
+                check(L.na_neus_render_fwd(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n,
+                                           ptr(s_dev), ptr(tc), ptr(ui), ptr(u_rand.contiguous()) if u_rand is not None else None,
+                                           C.byref(out), ptr(ws), ws.numel(), stream_ptr(dev)), 'na_neus_render_fwd')
         return o
 
     # ------------------------------------------------------------------------------------------
@@ -252,12 +264,13 @@ class NetEngine:
         cfg = NaTrainCfg(int(P), float(w_eikonal), int(eikonal_count), int(bool(white_bkgd)), float(speed_factor),
                          int(bool(train_surface)), int(bool(train_radiance)), PRECISIONS[self.precision])
         # the forward render of exactly these outputs left its stash in the workspace (volsdf_render(train_stash=True)): backward half only
-        stashed = (not neus) and getattr(self, '_stash_key', None) is not None and \
+        stashed = getattr(self, '_stash_key', None) is not None and \
             self._stash_key == (n, P, d_all.data_ptr(), fwd['radiance'].data_ptr(), self.precision, self._pack_key)
         self._stash_key = None
         self._train_workspace(n, P, dev)
         g = grad_rgb.reshape(-1, 3).float().contiguous()
-        fn = L.na_neus_render_bwd if neus else (L.na_volsdf_render_bwd_stashed if stashed else L.na_volsdf_render_bwd)
+        fn = (L.na_neus_render_bwd_stashed if stashed else L.na_neus_render_bwd) if neus else \
+            (L.na_volsdf_render_bwd_stashed if stashed else L.na_volsdf_render_bwd)
         with torch.cuda.device(dev):
             check(fn(C.byref(self.desc), ptr(self.packed), C.byref(cfg), ptr(rays_o), ptr(rays_d), n, ptr(scal), ptr(d_all),
                      ptr(fwd['sdf']), ptr(fwd['radiance']), ptr(fwd['nablas']), ptr(g), ptr(self._gpack),

@@ -195,10 +195,10 @@ def finetune_forward(trainer, framework, args, model_input, ground_truth, render
     gradient = rgb.grad.clone().detach()
     optimizer.zero_grad()
     kw = {k: v for k, v in render_kwargs_train.items() if k not in ('H', 'W', 'batched')}
-    # VolSDF, tensor-core modes: the patch's forward render is the forward half of the training program, the backward launch runs the
-    # backward half only (one network evaluation per sample, as in the reference's autograd).  NA_BW_SPLIT=0: the backward launch
-    # re-evaluates the forward pass (the only form for NeuS and the fp32 mode).
-    if framework == 'volsdf' and model.engine().precision in ('tc', 'tc_mixed') and os.environ.get('NA_BW_SPLIT', '1') != '0':
+    # tensor-core modes: the patch's forward render is the forward half of the training program, the backward launch runs the backward
+    # half only (one network evaluation per sample point, as in the reference's autograd).  NA_BW_SPLIT=0: the backward launch
+    # re-evaluates the forward pass (the only form in fp32 mode).
+    if model.engine().precision in ('tc', 'tc_mixed') and os.environ.get('NA_BW_SPLIT', '1') != '0':
         kw['train_stash'] = True
     scal, n_patches = backward_patches(model, framework, rays_o, rays_d, gradient, lambda ro, rd: render_patch(ro, rd, **kw),
                                        w_eikonal=args.finetune.w_eikonal if use_eik else 0.0,

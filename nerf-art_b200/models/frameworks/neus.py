@@ -104,13 +104,13 @@ class SingleRenderer(nn.Module):
 
 
 def render_patch(model, ro, rd, obj_bounding_radius=1.0, perturb=False, white_bkgd=False, N_samples=64, N_importance=64,
-                 N_upsample_iters=4, u_rand=None, **dummy_kwargs):
+                 N_upsample_iters=4, u_rand=None, train_stash=False, **dummy_kwargs):
     """Forward render of one flat ray patch with the detailed outputs the backward needs (defaults of neus.py:142-170).
-    Returns (flat outputs, {s} on the device)."""
+    Returns (flat outputs, {s} on the device).  train_stash: see volsdf.render_patch (split training program)."""
     s = model.forward_s().detach().reshape(1).float().contiguous()
     o = model.engine().neus_render(ro, rd, s, obj_bounding_radius=obj_bounding_radius, N_samples=N_samples,
                                    N_importance=N_importance, N_upsample_iters=N_upsample_iters, white_bkgd=white_bkgd,
-                                   perturb=perturb, detailed_output=True, u_rand=u_rand)
+                                   perturb=perturb, detailed_output=True, u_rand=u_rand, train_stash=train_stash)
     return o, s
 
 

@@ -406,3 +406,48 @@ def test_split_training_program_equals_the_one_launch_program(precision, white, 
     fwd, ab = render_patch(m, ro, rd, train_stash=True, **kw)
     render_patch(m, ro[:50].contiguous(), rd[:50].contiguous(), **kw)
     assert eng._stash_key is None
+
+
+@pytest.mark.parametrize('precision,w_eik', [('tc_mixed', 0.1), ('tc', 0.0)])
+def test_split_training_program_equals_the_one_launch_program_neus(precision, w_eik):
+    """NeuS (neus.py:520-576; radiance net frozen): na_neus_render_fwd_train + na_neus_render_bwd_stashed -- the two final evaluations of
+    the forward render (P points: sdf + nabla, P - 1 midpoints: radiance) are the forward halves, their stashes one behind the other in
+    the workspace; the backward launches run the second-order sweep + trunk (points) and GEMMs 21..40 (midpoints) only -- against the
+    one-launch programs: same forward outputs bit for bit, same gradients up to the order of the atomic sums."""
+    from nerfart_b200.models.frameworks.neus import render_patch
+    from nerfart_b200.utils import rend_util
+    m = make_neus(0.05, 0.5, device=DEV).train()
+    eng = m.engine(); eng.precision = precision
+    H, W = 24, 24
+    c2w, K = fx.tilted_camera(H, W)
+    c2w = c2w.clone(); c2w[:3, 3] = c2w[:3, 3] * 0.3                               # inside NeuS' unit bounding sphere
+    with torch.no_grad():
+        ro, rd, _ = rend_util.get_rays(c2w[None].to(DEV), K[None].to(DEV), H, W)
+    n = 401
+    ro, rd = ro[0, :n].contiguous(), rd[0, :n].contiguous()
+    g = torch.Generator(device=DEV); g.manual_seed(12)
+    G = 1e-2 * torch.randn(n, 3, device=DEV, generator=g)
+    kw = dict(obj_bounding_radius=1.0, N_samples=16, N_importance=16, N_upsample_iters=4, perturb=False, white_bkgd=False)
+    res = []
+    for stash in (False, True):
+        fwd, s = render_patch(m, ro, rd, train_stash=stash, **kw)
+        assert (eng._stash_key is not None) == stash
+        eng.grad_zero()
+        eng.render_bwd(ro, rd, s, fwd, G, w_eikonal=w_eik, eikonal_count=n * 32, white_bkgd=False, speed_factor=m.speed_factor,
+                       train_radiance=False)
+        assert eng._stash_key is None
+        pairs, scal = eng.unpack_grads(True, False)
+        torch.cuda.synchronize()
+        res.append((fwd, [(p, gr.clone()) for p, gr in pairs], scal.clone()))
+    (f0, p0, s0), (f1, p1, s1) = res
+    for k in ('rgb', 'd_all', 'sdf', 'radiance', 'nablas'):
+        assert torch.equal(f0[k], f1[k]), k
+    names = {id(p): k for k, p in m.named_parameters()}
+    worst = 0.0
+    for (pa, ga), (pb, gb) in zip(p0, p1):
+        assert pa is pb
+        e = float((ga - gb).abs().max() / (ga.abs().max() + 1e-30))
+        worst = max(worst, e)
+        assert e < 2e-3, (names[id(pa)], e)
+    print(f'NeuS split vs one-launch training program [{precision}, eik={w_eik}]: worst gradient difference {worst:.2e} of the tensor scale')
+    assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-12)
