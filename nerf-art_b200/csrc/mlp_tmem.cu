@@ -31,8 +31,13 @@ namespace na {
 namespace tm {
 
 constexpr int TM = 128;
-constexpr int THREADS = 576;
+// Register budget.  Two auxiliary warps (weight producer, MMA issuer) + 16 epilogue warps = 18 warps put FIVE warps on two of the four
+// schedulers, so the kernel is compiled for 16384 / (5 x 32) = 102 -> 96 registers per thread.  (Tried: making the auxiliary warps a
+// whole warpgroup that gives up registers with setmaxnreg.dec while the epilogue warpgroups take them with setmaxnreg.inc -- ptxas then
+// spills 0.5-2.3 KB per kernel instead of 0.1-0.2 KB for every split tried (32 / 112, 40 / 104, 56 / 104, 64 / 104); not kept.)
+constexpr int FIRST_EPI_WARP = 2;
 constexpr int EPI_THREADS = 512;
+constexpr int THREADS = 32 * FIRST_EPI_WARP + EPI_THREADS;
 #ifndef NA_TM_NS
 #define NA_TM_NS 5
 #endif
@@ -55,6 +60,15 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 // every wait are ~3 % of an SDF-only epilogue pass.
 #if defined(NA_TM_TRACE) && !defined(NA_TM_CYCLES)
 #define NA_TM_CYCLES
+#endif
+// NA_TM_FAKE_SCRATCH (experiment only, WRONG results): the backward half's scratch operands come from registers instead of memory --
+// the upper bound of what staging them through shared memory could gain
+#ifdef NA_TM_FAKE_SCRATCH
+#define NA_FAKE_LD2(x) make_uint2(0x3fff8000u + (unsigned)r, 0x80003fffu)
+#define NA_FAKE_LD4(x) make_uint4(0x3c003c00u + (unsigned)r, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u)
+#else
+#define NA_FAKE_LD2(x) (x)
+#define NA_FAKE_LD4(x) (x)
 #endif
 #ifdef NA_TM_CYCLES
 #define NA_CYC(...) __VA_ARGS__
@@ -210,19 +224,29 @@ enum EpiKind { K_FWD, K_FWD3, K_FWD7, K_FEAT, K_BWD, K_BWD4, K_BWD0, K_RAD0, K_R
                K_FWDX, K_BWDX, K_RADX };
 
 struct EpiCtx {
-    Smem* S; uint2* dh; float4* featp; float* misc; const float* pk; const PackF32* L; const EvalJob* job;
+    // (loop-invariant state is kept small on purpose: the kernels run at their 96-register budget, and whatever does not fit is
+    //  re-loaded from local memory inside the epilogue passes -- 56 more bytes of spills were 2.11 -> 2.9 ms per patch in the
+    //  backward half, profiles/r4b_split_program.md.  featp / misc are constant offsets from qp; t_wait / trace exist in
+    //  diagnostic builds only; the L2 policy of the stash stores is re-created where it is used.)
+    Smem* S; uint2* dh; const float* pk; const PackF32* L; const EvalJob* job;
+    __device__ __forceinline__ float4* featp() const { return reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(qp) - MISC_BYTES - FEAT_BYTES); }
+    __device__ __forceinline__ float* misc() const { return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(qp) - MISC_BYTES); }
     unsigned t_lane; int r, cq, g; float us; int sdim;
-    unsigned bias_s, w8_s, w4_s, radw_s, kb_bar, d_bar;
+    unsigned s_base;                // shared-space address of the Smem block; the tables / barriers below are constant offsets from it
+    __device__ __forceinline__ unsigned bias_s() const { return s_base + (unsigned)offsetof(Smem, BIAS); }
+    __device__ __forceinline__ unsigned w8_s() const { return s_base + (unsigned)offsetof(Smem, W8); }
+    __device__ __forceinline__ unsigned w4_s() const { return s_base + (unsigned)offsetof(Smem, W4); }
+    __device__ __forceinline__ unsigned radw_s() const { return s_base + (unsigned)offsetof(Smem, RADW); }
+    __device__ __forceinline__ unsigned kb_bar() const { return s_base + (unsigned)offsetof(Smem, kb_ready); }
+    __device__ __forceinline__ unsigned d_bar() const { return s_base + (unsigned)offsetof(Smem, d_ready); }
     int signal, need_lo, lane;
     unsigned short* st_row;         // ST: this thread's row in plane 0 of the 16-bit stash (st_wide + m * 256), nullptr beyond the allocation
-    size_t st_plane;                // ST: elements per plane
     int st_mpad;                    // ST: rows per plane (the TMA row coordinate of plane p, sample m is p * st_mpad + m: below 2^31)
     long long st_m;                 // ST: flat sample index of the row
-    const TmaMap* st_map;           // ST: tensor map of the wide planes (store boxes: 16 columns x 32 samples)
+    __device__ __forceinline__ const TmaMap* st_map() const { return &job->st_store_map; }   // ST: tensor map of the wide planes (store boxes: 16 columns x 32 samples)
     unsigned st_stg;                // ST: this warp's two 1 KB staging buffers in shared memory
     int st_row0;                    // ST: first sample (row of the plane) of this warp's 32 lanes in the current tile
     mutable unsigned st_cnt;        // ST: TMA stores issued by this warp so far (buffer parity)
-    unsigned long long st_policy;   // ST: L2 evict-first cache policy of the stash stores
     // BW: per-row power-of-two scale of the upstream gradient (the backward is linear in it and rows are independent, so every
     // backward quantity of the row is carried x rs in the fp16 operands and stored x irs) and the row's total d L / d nabla (x rs)
     float rs, irs, nbar[3];
@@ -232,7 +256,10 @@ struct EpiCtx {
     int bw;
     unsigned nx;                    // FULL: scratch planes the NEXT GEMM's epilogue reads, for the prefetch: softplus' plane | parked-term plane << 8 |
                                     // g plane << 16 | (feature rows) << 24; 0xff = none
-    unsigned d_phase; long long* t_wait; long long* trace;
+    unsigned d_phase;
+#ifdef NA_TM_CYCLES
+    long long* t_wait; long long* trace;
+#endif
 };
 
 // this warp's part of K-block kb of the next A operand is in TMEM (and its part of D columns [64kb, 64kb+64) is consumed)
@@ -341,8 +368,10 @@ __device__ __forceinline__ void stash16(const EpiCtx& c, int plane, int col0, co
     __syncwarp();
     if (c.lane == 0) {
         // L2 evict-first: the planes stream out to HBM and must not displace the per-CTA scratch (read back three times per tile)
+        unsigned long long st_policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(st_policy));
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
-                     :: "l"(c.st_map), "r"(col0), "r"(plane * c.st_mpad + c.st_row0), "r"(buf), "l"(c.st_policy) : "memory");
+                     :: "l"(c.st_map()), "r"(col0), "r"(plane * c.st_mpad + c.st_row0), "r"(buf), "l"(st_policy) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     ++c.st_cnt;
@@ -429,10 +458,10 @@ __device__ __forceinline__ void prefetch_next_gemm(const EpiCtx& c, int col0) {
     const unsigned dh_plane = c.nx & 0xffu, q_plane = (c.nx >> 8) & 0xffu, g_plane = (c.nx >> 16) & 0xffu;
     if (dh_plane != 0xffu) prefetch_l2(c.dh + (size_t)(dh_plane * 64 + (col0 >> 2) + (c.lane & 3)) * TM + c.r);
     if (ST && q_plane != 0xffu) prefetch_l2(c.qp + (size_t)(q_plane * 32 + (col0 >> 3) + (c.lane & 1)) * TM + c.r);
-    if (ST && g_plane != 0xffu && c.st_row) prefetch_l2(c.st_row + (size_t)(ST_G + g_plane) * c.st_plane + col0);
+    if (ST && g_plane != 0xffu && c.st_row) prefetch_l2(c.st_row + ((size_t)(ST_G + g_plane) * (size_t)c.st_mpad << 8) + col0);
     if (c.nx >> 24) {
         // geometry feature rows read by the tail of GEMM 16 (float4 per row and column quad: 2-row sectors)
-        const float4* f = c.featp + (size_t)((col0 >> 2) + (c.lane & 3)) * TM;
+        const float4* f = c.featp() + (size_t)((col0 >> 2) + (c.lane & 3)) * TM;
         prefetch_l2(f + c.r); prefetch_l2(f + (c.r ^ 2));
     }
 }
@@ -460,7 +489,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     const bool fwd3 = KIND == K_FWD3 || (KIND == K_FWDX && c.g == 3), fwd7 = KIND == K_FWD7 || (KIND == K_FWDX && c.g == 7);
     const bool bwd4 = KIND == K_BWD4 || (KIND == K_BWDX && c.g == 12), rad3 = KIND == K_RAD3 || (KIND == K_RADX && c.g == 20);
     const bool dr0 = KIND == K_DR && c.lyr == 0, so3 = KIND == K_SO && c.lyr == 3, so7 = KIND == K_SO && c.lyr == 7;
-    const unsigned bias = c.bias_s + (unsigned)(KIND == K_FEAT ? 8 : (IS_RAD ? 9 + (c.g - 17) : c.g)) * 1024u;
+    const unsigned bias = c.bias_s() + (unsigned)(KIND == K_FEAT ? 8 : (IS_RAD ? 9 + (c.g - 17) : c.g)) * 1024u;
     constexpr bool USES_DH = FULL && (KIND == K_FEAT || IS_BWD);
     constexpr int N_PASS = KIND == K_BWD0 ? 1 : 4;                  // reverse GEMM 0: only 39 useful columns, all in pass 0
     // softplus' plane this epilogue multiplies by: feature head (g = 8) -> layer 7, reverse GEMM g = 9..15 -> layer 15 - g
@@ -485,7 +514,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     if (PRE_S) {
         const uint2* p = c.dh + (size_t)(c.lyr * 64 + c.cq * 4) * TM + r;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) sn[j4] = p[(size_t)j4 * TM];
+        for (int j4 = 0; j4 < 4; ++j4) sn[j4] = NA_FAKE_LD2(p[(size_t)j4 * TM]);
     }
 #pragma unroll 1
     for (int c16 = 0; c16 < N_PASS; ++c16) {
@@ -516,21 +545,21 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         }
         if (PRE_G) {
             if (c.lyr == 0 && c16 == 0) { NA_TRACE_X(c.trace, 5); stash_flush(c); NA_TRACE_X(c.trace, 6); }     // the g planes (TMA-stored during the reverse sweep) are read back from here on
-            const uint4* p = reinterpret_cast<const uint4*>(c.st_row + (size_t)(ST_G + c.lyr) * c.st_plane + col0);
-            graw[0] = __ldcg(p); graw[1] = __ldcg(p + 1);
+            const uint4* p = reinterpret_cast<const uint4*>(c.st_row + ((size_t)(ST_G + c.lyr) * (size_t)c.st_mpad << 8) + col0);
+            graw[0] = NA_FAKE_LD4(__ldcg(p)); graw[1] = NA_FAKE_LD4(__ldcg(p + 1));
         }
         if (PRE_Q) {
             const uint4* p = c.qp + (size_t)((KIND == K_TR ? c.lyr : 7) * 32 + (col0 >> 3)) * TM + r;
-            if (KIND == K_TR || c.has_rad) { qraw[0] = p[0]; qraw[1] = p[TM]; }
+            if (KIND == K_TR || c.has_rad) { qraw[0] = NA_FAKE_LD4(p[0]); qraw[1] = NA_FAKE_LD4(p[TM]); }
             else { qraw[0] = make_uint4(0u, 0u, 0u, 0u); qraw[1] = qraw[0]; }
         }
         {                                                            // pass c16 reads N-quarter c16 of D
             NA_CYC(const long long t0 = clock64();)
-            mbar_wait_plain(c.d_bar + 8u * (unsigned)c16, c.d_phase);
+            mbar_wait_plain(c.d_bar() + 8u * (unsigned)c16, c.d_phase);
             if (N_PASS < 4) {
                 // a GEMM whose epilogue reads fewer than four N-quarters (the 64-wide reverse GEMM 0: its four d_ready commits are
                 // issued together): consume the other phases here, before anything is signalled to the MMA warp
-                for (int k = N_PASS; k < 4; ++k) mbar_wait_plain(c.d_bar + 8u * (unsigned)k, c.d_phase);
+                for (int k = N_PASS; k < 4; ++k) mbar_wait_plain(c.d_bar() + 8u * (unsigned)k, c.d_phase);
             }
             NA_CYC(*c.t_wait += clock64() - t0;)
             tc_fence_after();
@@ -549,7 +578,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         if (PRE_S && c16 + 1 < N_PASS) {
             const uint2* p = c.dh + (size_t)(c.lyr * 64 + ((col0 + 64) >> 2)) * TM + r;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) sn[j4] = p[(size_t)j4 * TM];
+            for (int j4 = 0; j4 < 4; ++j4) sn[j4] = NA_FAKE_LD2(p[(size_t)j4 * TM]);
         }
         float o[16];
         if (IS_FWD) {
@@ -605,7 +634,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
             if (fwd7) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
+                    const float4 w4 = lds128(c.w8_s() + (unsigned)(col0 + 4 * j4) * 4u);
                     sdf_part = fmaf(o[4 * j4], w4.x, sdf_part); sdf_part = fmaf(o[4 * j4 + 1], w4.y, sdf_part);
                     sdf_part = fmaf(o[4 * j4 + 2], w4.z, sdf_part); sdf_part = fmaf(o[4 * j4 + 3], w4.w, sdf_part);
                 }
@@ -617,14 +646,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 const float4 b4 = lds128(bias + (unsigned)(col0 + 4 * j4) * 4u);
                 const float4 f4 = make_float4(fmaf(acc[4 * j4], us, b4.x), fmaf(acc[4 * j4 + 1], us, b4.y),
                                               fmaf(acc[4 * j4 + 2], us, b4.z), fmaf(acc[4 * j4 + 3], us, b4.w));
-                if (FULL) c.featp[(size_t)((col0 >> 2) + j4) * TM + r] = f4;
+                if (FULL) c.featp()[(size_t)((col0 >> 2) + j4) * TM + r] = f4;
                 if (ST) { fst[4 * j4] = f4.x; fst[4 * j4 + 1] = f4.y; fst[4 * j4 + 2] = f4.z; fst[4 * j4 + 3] = f4.w; }
                 if (c.job->feat && S.OIDX[r] >= 0) *(reinterpret_cast<float4*>(c.job->feat + S.OIDX[r] * 256 + col0) + j4) = f4;
                 if (FULL) {
                     // next A: d sdf / d z7 = W8[0,:] * softplus'(z7)
                     float d4[4];
                     dh_decode4(q[j4], d4);
-                    const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
+                    const float4 w4 = lds128(c.w8_s() + (unsigned)(col0 + 4 * j4) * 4u);
                     o[4 * j4] = w4.x * d4[0] * ACT_SCALE; o[4 * j4 + 1] = w4.y * d4[1] * ACT_SCALE;
                     o[4 * j4 + 2] = w4.z * d4[2] * ACT_SCALE; o[4 * j4 + 3] = w4.w * d4[3] * ACT_SCALE;
                 }
@@ -639,14 +668,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int k = col0 + 4 * j4 + i;
-                    if (bwd4 && k >= SKIP_H) c.misc[(k - SKIP_H) * TM + r] = acc[4 * j4 + i] * us;      // embedding branch of the skip
+                    if (bwd4 && k >= SKIP_H) c.misc()[(k - SKIP_H) * TM + r] = acc[4 * j4 + i] * us;      // embedding branch of the skip
                     o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
                 }
             }
             if (ST) { stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc[k * TM + r] += acc[j] * us; }
+            for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k < EMB) c.misc()[k * TM + r] += acc[j] * us; }
         } else if (IS_BW) {
             // ---- backward program (BW): every value is carried x rs in the operands; stash planes receive x irs ----------------
             if (KIND == K_DR) {
@@ -662,7 +691,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const int srow = c.sdim - 3 + cc;
-                            const float4 w = (STASH && c.sdim == 9) ? lds128(c.radw_s + (unsigned)(srow * 256 + col0 + 4 * j4) * 4u)
+                            const float4 w = (STASH && c.sdim == 9) ? lds128(c.radw_s() + (unsigned)(srow * 256 + col0 + 4 * j4) * 4u)
                                                                     : __ldg(reinterpret_cast<const float4*>(c.pk + c.L->rad_wt[0] + (size_t)(256 + srow) * 256 + col0) + j4);
                             rgb_part[cc] = fmaf(o[4 * j4], w.x, rgb_part[cc]); rgb_part[cc] = fmaf(o[4 * j4 + 1], w.y, rgb_part[cc]);
                             rgb_part[cc] = fmaf(o[4 * j4 + 2], w.z, rgb_part[cc]); rgb_part[cc] = fmaf(o[4 * j4 + 3], w.w, rgb_part[cc]);
@@ -681,16 +710,41 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 // second-order sweep, layer lyr: g-bar = W v-bar; u-bar = g-bar s = v-bar_{lyr+1}; q = 100 g-bar g (1 - s) joins z-bar_lyr.
                 // Units are folded into the constants: o is carried x ACT_SCALE (the A operand's unit; the stash scale undoes it), q is
                 // produced x QP_SCALE (the parked plane's unit): t = 16 g-bar, q' = (t g) ((1 - s) 100 / 16 / 256).
-                float sv[16], gv[16], q[16];
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) { float d4[4]; dh_decode4(sraw[j4], d4); sv[4 * j4] = d4[0]; sv[4 * j4 + 1] = d4[1]; sv[4 * j4 + 2] = d4[2]; sv[4 * j4 + 3] = d4[3]; }
-                bf16x16_to_float(graw, gv);
+                // (written four columns at a time so that neither the decoded softplus' values nor the converted g values stay live: the
+                //  kernel runs at its 96-register budget and every spilled value in this loop costs -- 148 -> 204 bytes of spills were
+                //  2.11 -> 2.89 ms per patch, profiles/r4b_split_program.md)
+                float q[16];                                       // parked term x QP_SCALE; layer 7: z-bar_7 x ACT_SCALE instead
                 constexpr float QK = 100.f / ACT_SCALE * QP_SCALE;
+                const float gs16 = so7 ? S.BWV[6 * TM + r] * ACT_SCALE : 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float t = acc[j] * us16;
-                    q[j] = (t * gv[j]) * fmaf(sv[j], -QK, QK);
-                    o[j] = t * sv[j];
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float s4[4], g4[4];
+                    dh_decode4(sraw[j4], s4);
+                    {
+                        const uint4 gq = graw[j4 >> 1];
+                        const unsigned w0 = (j4 & 1) ? gq.z : gq.x, w1 = (j4 & 1) ? gq.w : gq.y;
+                        g4[0] = __uint_as_float(w0 << 16); g4[1] = __uint_as_float(w0 & 0xffff0000u);
+                        g4[2] = __uint_as_float(w1 << 16); g4[3] = __uint_as_float(w1 & 0xffff0000u);
+                    }
+                    float h4[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (so7) {
+                        // h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]   (x ACT_SCALE)
+                        const uint4 hq = qraw[j4 >> 1];
+                        const unsigned w0 = (j4 & 1) ? hq.z : hq.x, w1 = (j4 & 1) ? hq.w : hq.y;
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+                        const float4 w4 = lds128(c.w8_s() + (unsigned)(col0 + 4 * j4) * 4u);
+                        h4[0] = fmaf(gs16, w4.x, f0.x * (QP_UNSCALE * ACT_SCALE)); h4[1] = fmaf(gs16, w4.y, f0.y * (QP_UNSCALE * ACT_SCALE));
+                        h4[2] = fmaf(gs16, w4.z, f1.x * (QP_UNSCALE * ACT_SCALE)); h4[3] = fmaf(gs16, w4.w, f1.y * (QP_UNSCALE * ACT_SCALE));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = 4 * j4 + i;
+                        const float t = acc[j] * us16;
+                        const float qq = (t * g4[i]) * fmaf(s4[i], -QK, QK);
+                        o[j] = t * s4[i];
+                        // layer 7: z-bar_7 = h-bar_7 s_7 + q_7
+                        q[j] = so7 ? fmaf(h4[i], s4[i], qq * (QP_UNSCALE * ACT_SCALE)) : qq;
+                    }
                 }
                 if (so3 && c16 == 3 && c.cq >= 1) {
                     // skip connection: columns k >= SKIP_H = 217 of v-bar_4 are v-bar_0 entries k - 217 (this thread: 16 cq - 25 ..)
@@ -703,31 +757,27 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 stash16(c, ST_VB + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
                 NA_TRACE_XS(12);
                 if (so7) {
-                    // z-bar_7 = h-bar_7 s_7 + q_7 with h-bar_7 = (parked feature part) + masked d L / d sdf * W8[0,:]   (x ACT_SCALE)
-                    float hb[16];
-                    qdecode16(qraw, hb, QP_UNSCALE * ACT_SCALE);
-                    const float gs = S.BWV[6 * TM + r] * ACT_SCALE;
+                    stash16(c, ST_ZB + 7, col0, q, c.irs * (1.f / ACT_SCALE));
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 w4 = lds128(c.w8_s + (unsigned)(col0 + 4 * j4) * 4u);
-                        hb[4 * j4] = fmaf(gs, w4.x, hb[4 * j4]); hb[4 * j4 + 1] = fmaf(gs, w4.y, hb[4 * j4 + 1]);
-                        hb[4 * j4 + 2] = fmaf(gs, w4.z, hb[4 * j4 + 2]); hb[4 * j4 + 3] = fmaf(gs, w4.w, hb[4 * j4 + 3]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = fmaf(hb[j], sv[j], q[j] * (QP_UNSCALE * ACT_SCALE));
-                    stash16(c, ST_ZB + 7, col0, o, c.irs * (1.f / ACT_SCALE));
+                    for (int j = 0; j < 16; ++j) o[j] = q[j];                            // the trunk's first A operand is z-bar_7
                 } else {
                     qstore16<true>(c.qp, c.lyr, col0, r, q);                             // parked (x rs) until the trunk reaches this layer
                 }
                 NA_TRACE_XS(13);
             } else {
                 // trunk, K_TR: z-bar_lyr = h-bar_lyr s_lyr + q_lyr   (carried x ACT_SCALE, see K_SO)
-                float sv[16], qv[16];
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) { float d4[4]; dh_decode4(sraw[j4], d4); sv[4 * j4] = d4[0]; sv[4 * j4 + 1] = d4[1]; sv[4 * j4 + 2] = d4[2]; sv[4 * j4 + 3] = d4[3]; }
-                qdecode16(qraw, qv, QP_UNSCALE * ACT_SCALE);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = fmaf(acc[j] * us16, sv[j], qv[j]);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float s4[4];
+                    dh_decode4(sraw[j4], s4);
+                    const uint4 hq = qraw[j4 >> 1];
+                    const unsigned w0 = (j4 & 1) ? hq.z : hq.x, w1 = (j4 & 1) ? hq.w : hq.y;
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+                    o[4 * j4] = fmaf(acc[4 * j4] * us16, s4[0], f0.x * (QP_UNSCALE * ACT_SCALE));
+                    o[4 * j4 + 1] = fmaf(acc[4 * j4 + 1] * us16, s4[1], f0.y * (QP_UNSCALE * ACT_SCALE));
+                    o[4 * j4 + 2] = fmaf(acc[4 * j4 + 2] * us16, s4[2], f1.x * (QP_UNSCALE * ACT_SCALE));
+                    o[4 * j4 + 3] = fmaf(acc[4 * j4 + 3] * us16, s4[3], f1.y * (QP_UNSCALE * ACT_SCALE));
+                }
                 stash16(c, ST_ZB + c.lyr, col0, o, c.irs * (1.f / ACT_SCALE));
             }
             // (single-product fp16 operands: an outlier |x rs| > 4e3 saturates in store_a16's conversion instead of rounding to inf)
@@ -744,7 +794,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     if (c.sdim == 9) {
 #pragma unroll
                         for (int j = 0; j < 9; ++j) {
-                            const float4 w = STASH ? lds128(c.radw_s + (unsigned)(j * 256 + col0 + 4 * j4) * 4u) : __ldg(wsm + j * 64);
+                            const float4 w = STASH ? lds128(c.radw_s() + (unsigned)(j * 256 + col0 + 4 * j4) * 4u) : __ldg(wsm + j * 64);
                             z[0] = fmaf(small_in[j], w.x, z[0]); z[1] = fmaf(small_in[j], w.y, z[1]);
                             z[2] = fmaf(small_in[j], w.z, z[2]); z[3] = fmaf(small_in[j], w.w, z[3]);
                         }
@@ -773,7 +823,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                 for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 w = lds128(c.w4_s + (unsigned)(cc * 256 + col0 + 4 * j4) * 4u);
+                        const float4 w = lds128(c.w4_s() + (unsigned)(cc * 256 + col0 + 4 * j4) * 4u);
                         rgb_part[cc] = fmaf(o[4 * j4], w.x, rgb_part[cc]); rgb_part[cc] = fmaf(o[4 * j4 + 1], w.y, rgb_part[cc]);
                         rgb_part[cc] = fmaf(o[4 * j4 + 2], w.z, rgb_part[cc]); rgb_part[cc] = fmaf(o[4 * j4 + 3], w.w, rgb_part[cc]);
                     }
@@ -789,13 +839,19 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) discard_l2(dhp + (size_t)((col0 >> 2) + j4) * TM);
         }
-        if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar, c16, c.lane);
+        if (KIND != K_BWD0 && c.signal) signal_kb(c.kb_bar(), c16, c.lane);
     }
 }
 
-template <bool FULL, bool ST, bool BW>
+// B2: the backward half of the split training program as its own instantiation (program 21.. / 17.. only): without the forward
+// epilogues the kernel is a third of the code, and the register allocation of the second-order sweep is not disturbed by them
+// (with the prologue below compiled into the one-launch program, that kernel's spills went from 148 to 204 bytes and the
+// backward-only launch from 2.11 to 2.89 ms per patch)
+// (B2 = 1: with the radiance part, program 21..40; B2 = 2: without it -- NeuS pass A -- program 17..31: has_rad is a compile-time
+//  constant in both, so neither carries the other's prologue)
+template <bool FULL, bool ST, bool BW, int B2 = 0>
 __global__ void __launch_bounds__(THREADS, 1)
-mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ pk, const PackF32 L, const unsigned char* __restrict__ wimg,
+mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ pk, const __grid_constant__ PackF32 L, const unsigned char* __restrict__ wimg,
                 const float* __restrict__ unscale, const Program prog, unsigned char* __restrict__ scratch, const __grid_constant__ SpinCtx sc) {
     extern __shared__ unsigned char smem_raw_[];
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
@@ -1054,39 +1110,37 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 }
             }
         NA_CYC(if (job.dbg && blockIdx.x == 0 && lane == 0) { job.dbg[0] = clock64() - t_tot0; job.dbg[1] = t_a; job.dbg[2] = t_full; })
-    } else {
+    } else if (warp >= FIRST_EPI_WARP) {
         // ================= epilogue warps =================
-        const int q = warp & 3, cq = (warp - 2) >> 2;
+        const int q = warp & 3, cq = (warp - FIRST_EPI_WARP) >> 2;
         const int r = 32 * q + lane;                       // sample row == TMEM lane
         unsigned char* sp = scratch + (size_t)blockIdx.x * SCRATCH_BYTES;
         EpiCtx c;
-        c.S = &S; c.dh = reinterpret_cast<uint2*>(sp); c.featp = reinterpret_cast<float4*>(sp + DH_BYTES);
-        c.misc = reinterpret_cast<float*>(sp + DH_BYTES + FEAT_BYTES);
+        c.S = &S; c.dh = reinterpret_cast<uint2*>(sp);
         c.pk = pk; c.L = &L; c.job = &job; c.t_lane = tmem_d + ((unsigned)(32 * q) << 16); c.r = r; c.cq = cq;
         c.sdim = small_dim(job.multires_view);
-        c.bias_s = smem_u32(S.BIAS); c.w8_s = smem_u32(S.W8); c.w4_s = smem_u32(S.W4); c.radw_s = smem_u32(S.RADW);
-        c.kb_bar = smem_u32(&S.kb_ready[0]); c.d_bar = smem_u32(&S.d_ready[0]); c.lane = lane; c.signal = 0; c.need_lo = 1;
+        c.s_base = smem_u32(&S); c.lane = lane; c.signal = 0; c.need_lo = 1;
         c.d_phase = 0;
         NA_CYC(long long t_d = 0; const long long t_e0 = clock64(); c.t_wait = &t_d;)
-        c.trace = nullptr; c.st_row = nullptr; c.st_plane = job.st_mpad * 256; c.st_mpad = (int)job.st_mpad;
-        c.st_m = 0; c.st_map = &job.st_store_map; c.st_cnt = 0; c.st_row0 = 0;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.st_policy));
-        c.st_stg = smem_u32(S.Wst) + (unsigned)(NS - 1) * STAGE_BYTES + (unsigned)(warp - 2) * 2048u;
-        c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = job.rad != nullptr;
+        NA_CYC(c.trace = nullptr;)
+        c.st_row = nullptr; c.st_mpad = (int)job.st_mpad;
+        c.st_m = 0; c.st_cnt = 0; c.st_row0 = 0;
+        c.st_stg = smem_u32(S.Wst) + (unsigned)(NS - 1) * STAGE_BYTES + (unsigned)(warp - FIRST_EPI_WARP) * 2048u;
+        c.rs = 1.f; c.irs = 1.f; c.nbar[0] = c.nbar[1] = c.nbar[2] = 0.f; c.lyr = 0; c.has_rad = B2 == 1 ? 1 : (B2 == 2 ? 0 : (job.rad != nullptr));
         c.bw = BW ? 1 : 0;
         c.qp = reinterpret_cast<uint4*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES);
-        c.mk = reinterpret_cast<unsigned long long*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES) + (tid - 64);
-        const bool has_rad = job.rad != nullptr;
+        c.mk = reinterpret_cast<unsigned long long*>(sp + DH_BYTES + FEAT_BYTES + MISC_BYTES + QP_BYTES + GP_BYTES) + (tid - 32 * FIRST_EPI_WARP);
+        const bool has_rad = B2 == 1 ? true : (B2 == 2 ? false : job.rad != nullptr);
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #ifdef NA_TM_TRACE
-            c.trace = (job.dbg && blockIdx.x == 0 && tile == (long long)gridDim.x && tid == 64) ? job.dbg + 16 : nullptr;
+            c.trace = (job.dbg && blockIdx.x == 0 && tile == (long long)gridDim.x && tid == 32 * FIRST_EPI_WARP) ? job.dbg + 16 : nullptr;
 #endif
             if (ST && job.bw_split != 0) {
                 // split training program: the softplus' codes and ReLU masks of a tile outlive the forward launch
                 unsigned char* tb = job.tile_buf + (size_t)tile * TILE_BUF_BYTES;
                 c.dh = reinterpret_cast<uint2*>(tb);
-                c.mk = reinterpret_cast<unsigned long long*>(tb + DH_BYTES) + (tid - 64);
+                c.mk = reinterpret_cast<unsigned long long*>(tb + DH_BYTES) + (tid - 32 * FIRST_EPI_WARP);
             }
             // ---- tile inputs: point, encoding (x ACT_SCALE, hi/lo) into K-block 0 of region 0 ---------------------
             {
@@ -1156,9 +1210,9 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     uint4* erow = reinterpret_cast<uint4*>(job.st_emb + (size_t)w * ST_NLD + 16 * cq);
                     __stcs(erow, lo); __stcs(erow + 1, hi);
                 }
-                if (prog.g0 == 0) store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
+                if (!B2) store_a16(c.t_lane + (unsigned)(16 * cq), e, 1);
             }
-            if (prog.g0 == 0) { for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane); }
+            if (!B2) { for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar(), k, lane); }
 #ifndef NA_NO_INPUT_BAR
             epi_bar_sync();                                   // EMBS / X / V / BWV of this tile: written above by other warps, read from GEMM 3 on
 #endif
@@ -1183,7 +1237,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 NA_TRACE_X(c.trace, 2);
                 store_a16(t_region + (unsigned)(16 * cq), e, 0);
                 NA_TRACE_X(c.trace, 3);
-                for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar, k, lane);
+                for (int k = 0; k < 4; ++k) signal_kb(c.kb_bar(), k, lane);
                 NA_TRACE_X(c.trace, 4);
             };
             // BW: A <- delta_3 = (delta_4 W4) * [ys_4 > 0] (K-blocks 0..3 of radiance-backward GEMM 21), over this thread's own (consumed)
@@ -1198,8 +1252,8 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     float o[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 w0 = lds128(c.w4_s + (unsigned)(col0 + 4 * j4) * 4u), w1 = lds128(c.w4_s + (unsigned)(256 + col0 + 4 * j4) * 4u),
-                                     w2 = lds128(c.w4_s + (unsigned)(512 + col0 + 4 * j4) * 4u);
+                        const float4 w0 = lds128(c.w4_s() + (unsigned)(col0 + 4 * j4) * 4u), w1 = lds128(c.w4_s() + (unsigned)(256 + col0 + 4 * j4) * 4u),
+                                     w2 = lds128(c.w4_s() + (unsigned)(512 + col0 + 4 * j4) * 4u);
                         o[4 * j4] = d4[0] * w0.x + d4[1] * w1.x + d4[2] * w2.x; o[4 * j4 + 1] = d4[0] * w0.y + d4[1] * w1.y + d4[2] * w2.y;
                         o[4 * j4 + 2] = d4[0] * w0.z + d4[1] * w1.z + d4[2] * w2.z; o[4 * j4 + 3] = d4[0] * w0.w + d4[1] * w1.w + d4[2] * w2.w;
                     }
@@ -1207,10 +1261,10 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     for (int j = 0; j < 16; ++j) o[j] = ((m64 >> (16 * c16 + j)) & 1ull) ? o[j] * ACT_SCALE : 0.f;
                     stash16(c, ST_D + 3, col0, o, c.irs * (1.f / ACT_SCALE));
                     store_a16(t_region + col0, o, 0);               // GEMM 21 is a single-product GEMM: no lo words
-                    signal_kb(c.kb_bar, c16, lane);
+                    signal_kb(c.kb_bar(), c16, lane);
                 }
             };
-            if (BW && prog.g0 > 0) {
+            if (B2) {
                 // ---- backward half of the split program: what the tails of GEMMs 7 and 20 do in the one-launch program, from the
                 // forward launch's outputs: the masked d L / d sdf (flag in st_t1[.][1]) and delta_4 = d L / d radiance * rgb (1 - rgb)
                 if (cq == 0) {
@@ -1256,17 +1310,19 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 const unsigned t_dd = c.t_lane + (unsigned)((g + 1) & 1) * 256u;       // D of this GEMM == A of the next
                 // program order: 0..7 fwd | 8 feat | 9..15 bwd 7..1 | 16 bwd 0 | 17..20 radiance
                 if (BW && op != OP_FWD) {
-                    if (op == OP_DR) {
+                    if (B2 != 2 && op == OP_DR) {
                         epi_gemm<K_DR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
-                    } else if (op == OP_FB) {
+                    } else if (B2 != 2 && op == OP_FB) {
                         epi_gemm<K_FB, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
-                    } else if (op == OP_HB) {
+                    } else if (B2 != 2 && op == OP_HB) {
                         epi_gemm<K_HB, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else if (op == OP_SO) {
                         epi_gemm<K_SO, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     } else {
                         epi_gemm<K_TR, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     }
+                } else if (B2) {
+                    // (backward-only instantiation: the program holds no forward GEMM)
                 } else if (g < 8) {
                     if (ST) epi_gemm<K_FWDX, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
                     else if (g == 3) epi_gemm<K_FWD3, FULL, ST>(c, t_dd, sdf_part, rgb_part, small_in);
@@ -1326,7 +1382,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                 }
                 c.d_phase ^= 1;
                 // ---- per-GEMM tails ------------------------------------------------------------------------
-                if (g == 7) {
+                if (!B2 && g == 7) {
                     // fwd layer 7 stored h8 x16: undo in the head.  sdf = <h8, W8[0]> + b8[0]
                     S.PART[cq * TM + r] = sdf_part * (1.f / ACT_SCALE); sdf_part = 0.f;
                     epi_bar_sync();
@@ -1360,13 +1416,13 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                     }
                     if (BW) epi_bar_sync();                   // BWV[6] (masked d L / d sdf) is read by every column quarter in the trunk
                 }
-                if (FULL && g == 16) {
+                if (!B2 && FULL && g == 16) {
                     if (has_rad) {
                         // A <- geometry feature (x16) for radiance layer 0, written over this thread's own (consumed) columns of D of
                         // GEMM 16; signalled at once, so radiance GEMM 0 runs under the nabla arithmetic below
                         float4 fn[4];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) fn[j4] = c.featp[(size_t)(cq * 4 + j4) * TM + r];
+                        for (int j4 = 0; j4 < 4; ++j4) fn[j4] = c.featp()[(size_t)(cq * 4 + j4) * TM + r];
 #pragma unroll 1
                         for (int c16 = 0; c16 < 4; ++c16) {
                             const int col0 = c16 * 64 + cq * 16;
@@ -1378,14 +1434,14 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                             }
                             if (c16 < 3) {
 #pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) fn[j4] = c.featp[(size_t)(((col0 + 64) >> 2) + j4) * TM + r];
+                                for (int j4 = 0; j4 < 4; ++j4) fn[j4] = c.featp()[(size_t)(((col0 + 64) >> 2) + j4) * TM + r];
                             }
                             store_a16(t_dd + col0, h, c.need_lo);
                             if ((lane & 7) == 0) {
 #pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) discard_l2(c.featp + (size_t)((col0 >> 2) + j4) * TM + r);
+                                for (int j4 = 0; j4 < 4; ++j4) discard_l2(c.featp() + (size_t)((col0 >> 2) + j4) * TM + r);
                             }
-                            signal_kb(c.kb_bar, c16, lane);
+                            signal_kb(c.kb_bar(), c16, lane);
                         }
                     }
                     epi_bar_sync();                                       // all 39 d sdf/d emb entries complete
@@ -1393,14 +1449,14 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         // nabla component cq in closed form: one column quarter per coordinate
                         const int cc = cq;
                         const float xc = S.X[cc * TM + r];
-                        float n = c.misc[cc * TM + r];
+                        float n = c.misc()[cc * TM + r];
 #pragma unroll
                         for (int f = 0; f < 6; ++f) {
                             const float fr = (float)(1 << f);
                             float sn, cs;
                             if (STASH) { sn = S.EMBS[(3 + 6 * f + cc) * TM + r] * (1.f / ACT_SCALE); cs = S.EMBS[(6 + 6 * f + cc) * TM + r] * (1.f / ACT_SCALE); }
                             else sincosf(__fmul_rn(xc, fr), &sn, &cs);
-                            n += fr * (c.misc[(3 + 6 * f + cc) * TM + r] * cs - c.misc[(6 + 6 * f + cc) * TM + r] * sn);
+                            n += fr * (c.misc()[(3 + 6 * f + cc) * TM + r] * cs - c.misc()[(6 + 6 * f + cc) * TM + r] * sn);
                         }
                         S.PART[cc * TM + r] = n;
                     }
@@ -1426,7 +1482,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
                         c.nbar[cc] = S.PART[cc * TM + r] + S.PART[(3 + cc) * TM + r] + S.PART[(6 + cc) * TM + r] + S.PART[(9 + cc) * TM + r] + S.BWV[cc * TM + r];
                 }
                 if (BW && op == OP_HB) write_vbar0(t_dd);
-                if (FULL && g == 20 && op == OP_FWD) {
+                if (!B2 && FULL && g == 20 && op == OP_FWD) {
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) { S.PART[(cq * 3 + cc) * TM + r] = rgb_part[cc]; rgb_part[cc] = 0.f; }
                     epi_bar_sync();
@@ -1456,7 +1512,7 @@ mlp_tmem_kernel(const __grid_constant__ EvalJob job, const float* __restrict__ p
             }
         }
         if (ST) stash_flush(c);
-        NA_CYC(if (job.dbg && blockIdx.x == 0 && tid == 64) { job.dbg[3] = clock64() - t_e0; job.dbg[4] = t_d; })
+        NA_CYC(if (job.dbg && blockIdx.x == 0 && tid == 32 * FIRST_EPI_WARP) { job.dbg[3] = clock64() - t_e0; job.dbg[4] = t_d; })
     }
     tc_fence_before();
     __syncthreads();
@@ -1573,6 +1629,8 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
         NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+        NA_TRY(check_cuda(cudaFuncSetAttribute(mlp_tmem_kernel<true, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     }
     const long long total = job.x ? job.m : (long long)job.n_rows * job.P;
     if (total <= 0) return NA_OK;
@@ -1632,7 +1690,11 @@ int launch_mlp_tmem(const EvalJob& job_, const float* pk_f32, const unsigned cha
     const float* usc = (const float*)(image + T.unscale_off);
     if (job.st_wide && !job.want_full) return NA_ERR_BAD_ARG;
     const SpinCtx sc = diag_next(DK_MLP_TMEM, grid);
-    if (job.bw)             mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    if (job.bw && prog.g0 > 0 && job.rad)
+                            mlp_tmem_kernel<true, true, true, 1><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else if (job.bw && prog.g0 > 0)
+                            mlp_tmem_kernel<true, true, true, 2><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
+    else if (job.bw)        mlp_tmem_kernel<true, true, true><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     else if (job.st_wide && job.bw_split == 1)
                             mlp_tmem_kernel<true, true, false><<<grid, THREADS, smem, stream>>>(job, pk_f32, L, image, usc, prog, scratch, sc);
     else if (job.st_wide)   return NA_ERR_UNSUPPORTED;               // the stash is written by the training programs only
@@ -1647,6 +1709,8 @@ int preload_mlp_tmem() {
     NA_PRELOAD((tm::mlp_tmem_kernel<true, false, false>));
     NA_PRELOAD((tm::mlp_tmem_kernel<true, true, true>));
     NA_PRELOAD((tm::mlp_tmem_kernel<true, true, false>));
+    NA_PRELOAD((tm::mlp_tmem_kernel<true, true, true, 1>));
+    NA_PRELOAD((tm::mlp_tmem_kernel<true, true, true, 2>));
     NA_PRELOAD(tm::pack_kernel);
     NA_PRELOAD(tm::absmax_kernel);
     return NA_OK;
