@@ -156,6 +156,21 @@ using namespace na;
 
 extern "C" int na_version(void) { return 100; }
 // diagnostics only: device buffer of >= 8 int64 that mlp_tc_kernel fills with cycle counters of CTA 0 (NULL disables)
+namespace na {
+struct SmallBlob { unsigned w[256]; };
+__global__ void upload_small_kernel(const SmallBlob blob, unsigned* __restrict__ dst, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = blob.w[i];
+}
+int upload_small(void* dst, const void* src, size_t n, cudaStream_t stream) {
+    if (!dst || !src || n == 0 || n > sizeof(SmallBlob) || (n & 3)) return NA_ERR_BAD_ARG;
+    SmallBlob b;
+    memcpy(b.w, src, n);
+    upload_small_kernel<<<1, 128, 0, stream>>>(b, (unsigned*)dst, (int)(n / 4));
+    NA_CHECK_LAUNCH();
+    return NA_OK;
+}
+}  // namespace na
+
 extern "C" int na_debug_set_buffer(void* dev_ptr) { g_tc_dbg = (long long*)dev_ptr; return NA_OK; }
 extern "C" const char* na_error_string(int code) {
     switch (code) {
@@ -245,7 +260,7 @@ extern "C" int na_pack_weights(const NaNetDesc* desc, const NaRawParams* raw, vo
     dims[13][0] = 3; dims[13][1] = W;
     float* scale = packed + pack_scale_off(L);
     int* dims_dev = (int*)(packed + pack_dims_off(L));
-    NA_TRY(check_cuda(cudaMemcpyAsync(dims_dev, dims, sizeof(dims), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(upload_small(dims_dev, dims, sizeof(dims), stream));
     wn_scale_kernel<<<dim3((257 + 7) / 8, 14), 256, 0, stream>>>(*raw, dims_dev, scale);
     NA_CHECK_LAUNCH();
 

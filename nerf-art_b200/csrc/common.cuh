@@ -24,6 +24,9 @@ inline int check_cuda(cudaError_t e) {
          if (_e != cudaSuccess) { na::g_last_cuda_error = (int)_e; return NA_ERR_CUDA; } \
          if (na::g_diag_on >= 2) na::diag_mark(__FILE__, __LINE__, (cudaStream_t)(NA_DIAG_STREAM)); } while (0)
 #define NA_TRY(x) do { int _r = (x); if (_r != NA_OK) return _r; } while (0)
+// small host table -> device memory, carried as a by-value kernel argument (csrc/api.cu): no pageable-memory cudaMemcpyAsync (which
+// stages through the driver and synchronises the host) in the weight-packing path; n <= 1024 bytes, a multiple of 4
+int upload_small(void* dst, const void* src, size_t n, cudaStream_t stream);
 #define NA_PRELOAD(k) do { cudaFuncAttributes _a; NA_TRY(na::check_cuda(cudaFuncGetAttributes(&_a, k))); } while (0)
 
 int num_sms();

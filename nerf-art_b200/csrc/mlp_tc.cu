@@ -720,11 +720,11 @@ int tc_pack(const float* pk_f32, const PackF32& L, unsigned char* base, const Tc
     unsigned char* meta = base + T.meta_off;
     size_t* d_offs = (size_t*)meta; int* d_rows = (int*)(meta + 256); int* d_kb = (int*)(meta + 512); int* d_nh = (int*)(meta + 768);
     unsigned* d_st = (unsigned*)(meta + 1024); float* d_absmax = (float*)(meta + 1280);
-    NA_TRY(check_cuda(cudaMemcpyAsync(d_offs, offs, sizeof(offs), cudaMemcpyHostToDevice, stream)));
-    NA_TRY(check_cuda(cudaMemcpyAsync(d_rows, rows, sizeof(rows), cudaMemcpyHostToDevice, stream)));
-    NA_TRY(check_cuda(cudaMemcpyAsync(d_kb, T.n_kb, sizeof(T.n_kb), cudaMemcpyHostToDevice, stream)));
-    NA_TRY(check_cuda(cudaMemcpyAsync(d_nh, T.n_nh, sizeof(T.n_nh), cudaMemcpyHostToDevice, stream)));
-    NA_TRY(check_cuda(cudaMemcpyAsync(d_st, T.stage0, sizeof(T.stage0), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(upload_small(d_offs, offs, sizeof(offs), stream));
+    NA_TRY(upload_small(d_rows, rows, sizeof(rows), stream));
+    NA_TRY(upload_small(d_kb, T.n_kb, sizeof(T.n_kb), stream));
+    NA_TRY(upload_small(d_nh, T.n_nh, sizeof(T.n_nh), stream));
+    NA_TRY(upload_small(d_st, T.stage0, sizeof(T.stage0), stream));
     plane_absmax_kernel<<<TC_N_PLANES, 256, 0, stream>>>(pk_f32, d_offs, d_rows, d_absmax);
     NA_CHECK_LAUNCH();
     tc_pack_kernel<<<dim3(32, TC_N_PLANES), 256, 0, stream>>>(pk_f32, d_offs, d_rows, d_kb, d_nh, d_st, d_absmax, base + T.wtc_off,

@@ -1595,14 +1595,14 @@ int tmem_pack(const float* pk_f32, const size_t* d_offs, const int* d_rows, cons
     for (int g = 0; g < N_PLANES; ++g) { meta[g * 4] = T.n_kb[g]; meta[g * 4 + 1] = T.N[g]; meta[g * 4 + 2] = (int)(T.w_off[g] / 16); meta[g * 4 + 3] = 0; }
     unsigned char* mbase = image + T.meta_off;
     int* d_meta = (int*)mbase; size_t* offs = (size_t*)(mbase + 512); int* rows = (int*)(mbase + 768); float* absmax = (float*)(mbase + 1024);
-    NA_TRY(check_cuda(cudaMemcpyAsync(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(upload_small(d_meta, meta, sizeof(meta), stream));
     NA_TRY(check_cuda(cudaMemcpyAsync(offs, d_offs, 21 * sizeof(size_t), cudaMemcpyDeviceToDevice, stream)));
     NA_TRY(check_cuda(cudaMemcpyAsync(rows, d_rows, 21 * sizeof(int), cudaMemcpyDeviceToDevice, stream)));
     NA_TRY(check_cuda(cudaMemcpyAsync(absmax, d_absmax, 21 * sizeof(float), cudaMemcpyDeviceToDevice, stream)));
     const size_t offs_bw[5] = {train_off + TP.rad_w[3], train_off + TP.rad_w[2], train_off + TP.rad_w[1], train_off + TP.rad_w[0], train_off + TP.w8_feat};
     const int rows_bw[5] = {256, 256, 256, 256, 256};
-    NA_TRY(check_cuda(cudaMemcpyAsync(offs + 21, offs_bw, sizeof(offs_bw), cudaMemcpyHostToDevice, stream)));
-    NA_TRY(check_cuda(cudaMemcpyAsync(rows + 21, rows_bw, sizeof(rows_bw), cudaMemcpyHostToDevice, stream)));
+    NA_TRY(upload_small(offs + 21, offs_bw, sizeof(offs_bw), stream));
+    NA_TRY(upload_small(rows + 21, rows_bw, sizeof(rows_bw), stream));
     absmax_kernel<<<5, 256, 0, stream>>>(pk_f32, offs + 21, rows + 21, absmax + 21);
     NA_CHECK_LAUNCH();
     pack_kernel<<<dim3(32, N_PLANES), 256, 0, stream>>>(pk_f32, offs, rows, d_meta, absmax, image, (float*)(image + T.unscale_off));
