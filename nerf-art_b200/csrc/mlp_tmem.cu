@@ -61,15 +61,6 @@ constexpr int N_PLANES = 26;                     // weight images: 0..7 fwd | 8 
 #if defined(NA_TM_TRACE) && !defined(NA_TM_CYCLES)
 #define NA_TM_CYCLES
 #endif
-// NA_TM_FAKE_SCRATCH (experiment only, WRONG results): the backward half's scratch operands come from registers instead of memory --
-// the upper bound of what staging them through shared memory could gain
-#ifdef NA_TM_FAKE_SCRATCH
-#define NA_FAKE_LD2(x) make_uint2(0x3fff8000u + (unsigned)r, 0x80003fffu)
-#define NA_FAKE_LD4(x) make_uint4(0x3c003c00u + (unsigned)r, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u)
-#else
-#define NA_FAKE_LD2(x) (x)
-#define NA_FAKE_LD4(x) (x)
-#endif
 #ifdef NA_TM_CYCLES
 #define NA_CYC(...) __VA_ARGS__
 #else
@@ -297,13 +288,20 @@ __device__ __forceinline__ void store_a16(unsigned taddr, const float (&o)[16], 
     tmem_wait_st();
 }
 
-// softplus'(z) = sigmoid(100 z) as a 16-bit code: bit 15 = (z >= 0), low 15 bits = round(t * 32767.49), t = exp(-|100 z|);
-// decoded as r = 1 / (1 + code/32768), z >= 0 ? r : 1 - r   (absolute error <= 2e-5).  The decode is two bit operations, one
-// MUFU.RCP and one add: the 15 bits are dropped straight into the mantissa of a float in [1, 2), which *is* 1 + t.
+// softplus'(z) = sigmoid(100 z) as a 16-bit code.
+// NA_TM_CODE15 (the round-2 scheme): bit 15 = (z >= 0), low 15 bits = round(t * 32767.49), t = exp(-|100 z|); decoded as
+// r = 1 / (1 + code/32768), z >= 0 ? r : 1 - r (absolute error <= 2e-5): cheap to encode (no MUFU), but every decode is two bit
+// operations, one MUFU.RCP, an add, a bit test and a select.
+// Default: code = round(s * 65535), s = z >= 0 ? r : t r with r = 1 / (1 + t) (one MUFU.RCP and two more FMA-pipe instructions at the
+// ONE encode); decoded as (code + 2^23 as a float) - 2^23, times 1/65535: three instructions, no MUFU, absolute error <= 7.7e-6, exact
+// 0 and 1 (saturated units carry no bias).  The codes are decoded once in the render kernel and three times in the training programs
+// (reverse sweep, second-order sweep, trunk).
+#ifdef NA_TM_CODE15
 __device__ __forceinline__ unsigned dh_code(float z16, float t) {
     // round(t * 32767.49) through the 2^23 magic number (FMA pipe; F2I would go to the XU pipe the softplus already saturates)
     return ((~__float_as_uint(z16) >> 16) & 0x8000u) | (__float_as_uint(fmaf(t, 32767.49f, 8388608.f)) & 0x7fffu);
 }
+__device__ __forceinline__ unsigned dh_pack2(unsigned a, unsigned b) { return a | (b << 16); }
 __device__ __forceinline__ float dh_decode_lo(unsigned w) {            // code in bits [0,16)
     const float ru = rcp_approx(__uint_as_float(((w & 0x7fffu) << 8) | 0x3f800000u));
     return (w & 0x8000u) ? ru : 1.f - ru;
@@ -312,6 +310,20 @@ __device__ __forceinline__ float dh_decode_hi(unsigned w) {            // code i
     const float ru = rcp_approx(__uint_as_float(((w >> 8) & 0x7fff00u) | 0x3f800000u));
     return (w & 0x80000000u) ? ru : 1.f - ru;
 }
+#else
+__device__ __forceinline__ unsigned dh_code(float z16, float t) {      // returns 2^23-biased float bits: the code is the low 16 bits
+    const float r = rcp_approx(1.f + t);
+    const float s = z16 >= 0.f ? r : t * r;
+    return __float_as_uint(fmaf(s, 65535.f, 8388608.f));
+}
+__device__ __forceinline__ unsigned dh_pack2(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5410); }      // low halves of a | b << 16
+__device__ __forceinline__ float dh_decode_lo(unsigned w) {            // code in bits [0,16)
+    return (__uint_as_float((w & 0xffffu) | 0x4b000000u) - 8388608.f) * (1.f / 65535.f);
+}
+__device__ __forceinline__ float dh_decode_hi(unsigned w) {            // code in bits [16,32)
+    return (__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7632)) - 8388608.f) * (1.f / 65535.f);
+}
+#endif
 __device__ __forceinline__ void dh_decode4(const uint2 q, float (&d)[4]) {
     d[0] = dh_decode_lo(q.x); d[1] = dh_decode_hi(q.x); d[2] = dh_decode_lo(q.y); d[3] = dh_decode_hi(q.y);
 }
@@ -514,7 +526,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
     if (PRE_S) {
         const uint2* p = c.dh + (size_t)(c.lyr * 64 + c.cq * 4) * TM + r;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) sn[j4] = NA_FAKE_LD2(p[(size_t)j4 * TM]);
+        for (int j4 = 0; j4 < 4; ++j4) sn[j4] = p[(size_t)j4 * TM];
     }
 #pragma unroll 1
     for (int c16 = 0; c16 < N_PASS; ++c16) {
@@ -546,11 +558,11 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         if (PRE_G) {
             if (c.lyr == 0 && c16 == 0) { NA_TRACE_X(c.trace, 5); stash_flush(c); NA_TRACE_X(c.trace, 6); }     // the g planes (TMA-stored during the reverse sweep) are read back from here on
             const uint4* p = reinterpret_cast<const uint4*>(c.st_row + ((size_t)(ST_G + c.lyr) * (size_t)c.st_mpad << 8) + col0);
-            graw[0] = NA_FAKE_LD4(__ldcg(p)); graw[1] = NA_FAKE_LD4(__ldcg(p + 1));
+            graw[0] = __ldcg(p); graw[1] = __ldcg(p + 1);
         }
         if (PRE_Q) {
             const uint4* p = c.qp + (size_t)((KIND == K_TR ? c.lyr : 7) * 32 + (col0 >> 3)) * TM + r;
-            if (KIND == K_TR || c.has_rad) { qraw[0] = NA_FAKE_LD4(p[0]); qraw[1] = NA_FAKE_LD4(p[TM]); }
+            if (KIND == K_TR || c.has_rad) { qraw[0] = p[0]; qraw[1] = p[TM]; }
             else { qraw[0] = make_uint4(0u, 0u, 0u, 0u); qraw[1] = qraw[0]; }
         }
         {                                                            // pass c16 reads N-quarter c16 of D
@@ -578,7 +590,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
         if (PRE_S && c16 + 1 < N_PASS) {
             const uint2* p = c.dh + (size_t)(c.lyr * 64 + ((col0 + 64) >> 2)) * TM + r;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) sn[j4] = NA_FAKE_LD2(p[(size_t)j4 * TM]);
+            for (int j4 = 0; j4 < 4; ++j4) sn[j4] = p[(size_t)j4 * TM];
         }
         float o[16];
         if (IS_FWD) {
@@ -607,7 +619,7 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                         cd[i] = dh_code(z16[j], t[j]);
                         if (fwd3 && col0 + j >= SKIP_H) cd[i] = 0u;          // decodes to 0
                     }
-                    c.dh[(size_t)(c.g * 64 + (col0 >> 2) + j4) * TM + r] = make_uint2(cd[0] | (cd[1] << 16), cd[2] | (cd[3] << 16));
+                    c.dh[(size_t)(c.g * 64 + (col0 >> 2) + j4) * TM + r] = make_uint2(dh_pack2(cd[0], cd[1]), dh_pack2(cd[2], cd[3]));
                 }
             }
             if (fwd3 && c16 == 3 && c.cq >= 1) {
