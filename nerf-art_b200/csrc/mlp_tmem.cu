@@ -617,7 +617,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
                     for (int i = 0; i < 4; ++i) {
                         const int j = 4 * j4 + i;
                         cd[i] = dh_code(z16[j], t[j]);
-                        if (fwd3 && col0 + j >= SKIP_H) cd[i] = 0u;          // decodes to 0
+                        // skip-connection columns (k >= 217) carry no softplus: their code decodes to 0.  The test is on the pass
+                        // (warp-uniform, one branch) before it is on the column: in the merged kind of the training programs `fwd3` is
+                        // a run-time value and a per-element test costs 4 % of the forward half (profiles/r4b_split_program.md)
+                        if (KIND == K_FWD3) { if (col0 + j >= SKIP_H) cd[i] = 0u; }
+                    }
+                    if (KIND == K_FWDX && fwd3 && c16 == 3 && c.cq >= 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (col0 + 4 * j4 + i >= SKIP_H) cd[i] = 0u;
                     }
                     c.dh[(size_t)(c.g * 64 + (col0 >> 2) + j4) * TM + r] = make_uint2(dh_pack2(cd[0], cd[1]), dh_pack2(cd[2], cd[3]));
                 }
@@ -680,9 +687,14 @@ __device__ __forceinline__ void epi_gemm(const EpiCtx& c, const unsigned t_d, fl
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int k = col0 + 4 * j4 + i;
-                    if (bwd4 && k >= SKIP_H) c.misc()[(k - SKIP_H) * TM + r] = acc[4 * j4 + i] * us;      // embedding branch of the skip
+                    if (KIND == K_BWD4) { if (k >= SKIP_H) c.misc()[(k - SKIP_H) * TM + r] = acc[4 * j4 + i] * us; }      // embedding branch of the skip
                     o[4 * j4 + i] = acc[4 * j4 + i] * us16 * dd[i];
                 }
+            }
+            if (KIND == K_BWDX && bwd4 && c16 == 3 && c.cq >= 1) {
+                // (merged kind: the same stores behind ONE warp-uniform test; columns >= 217 lie in pass 3 of column quarters 1..3)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int k = col0 + j; if (k >= SKIP_H) c.misc()[(k - SKIP_H) * TM + r] = acc[j] * us; }
             }
             if (ST) { stash16(c, ST_G + 15 - c.g, col0, o, 1.f / ACT_SCALE); }
         } else if (KIND == K_BWD0) {
