@@ -313,6 +313,8 @@ def main():
     ap.add_argument('--workload', default='render', choices=['render', 'train'],
                     help="'render' (default): BASELINE configs[1]; 'train': the fine-tune step, see bench_train.py")
     ap.add_argument('--style', default='clip', choices=['clip', 'mse'], help='--workload train: style loss (see bench_train.py)')
+    ap.add_argument('--framework', default='volsdf', choices=['volsdf', 'neus'],
+                    help="--workload train: 'neus' = BASELINE configs[2] (NeuS fine-tune step: radiance net frozen, 64+64 samples)")
     ap.add_argument('--config', type=int, default=2, choices=[2, 4],
                     help='BASELINE.json configs[] entry: 2 = VolSDF 480x270, 128 samples (the metric, default); 4 = 960x540, 256 samples (8-GPU config)')
     args = ap.parse_args()

@@ -71,10 +71,12 @@ def main(args):
         return
     import nerfart_b200
     import bench as B
-    from helpers import make_volsdf
+    from helpers import make_volsdf, make_neus
     import fixtures as fx
-    from nerfart_b200.models.frameworks import volsdf as pv
+    from nerfart_b200.models.frameworks import volsdf as pv, neus as pn
     import torch.distributed as dist
+    neus = getattr(args, 'framework', 'volsdf') == 'neus'
+    P = 128 if neus else N_SAMPLES + N_IMPORTANCE                  # NeuS: configs/neus_fangzhou_vangogh.yaml geometry, 64 + 64 samples
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     saved_stdout = None
@@ -83,7 +85,7 @@ def main(args):
         dist.init_process_group('nccl', device_id=dev); dist.barrier()
     if args.precision == 'auto':
         args.precision = nerfart_b200.default_precision()
-    model = make_volsdf(0.1, 0.0, device=dev).train()
+    model = (make_neus(0.05, 0.0, device=dev) if neus else make_volsdf(0.1, 0.0, device=dev)).train()
     model.engine().precision = args.precision
     n_rays = H * W
     target = torch.full((1, n_rays, 3), 0.25)
@@ -108,21 +110,26 @@ def main(args):
             text(s_, True)
     else:
         loss_dict = {'clip': lambda gt, s, pred, t: ((pred - gt) ** 2 * wts).mean(), 'perceptual': None, 'contrastive': zero, 'patchnce': zero}
-    trainer = pv.Trainer(model, is_finetune=True, target_hw=[H, W], loss_dict=loss_dict)
+    trainer = (pn if neus else pv).Trainer(model, is_finetune=True, target_hw=[H, W], loss_dict=loss_dict)
     trainer.neg_texts = [f'negative prompt {i}' for i in range(40)]
     targs = _A(training=_A(is_finetune=True), data=_A(downscale=2), model=_A(radiance=_A(use_view_dirs=True)),
                finetune=_A(use_eikonal=True, w_eikonal=0.1, w_clip=1.0, w_perceptual=2.0, w_contrastive=0.2, w_patchnce=0.1,
                            src_text='photo', target_text='painting'))
     c2w, K = fx.closed_form_camera(H, W)
+    if neus:
+        c2w = c2w.clone(); c2w[2, 3] = -0.9                                      # inside NeuS' unit bounding sphere
+        kw = dict(batched=True, perturb=True, white_bkgd=False, upsample_algo='official_solution', N_upsample_iters=4, N_outside=0,
+                  obj_bounding_radius=1.0, H=H, W=W, N_samples=64, N_importance=64)
+    else:
+        kw = dict(near=0.0, far=6.0, batched=True, perturb=True, white_bkgd=False, max_upsample_steps=6, use_nerfplusplus=False,
+                  obj_bounding_radius=3.0, H=H, W=W, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
     c2w_pin, K_pin, tgt_pin = c2w[None].pin_memory(), K[None].pin_memory(), target.pin_memory()
-    kw = dict(near=0.0, far=6.0, batched=True, perturb=True, white_bkgd=False, max_upsample_steps=6, use_nerfplusplus=False,
-              obj_bounding_radius=3.0, H=H, W=W, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
     opt = torch.optim.Adam(model.parameters(), lr=1e-6)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     # phase timers around the engine calls of pass 2
     eng = model.engine()
     phases = {'render_bwd': [], 'patch_fwd': []}
-    orig_bwd, orig_fwd = eng.render_bwd, eng.volsdf_render
+    orig_bwd, orig_fwd = eng.render_bwd, (eng.neus_render if neus else eng.volsdf_render)
 
     def timed_call(name, fn):
         def wrap(*a, **k):
@@ -132,7 +139,10 @@ def main(args):
             return r
         return wrap
     eng.render_bwd = timed_call('render_bwd', orig_bwd)
-    eng.volsdf_render = timed_call('patch_fwd', orig_fwd)
+    if neus:
+        eng.neus_render = timed_call('patch_fwd', orig_fwd)
+    else:
+        eng.volsdf_render = timed_call('patch_fwd', orig_fwd)
     from nerfart_b200.models.frameworks import _finetune
     phases['style'] = []
     style_host = []
@@ -193,17 +203,21 @@ def main(args):
         pk, kind = B.peaks()
         n_local = n_rays if world == 1 else None
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not neus:
             v, dt = cpu_baseline_train()
             cpu = {'value': v, 'unit': 'samples/s', 'cores': os.cpu_count(), 'kind': 'port',
                    'sample': f'pass 2 only on 48 strided rays x 192 samples ({dt:.1f} s), numpy float32 port (render + closed-form backward)'}
-        ach = n_rays * P * F_BWD / max(t_bwd, 1e-9) / 1e12 / world
-        line = {'metric': 'MLP samples/sec (VolSDF 480x270x128 fine-tune step)', 'value': n_rays * P * args.steps / t, 'unit': 'samples/s',
+        # NeuS (radiance net frozen): P points carry trunk + second-order sweep (data + weight gradients), P - 1 midpoints the same
+        # plus the radiance net's backward-data GEMMs
+        flop_ray = (P * 2 * (2 * 524544 + 2 * 459008) + (P - 1) * 2 * (265216 + 2 * 524544 + 2 * 459008)) if neus else P * F_BWD
+        ach = n_rays * flop_ray / max(t_bwd, 1e-9) / 1e12 / world
+        line = {'metric': 'MLP samples/sec (NeuS 480x270x64+64 fine-tune step)' if neus else 'MLP samples/sec (VolSDF 480x270x128 fine-tune step)', 'value': n_rays * P * args.steps / t, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': ('backward: forward + backward-data GEMMs of a patch in one tcgen05 launch (f16 operands, f32 accumulate), weight-gradient GEMMs tcgen05 f16/bf16 operands from a 16-bit stash, f32 accumulate; ' if args.precision != 'fp32' else 'backward: f32 recompute + tf32 mma.sync; ') + 'CLIP tower linear layers tcgen05 tf32; forward: ' + args.precision, 'data': 'synthetic',
-                'config': {'workload': f'VolSDF fine-tune step {H}x{W} ({n_rays} rays), 128+64 samples/ray, pass 1 + pass 2 in 108 patches of '
-                                       '1200 rays, eikonal on, perturb on, style=' + style + (' (3 CLIP losses, seeded random ViT-B/32 weights + stand-in text features, no VGG)' if style == 'clip' else ' (weighted MSE)') + ', Adam step',
+                'dtype': ('backward: the patch forward render leaves the activations (16-bit stash), the 20 backward-data GEMMs per tile in one tcgen05 launch (f16 operands, f32 accumulate), weight-gradient GEMMs tcgen05 bf16 operands from the stash, f32 accumulate; ' if args.precision != 'fp32' else 'backward: f32 recompute + tf32 mma.sync; ') + 'CLIP tower linear layers tcgen05 tf32; forward: ' + args.precision, 'data': 'synthetic',
+                'config': {'workload': (f'NeuS fine-tune step {H}x{W} ({n_rays} rays), 64+64 samples/ray (sdf / nabla at 128 points + radiance at 127 '
+                                        'midpoints), radiance net frozen, ' if neus else f'VolSDF fine-tune step {H}x{W} ({n_rays} rays), 128+64 samples/ray, ') +
+                                       'pass 1 + pass 2 in 108 patches of 1200 rays, eikonal on, perturb on, style=' + style + (' (3 CLIP losses, seeded random ViT-B/32 weights + stand-in text features, no VGG)' if style == 'clip' else ' (weighted MSE)') + ', Adam step',
                            'parallelism': f'patch round-robin x{world}' + (' + NCCL all-reduce of the packed gradient' if world > 1 else ''),
                            'l2': 'per-patch stash (5.0 GB) >> 126 MB L2; no explicit flush'},
                 'phases_ms': {'pass1_render': 1e3 * t_p1, 'pass2_patch_forward': 1e3 * t_pfwd, 'pass2_backward': 1e3 * t_bwd,
@@ -215,10 +229,11 @@ def main(args):
                         'h2d_bytes_per_step': 2 * 64 + n_rays * 12, 'd2h_bytes_per_step': 4,
                         'note': 'the step is timed through Trainer.forward with pinned-host camera / target image in and the loss out'},
                 'gpu_launches': int(launches), 'clocks': clk,
-                'roofline': {'bound': 'tensor', 'kernel': 'tm::mlp_tmem_kernel<BW> + wf::wgrad_f16_kernel (pass-2 backward)',
+                'roofline': {'bound': 'tensor', 'kernel': 'tm::mlp_tmem_kernel<1,1,1,*> (backward half) + wf::wgrad_f16_kernel (pass-2 backward)',
                              'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops'], 'traffic': None,
-                             'flop_per_sample': F_BWD, 'note': 'algorithmic backward FLOPs / time inside render_bwd; the 41 tile GEMMs of a patch (forward re-evaluation + backward-data) run '
-                             'on tcgen05 in one launch, all weight-gradient GEMMs on tcgen05 kind::f16 fed by TMA from the 16-bit stash', 'peak_kind': f'{kind} bf16 burst'},
+                             'flop_per_sample': flop_ray / P, 'note': 'algorithmic backward FLOPs / time inside render_bwd (compositing backward + backward half of the split training program '
+                             '+ weight gradients); NA_BW_SPLIT=0: the launch also re-evaluates the forward pass (41 tile GEMMs); all weight-gradient GEMMs on '
+                             'tcgen05 kind::f16 fed by TMA from the 16-bit stash', 'split_program': os.environ.get('NA_BW_SPLIT', '1') != '0' and args.precision != 'fp32', 'peak_kind': f'{kind} bf16 burst'},
                 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
